@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerate tests/golden/*.npz from the real reference.
+
+Run in the authoring container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+For each case it runs the UNMODIFIED reference ``aaerec.aae.AdversarialAutoEncoder.fit``
+/ ``.predict`` and ``aaerec.evaluation.remove_non_missing`` / ``argtopk`` on seeded
+inputs and stores inputs, initial weights, per-step losses, final weights, predictions
+and rankings.  ``tests/test_oracle.py`` pins ``oracle/aae_oracle.py`` against these
+files; the GPU parity tests compare the CUDA path with the same files.
+"""
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "aae-recommender_b200"))
+
+from oracle.reference_loader import load_reference  # noqa: E402
+from aaerec_b200.synth import synth_sets  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _state(model):
+    out = {}
+    for pre, mod in (("enc", model.enc), ("dec", model.dec), ("disc", model.disc)):
+        for k, v in mod.state_dict().items():
+            out[pre + "." + k] = v.detach().cpu().numpy().copy()
+    return out
+
+
+def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0, mean_len=6,
+             store_weights=True, k=10):
+    aae = ref.aae
+    X = synth_sets(n, V, mean_len, min_len=2, seed=data_seed)
+    conditions = None
+    cond_data = None
+    cond = None
+    if cond_dim:
+        cond = (np.random.RandomState(data_seed + 1).randn(n, cond_dim) * 0.5).astype(np.float32)
+
+        class MatrixCondition(ref.condition.ConcatenationBasedConditioning):
+            """precomputed float rows, concatenated on the code (condition.py:300-316, 363-369)"""
+
+            def __init__(self, dim):
+                self._d = dim
+
+            def encode(self, inputs):
+                return torch.as_tensor(inputs, dtype=torch.float32)
+
+            def size_increment(self):
+                return self._d
+        conditions = ref.condition.ConditionList([("title", MatrixCondition(cond_dim))])
+        cond_data = [cond]
+
+    losses = []
+    orig = {k_: getattr(aae.AdversarialAutoEncoder, k_) for k_ in ("ae_step", "disc_step", "gen_step")}
+
+    def wrap(fn_name):
+        fn = orig[fn_name]
+
+        def inner(self, *a, **kw):
+            val = fn(self, *a, **kw)
+            losses.append(val)
+            return val
+        return inner
+    for k_ in orig:
+        setattr(aae.AdversarialAutoEncoder, k_, wrap(k_))
+    init = {}
+    try:
+        torch.manual_seed(42)     # aae.py:27 executes this at import; redo it per case
+        np.random.seed(42)
+        model = aae.AdversarialAutoEncoder(n_hidden=H, n_code=C, batch_size=B, n_epochs=epochs,
+                                           dropout=dropout, conditions=conditions, verbose=False)
+        # capture the initial weights: replay the same construction order under the same seed
+        from oracle.aae_oracle import init_params
+        init = {k_: v.numpy().copy() for k_, v in init_params(V, H, C, C + cond_dim, seed=42).items()}
+        torch.manual_seed(42)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.fit(X, condition_data=cond_data)
+        final = _state(model)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pred = model.predict(X[:40], condition_data=[cond[:40]] if cond_dim else None)
+    finally:
+        for k_, fn in orig.items():
+            setattr(aae.AdversarialAutoEncoder, k_, fn)
+    Xd = X[:40].toarray()
+    masked = ref.evaluation.remove_non_missing(pred, Xd, copy=True)
+    topk = ref.evaluation.argtopk(masked, k)[1]
+    out = dict(
+        n=n, V=V, H=H, C=C, B=B, epochs=epochs, dropout=np.asarray(dropout, dtype=np.float64),
+        cond_dim=cond_dim, k=k,
+        indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32),
+        losses=np.asarray(losses, dtype=np.float64).reshape(-1, 3),
+        pred=pred.astype(np.float32), masked=masked.astype(np.float32), topk=topk.astype(np.int64),
+    )
+    if cond_dim:
+        out["cond"] = cond
+    if store_weights:
+        for k_, v in init.items():
+            out["init/" + k_] = v
+        for k_, v in final.items():
+            out["final/" + k_] = v
+    else:
+        for k_, v in final.items():
+            out["abssum/" + k_] = np.float64(np.abs(v.astype(np.float64)).sum())
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "steps", len(losses) // 3, "first", out["losses"][0], "last", out["losses"][-1])
+    return out
+
+
+def ranking_case(ref):
+    rs = np.random.RandomState(7)
+    Y = rs.rand(9, 64).astype(np.float32)
+    Y[3, :] = 0.25                 # constant row: zero range
+    Y[4, 10:20] = Y[4, 5]          # ties
+    Xk = (rs.rand(9, 64) < 0.1).astype(np.float32)
+    masked = ref.evaluation.remove_non_missing(Y, Xk, copy=True)
+    cols5 = ref.evaluation.argtopk(masked, 5)[1]
+    cols_all = ref.evaluation.argtopk(masked, None)[1]
+    np.savez_compressed(os.path.join(GOLDEN, "ranking.npz"), Y=Y, Xk=Xk, masked=masked,
+                        top5=cols5.astype(np.int64), full=cols_all.astype(np.int64))
+    print("ranking ok")
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = load_reference()
+    run_case(ref, "aae_small_dropout", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2))
+    run_case(ref, "aae_small_nodrop", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(0, 0))
+    run_case(ref, "aae_small_cond", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2), cond_dim=7)
+    run_case(ref, "aae_h100_dropout", n=96, V=520, H=100, C=50, B=32, epochs=2, dropout=(.2, .2), mean_len=8)
+    # SURVEY 8(c) indicative configuration (losses + |W| sums only, weights rebuilt from the seed)
+    run_case(ref, "aae_survey_nodrop", n=300, V=1000, H=100, C=50, B=100, epochs=1, dropout=(0, 0),
+             mean_len=8, store_weights=False)
+    run_case(ref, "aae_survey_dropout", n=300, V=1000, H=100, C=50, B=100, epochs=1, dropout=(.2, .2),
+             mean_len=8, store_weights=False)
+    ranking_case(ref)
+
+
+if __name__ == "__main__":
+    main()

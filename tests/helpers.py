@@ -1,0 +1,58 @@
+"""Shared helpers for the tests: golden loading and the oracle replay of a golden case."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+AAE_CASES = ["aae_small_dropout", "aae_small_nodrop", "aae_small_cond", "aae_h100_dropout",
+             "aae_survey_nodrop", "aae_survey_dropout"]
+
+
+def load_case(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g["X"] = sp.csr_matrix((np.ones(len(g["indices"]), dtype=np.float32), g["indices"], g["indptr"]),
+                           shape=(int(g["n"]), int(g["V"])))
+    g["dropout"] = tuple(float(x) for x in g["dropout"])
+    for k in ("n", "V", "H", "C", "B", "epochs", "cond_dim", "k"):
+        g[k] = int(g[k])
+    return g
+
+
+def group(g, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in g.items() if k.startswith(prefix + "/")}
+
+
+def oracle_replay(g, record_rng=False):
+    """Run oracle/aae_oracle.py over a golden case exactly as the reference's fit loop does
+    (aae.py:768-837): seed, build, shuffle per epoch, slice batches, three phases per batch."""
+    from oracle import aae_oracle as O
+    V, H, C, B = g["V"], g["H"], g["C"], g["B"]
+    cond = g.get("cond")
+    torch.manual_seed(42)
+    np.random.seed(42)
+    params = O.init_params(V, H, C, C + g["cond_dim"], seed=None)
+    model = O.OracleAAE(params, n_code=C)
+    X = g["X"]
+    losses, rngs, batches = [], [], []
+    for _ in range(g["epochs"]):
+        perm = O.fit_epoch_order(X.shape[0])
+        Xs = X[perm]
+        cs = cond[perm] if cond is not None else None
+        for s in range(0, X.shape[0], B):
+            xb = Xs[s:s + B]
+            cb = [cs[s:s + B]] if cs is not None else None
+            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"])
+            losses.append(model.partial_fit(xb.toarray(), cb, rng))
+            if record_rng:
+                rngs.append(rng)
+                batches.append((xb, cb))
+    return model, np.asarray(losses), rngs, batches
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
