@@ -1,0 +1,416 @@
+"""B200-native Adversarial Autoencoder recommender behind the reference's own API.
+
+Mirrors ``aaerec/aae.py``: ``AdversarialAutoEncoder`` (589-870; same constructor kwargs and
+defaults, ``fit`` / ``partial_fit`` / ``predict`` / ``eval`` / ``train`` / ``__str__``) and
+``AAERecommender`` (873-977; ``train(training_set)`` / ``predict(test_set)``), so that
+``main.py`` / ``eval/*.py`` can construct it unchanged.  All numerics run in the CUDA kernels of
+``libaae_b200.so`` through :class:`aaerec_b200.engine.AAEEngine`; there is no PyTorch/CPU fallback.
+
+Additions that are not in the reference (defaults keep the reference's behaviour):
+  ``predict_topk(X, k)``  fused predict + remove_non_missing + argtopk without the dense [n,V] matrix
+  ``rng='native'|'oracle'``  in-kernel Philox dropout / prior sampling, or the reference's CPU-generator
+                           draws in the reference's order (bit-identical masks; used by parity tests)
+  ``impl``  decoder-output kernel: 'simt' (exact fp32 CUDA cores), 'tc' (tcgen05 3xTF32), 'tf32'
+  ``device`` / ``rank`` / ``world``  item-sharded multi-GPU
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from .base import Recommender
+from .condition import _check_conditions, ConditionList
+from .engine import AAEEngine
+
+torch.manual_seed(42)   # aae.py:27 -- the reference seeds the CPU generator at import
+TINY = 1e-12
+STATUS_FORMAT = "[ R: {:.4f} | D: {:.4f} | G: {:.4f} ]"
+
+
+def log_losses(*losses):
+    print('\r' + STATUS_FORMAT.format(*losses), end='', flush=True)
+
+
+PRIOR_ACTIVATIONS = {'categorical': 'softmax', 'bernoulli': 'sigmoid', 'gauss': 'linear'}
+SUPPORTED_OPTIMIZERS = {'adam'}   # the reference's table also has 'sgd' (aae.py:216-219)
+
+
+def _init_linear_params(n_items, n_hidden, n_code, code_size):
+    """Same construction order and stock nn.Linear init as aae.py:782-792, on the CPU generator."""
+    out = {}
+    for name, fin, fout in (
+            ("enc.lin1", n_items, n_hidden), ("enc.lin2", n_hidden, n_hidden), ("enc.lin3", n_hidden, n_code),
+            ("dec.lin1", code_size, n_hidden), ("dec.lin2", n_hidden, n_hidden), ("dec.lin3", n_hidden, n_items),
+            ("disc.lin1", n_code, n_hidden), ("disc.lin2", n_hidden, n_hidden), ("disc.lin3", n_hidden, 1)):
+        lin = torch.nn.Linear(fin, fout)
+        out[name + ".weight"] = lin.weight.detach()
+        out[name + ".bias"] = lin.bias.detach()
+    return out
+
+
+def _draw_step_rng(B, n_hidden, n_code, dropout, prior_scale):
+    """The reference's draws for one partial_fit, same calls in the same order on torch's global CPU
+    generator: nn.Dropout == x * empty_like(x).bernoulli_(1-p).div_(1-p); p == 0 draws
+    nothing; z_real = torch.randn (aae.py:716)."""
+    p1, p2 = dropout
+
+    def mask(p):
+        if p == 0:
+            return None
+        return torch.empty((B, n_hidden), dtype=torch.float32).bernoulli_(1 - p).div_(1 - p)
+
+    def pair():
+        return (mask(p1), mask(p2))
+    r = {"ae_enc": pair(), "ae_dec": pair()}
+    z = torch.randn((B, n_code))
+    if prior_scale is not None:
+        z = z * prior_scale
+    r["z_real"] = z
+    r["disc_real"] = pair()
+    r["disc_fake"] = pair()
+    r["gen_enc"] = pair()
+    r["gen_disc"] = pair()
+    return r
+
+
+class _LinearView(object):
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+
+class _ModuleView(object):
+    """Read-only view of a module's weights in the reference's layout (``.lin1.weight`` ...)."""
+
+    def __init__(self, sd, prefix):
+        self._sd = {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+        for i in (1, 2, 3):
+            setattr(self, "lin%d" % i, _LinearView(self._sd["lin%d.weight" % i], self._sd["lin%d.bias" % i]))
+
+    def state_dict(self):
+        return dict(self._sd)
+
+
+class AdversarialAutoEncoder(object):
+    """ Adversarial Autoencoder (aae.py:589) """
+
+    def __init__(self,
+                 n_hidden=100,
+                 n_code=50,
+                 gen_lr=0.001,
+                 reg_lr=0.001,
+                 prior='gauss',
+                 prior_scale=None,
+                 batch_size=100,
+                 n_epochs=500,
+                 optimizer='adam',
+                 normalize_inputs=True,
+                 activation='ReLU',
+                 dropout=(.2, .2),
+                 conditions=None,
+                 verbose=True,
+                 rng='native',
+                 impl='auto',
+                 device=None,
+                 rank=0,
+                 world=1,
+                 group=None,
+                 seed=0,
+                 use_graph=True):
+        self.prior = prior.lower()
+        self.prior_scale = prior_scale
+        self.encoder_activation = PRIOR_ACTIVATIONS[self.prior]   # KeyError on unknown prior, as aae.py:612-613
+        self.optimizer = optimizer.lower()
+        self.n_hidden = n_hidden
+        self.n_code = n_code
+        self.gen_lr, self.reg_lr = gen_lr, reg_lr
+        self.batch_size = batch_size
+        self.verbose = verbose
+        self.n_epochs = n_epochs
+        self.normalize_inputs = normalize_inputs
+        self.dropout = dropout
+        self.activation = activation
+        self.conditions = conditions
+        self.rng = rng
+        self.impl = impl
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.seed = seed
+        self.use_graph = use_graph
+        self.engine = None
+        self._mode_train = True
+        self.record_losses = False   # True: keep every step's (R, D, G) in .loss_history (forces a sync per step)
+        # supported envelope; everything else fails loudly, there is no fallback path
+        if self.prior != 'gauss':
+            raise NotImplementedError("accelerated path supports prior='gauss' only (got %r)" % prior)
+        if activation != 'ReLU':
+            raise NotImplementedError("accelerated path supports activation='ReLU' only (got %r)" % activation)
+        if self.optimizer not in SUPPORTED_OPTIMIZERS:
+            if self.optimizer == 'sgd':
+                raise NotImplementedError("accelerated path supports optimizer='adam' only")
+            raise KeyError(optimizer)
+        if rng not in ('native', 'oracle'):
+            raise ValueError("rng must be 'native' or 'oracle'")
+
+    def __str__(self):
+        desc = "Adversarial Autoencoder"
+        n_h, n_c = self.n_hidden, self.n_code
+        gen, reg = self.gen_lr, self.reg_lr
+        desc += " ({}, {}, {}, {}, {})".format(n_h, n_h, n_c, n_h, n_h)
+        desc += " optimized by " + self.optimizer
+        desc += " with learning rates Gen, Reg = {}, {}".format(gen, reg)
+        desc += ", using a batch size of {}".format(self.batch_size)
+        desc += "\nMatching the {} distribution".format(self.prior)
+        desc += " by {} activation.".format(self.encoder_activation)
+        if self.conditions:
+            desc += "\nConditioned on " + ', '.join(self.conditions.keys())
+        return desc
+
+    # -- mode switches (dropout is decided per kernel call; kept for API compatibility, aae.py:636-660)
+    def eval(self):
+        self._mode_train = False
+        if self.conditions:
+            self.conditions.eval()
+
+    def train(self):
+        self._mode_train = True
+        if self.conditions:
+            self.conditions.train()
+
+    def zero_grad(self):
+        """Gradients never persist between kernels; nothing to clear."""
+
+    def ae_step(self, batch, condition_data=None):
+        raise NotImplementedError("the three phases are fused into partial_fit on the device; "
+                                  "call partial_fit and read .last_losses")
+
+    disc_step = gen_step = ae_step
+
+    # -- weights in the reference's layout
+    @property
+    def enc(self):
+        return _ModuleView(self.engine.state_dict(), "enc") if self.engine else None
+
+    @property
+    def dec(self):
+        return _ModuleView(self.engine.state_dict(), "dec") if self.engine else None
+
+    @property
+    def disc(self):
+        return _ModuleView(self.engine.state_dict(), "disc") if self.engine else None
+
+    def state_dict(self):
+        return self.engine.state_dict()
+
+    # -- helpers
+    def _build(self, n_items, code_size, params=None):
+        if params is None:
+            params = _init_linear_params(n_items, self.n_hidden, self.n_code, code_size)
+        self.engine = AAEEngine(n_items, self.n_hidden, self.n_code, cond_dim=code_size - self.n_code,
+                                gen_lr=self.gen_lr, reg_lr=self.reg_lr, dropout=self.dropout,
+                                prior_scale=self.prior_scale, normalize_inputs=self.normalize_inputs,
+                                device=self.device, rank=self.rank, world=self.world, group=self.group,
+                                impl=self.impl, seed=self.seed, max_batch=self.batch_size,
+                                use_graph=self.use_graph)
+        self.engine.load_params(params)
+        self.last_losses = None
+
+    @staticmethod
+    def _csr_batch(X):
+        """Any 2-D batch (dense ndarray as the reference passes to partial_fit, or scipy sparse) ->
+        (indptr int32, indices int32) with sorted unique columns.  Values must be binary: the
+        reference's BCE rejects targets outside [0,1]."""
+        if not sp.issparse(X):
+            X = sp.csr_matrix(np.asarray(X))
+        X = X.tocsr()
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        if X.nnz and (X.data.max() > 1 or X.data.min() < 0):
+            raise RuntimeError("all elements of target should be between 0 and 1")
+        if X.nnz and (X.data == 0).any():
+            X = X.copy()
+            X.eliminate_zeros()
+        return X.indptr.astype(np.int32, copy=False), X.indices.astype(np.int32, copy=False)
+
+    def _cond_rows(self, condition_data):
+        if not self.conditions:
+            return None
+        return self.conditions.fused_rows(condition_data)
+
+    # -- training
+    def partial_fit(self, X, y=None, condition_data=None, step=None):
+        """ Performs reconstrction, discimination, generator training steps (aae.py:745-766) """
+        if y is not None:
+            raise NotImplementedError("(Semi-)supervised usage not supported")
+        use_condition = _check_conditions(self.conditions, condition_data)
+        if self.engine is None:
+            code_size = self.n_code + (self.conditions.size_increment() if use_condition else 0)
+            self._build(X.shape[1], code_size)
+        indptr, indices = self._csr_batch(X)
+        self._partial_fit_csr(indptr, indices, self._cond_rows(condition_data) if use_condition else None)
+        if self.verbose:
+            log_losses(*self.losses())
+        return self
+
+    def _partial_fit_csr(self, indptr, indices, cond_rows):
+        eng = self.engine
+        self.train()
+        B, _ = eng.upload_csr(indptr, indices, cond_rows)
+        injected = False
+        if self.rng == 'oracle':
+            draws = _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale)
+            eng.set_rng_draws(B, draws)
+            injected = True
+        eng.train_step(B, injected=injected)
+
+    def losses(self):
+        """(recon, disc, gen) losses of the last step -- a device->host read (synchronises)."""
+        self.last_losses = tuple(float(x) for x in self.engine.losses.cpu().tolist())
+        return self.last_losses
+
+    def fit(self, X, y=None, condition_data=None):
+        """aae.py:768-837: build, then per epoch shuffle and walk the batches."""
+        if y is not None:
+            raise NotImplementedError("(Semi-)supervised usage not supported")
+        use_condition = _check_conditions(self.conditions, condition_data)
+        if use_condition:
+            code_size = self.n_code + self.conditions.size_increment()
+            print("Using condition, code size:", code_size)
+        else:
+            code_size = self.n_code
+            print("Not using condition, code size:", code_size)
+        X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        if X.nnz and (X.data.max() > 1 or X.data.min() < 0):
+            raise RuntimeError("all elements of target should be between 0 and 1")
+        self._build(X.shape[1], code_size)
+        cond_all = self._cond_rows(condition_data) if use_condition else None
+        n = X.shape[0]
+        self.loss_history = []
+        step = 0
+        for epoch in range(self.n_epochs):
+            if self.verbose:
+                print("Epoch", epoch + 1)
+            # sklearn.utils.shuffle(X, *condition_data) with random_state=None permutes arange(n) with the
+            # global numpy generator (aae.py:815-817); same stream consumption here.
+            perm = np.arange(n)
+            np.random.shuffle(perm)
+            X_shuf = X[perm]
+            c_shuf = cond_all[perm] if cond_all is not None else None
+            indptr = X_shuf.indptr
+            indices = X_shuf.indices.astype(np.int32, copy=False)
+            for start in range(0, n, self.batch_size):
+                end = min(start + self.batch_size, n)
+                lo, hi = int(indptr[start]), int(indptr[end])
+                ip = (indptr[start:end + 1] - lo).astype(np.int32)
+                self._partial_fit_csr(ip, indices[lo:hi], c_shuf[start:end] if c_shuf is not None else None)
+                if self.verbose or self.record_losses:
+                    cur = self.losses()
+                    if self.record_losses:
+                        self.loss_history.append(cur)
+                    if self.verbose:
+                        log_losses(*cur)
+                step += 1
+            if self.verbose:
+                print()
+        return self
+
+    # -- prediction
+    def _iter_batches(self, X, condition_data):
+        use_condition = _check_conditions(self.conditions, condition_data)
+        self.eval()
+        X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        cond_all = self._cond_rows(condition_data) if use_condition else None
+        n = X.shape[0]
+        indptr = X.indptr
+        indices = X.indices.astype(np.int32, copy=False)
+        for start in range(0, n, self.batch_size):
+            end = min(start + self.batch_size, n)
+            lo, hi = int(indptr[start]), int(indptr[end])
+            ip = (indptr[start:end + 1] - lo).astype(np.int32)
+            B, _ = self.engine.upload_csr(ip, indices[lo:hi], cond_all[start:end] if cond_all is not None else None)
+            yield start, end, B
+
+    def predict(self, X, condition_data=None):
+        """aae.py:840-870: dense float32 [n, n_items] sigmoid probabilities (API-compatible; for
+        million-item vocabularies use predict_topk)."""
+        eng = self.engine
+        n = X.shape[0]
+        out = np.empty((n, eng.V), dtype=np.float32)
+        dev = torch.empty(self.batch_size, eng.Vloc, dtype=torch.float32, device=eng.dev)
+        for start, end, B in self._iter_batches(X, condition_data):
+            eng.scores(B, dev, apply_sigmoid=True)
+            if eng.world == 1:
+                out[start:end] = dev[:B].cpu().numpy()
+            else:
+                out[start:end] = eng._gather_items(dev[:B].t().contiguous()).t().cpu().numpy()
+        return out
+
+    def predict_topk(self, X, k, condition_data=None, mask_known=True, return_scores=False):
+        """Top-k unknown items per row = argtopk(remove_non_missing(predict(X), X), k)[1]
+        (evaluation.py:183-199, 20-58) without materialising [n, n_items] on the host."""
+        eng = self.engine
+        n = X.shape[0]
+        kk = min(k, eng.V)
+        idx = np.empty((n, kk), dtype=np.int64)
+        val = np.empty((n, kk), dtype=np.float32) if return_scores else None
+        scratch = torch.empty(self.batch_size, eng.Vloc, dtype=torch.float32, device=eng.dev)
+        for start, end, B in self._iter_batches(X, condition_data):
+            i, v = eng.topk(B, kk, scratch=scratch, mask_known=mask_known)
+            idx[start:end] = i.cpu().numpy()
+            if return_scores:
+                val[start:end] = v.cpu().numpy()
+        return (idx, val) if return_scores else idx
+
+
+class AAERecommender(Recommender):
+    """Adversarially Regularized Recommender (aae.py:873-977)."""
+
+    def __init__(self, adversarial=True, conditions=None, **kwargs):
+        super().__init__()
+        self.verbose = kwargs.get('verbose', True)
+        self.conditions = conditions
+        self.model_params = kwargs
+        self.adversarial = adversarial
+        self.model = None
+
+    def __str__(self):
+        desc = "Adversarial Autoencoder" if self.adversarial else "Autoencoder"
+        if self.conditions:
+            desc += " conditioned on: " + ', '.join(self.conditions.keys())
+        desc += '\nModel Params: ' + str(self.model_params)
+        return desc
+
+    def _condition_data(self, bags, fit):
+        if not self.conditions:
+            return None
+        raw = bags.get_attributes(self.conditions.keys())
+        return self.conditions.fit_transform(raw) if fit else self.conditions.transform(raw)
+
+    def train(self, training_set):
+        print(self)
+        X = training_set.tocsr()
+        if self.conditions:
+            print("Fit transforming conditions:", self.conditions)
+        else:
+            print("Start of training, not using condition...", self.conditions)
+        condition_data = self._condition_data(training_set, fit=True)
+        if self.adversarial:
+            self.model = AdversarialAutoEncoder(conditions=self.conditions, **self.model_params)
+        else:
+            raise NotImplementedError("adversarial=False (plain AutoEncoder, aae.py:221-458) is not on the "
+                                      "accelerated path yet (SURVEY 8(f) rank 1)")
+        print(self.model)
+        print(self.conditions)
+        self.model.fit(X, condition_data=condition_data)
+
+    def predict(self, test_set):
+        X = test_set.tocsr()
+        condition_data = self._condition_data(test_set, fit=False)
+        return self.model.predict(X, condition_data=condition_data)
+
+    def predict_topk(self, test_set, k, mask_known=True):
+        X = test_set.tocsr()
+        condition_data = self._condition_data(test_set, fit=False)
+        return self.model.predict_topk(X, k, condition_data=condition_data, mask_known=mask_known)

@@ -1,0 +1,447 @@
+"""Device-side state and step orchestration of the AAE hot path.
+
+``AAEEngine`` owns the weights, the four Adam states and the per-batch workspaces in HBM and
+enqueues the kernels of one ``partial_fit`` (reference: aaerec/aae.py:745-766 -> ae_step 676-711,
+disc_step 713-732, gen_step 734-743) and of ``predict`` (aae.py:840-870) through the C ABI in
+``include/aae_b200.h``.  PyTorch is used for memory, streams, CUDA graphs and (multi-GPU)
+``torch.distributed`` only -- every numeric op on the path is one of our kernels.
+
+HBM layout (fp32, row-major)
+  W1t  [Vloc,H]  enc.lin1.weight transposed (+ m1,v1 for enc_optim, m2,v2 for gen_optim)
+  Wd3  [Vloc,H]  dec.lin3.weight (+ m,v), bd3 [Vloc] (+ m,v)
+  enc/dec/disc   small layers packed in one block each (see aae_b200.h), with moment/grad blocks
+Item-sharded over ``world`` ranks: rank r owns items [v_begin, v_end); small layers replicated and
+computed redundantly (identical inputs and RNG on every rank), so the only exchanges are the
+all-reduce of h1pre partial sums and of (dh2, loss) -- SURVEY.md 8(e).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import call, ptr, AaeDims
+
+# Philox stream ids of the 12 dropout layers of one step, in the reference's draw order (A11)
+_DROP_ORDER = ("ae_e1", "ae_e2", "ae_d1", "ae_d2", "disc_r1", "disc_r2", "disc_f1", "disc_f2",
+               "gen_e1", "gen_e2", "gen_q1", "gen_q2")
+
+
+def shard_range(V, rank, world):
+    """Contiguous item range of ``rank``: ceil-divided so every rank but the last is equal."""
+    per = (V + world - 1) // world
+    lo = min(V, rank * per)
+    return lo, min(V, lo + per)
+
+
+def enc_block_sizes(H, C_):
+    return [("enc.lin1.bias", H), ("enc.lin2.weight", H * H), ("enc.lin2.bias", H),
+            ("enc.lin3.weight", C_ * H), ("enc.lin3.bias", C_)]
+
+
+def dec_block_sizes(H, Cp):
+    return [("dec.lin1.weight", H * Cp), ("dec.lin1.bias", H), ("dec.lin2.weight", H * H), ("dec.lin2.bias", H)]
+
+
+def disc_block_sizes(H, C_):
+    return [("disc.lin1.weight", H * C_), ("disc.lin1.bias", H), ("disc.lin2.weight", H * H),
+            ("disc.lin2.bias", H), ("disc.lin3.weight", H), ("disc.lin3.bias", 1)]
+
+
+class AAEEngine(object):
+    def __init__(self, n_items, n_hidden=100, n_code=50, cond_dim=0, gen_lr=1e-3, reg_lr=1e-3,
+                 dropout=(.2, .2), prior_scale=None, normalize_inputs=True, device=None,
+                 rank=0, world=1, group=None, impl="auto", seed=0, max_batch=128, max_nnz=None,
+                 use_graph=True, overlap_sweep=True):
+        N.require_device(0 if device is None else (torch.device(device).index or 0))
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.V, self.H, self.C, self.D = int(n_items), int(n_hidden), int(n_code), int(cond_dim)
+        self.Cp = self.C + self.D
+        self.gen_lr, self.reg_lr = float(gen_lr), float(reg_lr)
+        self.dropout = (float(dropout[0]), float(dropout[1]))
+        self.prior_scale = 1.0 if prior_scale is None else float(prior_scale)
+        self.normalize = 1 if normalize_inputs else 0
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.v_begin, self.v_end = shard_range(self.V, self.rank, self.world)
+        self.Vloc = self.v_end - self.v_begin
+        self.seed = int(seed)
+        self.use_graph = bool(use_graph) and self.world == 1
+        self.overlap_sweep = bool(overlap_sweep)
+        self.impl = self._pick_impl(impl)
+        self.steps_done = 0
+        self._launches_per_step = 0
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        H, Cc, Cp, Vl = self.H, self.C, self.Cp, max(self.Vloc, 1)
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.W1t, self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2 = (z(Vl, H) for _ in range(5))
+        self.Wd3, self.Wd3_m, self.Wd3_v = (z(Vl, H) for _ in range(3))
+        self.bd3, self.bd3_m, self.bd3_v = (z(Vl) for _ in range(3))
+        self.n_enc = sum(s for _, s in enc_block_sizes(H, Cc))
+        self.n_dec = sum(s for _, s in dec_block_sizes(H, Cp))
+        self.n_disc = sum(s for _, s in disc_block_sizes(H, Cc))
+        self.enc, self.enc_m1, self.enc_v1, self.enc_m2, self.enc_v2, self.g_enc = (z(self.n_enc) for _ in range(6))
+        self.dec, self.dec_m, self.dec_v, self.g_dec = (z(self.n_dec) for _ in range(4))
+        self.disc, self.disc_m, self.disc_v, self.g_disc = (z(self.n_disc) for _ in range(4))
+        self.state = torch.zeros(C.sizeof(N.StepState), dtype=torch.uint8, device=self.dev)
+        self.slot_of = torch.full((Vl,), -1, dtype=torch.int32, device=self.dev)
+        self.loss_sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self.losses = torch.zeros(3, **f32)
+        self._ws_B = 0
+        self._ws_nnz = 0
+        self._graphs = {}
+        self.side = torch.cuda.Stream(device=self.dev)
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
+        call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
+        self._ensure_ws(max_batch, max_nnz or max_batch * 64)
+
+    # ------------------------------------------------------------------ plumbing
+    def _pick_impl(self, impl):
+        names = {"simt": 0, "fp32": 0, "tc": 1, "tc3": 1, "parity": 1, "tf32": 2, "fast": 2}
+        if impl == "auto":
+            return 0
+        if isinstance(impl, int):
+            return impl
+        return names[impl]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _ensure_ws(self, B, nnz):
+        if B <= self._ws_B and nnz <= self._ws_nnz:
+            return
+        B = max(B, self._ws_B)
+        nnz = max(nnz, self._ws_nnz, 1)
+        torch.cuda.synchronize(self.dev)
+        self._graphs.clear()
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        H, Cc, Cp, D = self.H, self.C, self.Cp, self.D
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.indptr = torch.zeros(B + 1, **i32)
+        self.indices = torch.zeros(nnz, **i32)
+        self.cond = z(B, max(D, 1))
+        self.masks = z(12, B, H)
+        self.z_real = z(B, Cc)
+        self.uniq = torch.zeros(nnz, **i32)
+        self.n_uniq = torch.zeros(1, **i32)
+        self.G1, self.G2 = z(nnz, H), z(nnz, H)
+        self.h1pre, self.a1, self.a2, self.dd1, self.h2, self.dh2 = (z(B, H) for _ in range(6))
+        self.zc = z(B, Cp)
+        self.g_d2, self.g_d1, self.g_e2, self.g_h1 = (z(B, H) for _ in range(4))
+        self.g_z = z(B, Cc)
+        self.h1pre2, self.ga1, self.ga2, self.gg_e2, self.gg_h1 = (z(B, H) for _ in range(5))
+        self.gg_z = z(B, Cc)
+        self.disc_acts = z(B, 2 * (Cc + 2 * H))
+        self.disc_grads = z(B, 2 * (2 * H + 1))
+        # pinned staging ring for the host-buffer (end-to-end) entry
+        self._pin = []
+        for _ in range(4):
+            self._pin.append(dict(
+                indptr=torch.zeros(B + 1, dtype=torch.int32).pin_memory(),
+                indices=torch.zeros(nnz, dtype=torch.int32).pin_memory(),
+                cond=torch.zeros(B, max(D, 1), dtype=torch.float32).pin_memory(),
+                ev=None))
+        self._pin_i = 0
+        self._ws_B, self._ws_nnz = B, nnz
+
+    # ------------------------------------------------------------------ parameters
+    def load_params(self, params):
+        """``params``: torch-layout state dict (keys ``enc.lin1.weight`` ... as in the reference's
+        modules, aae.py:104-213); values numpy arrays or tensors (full, unsharded)."""
+        def t(name):
+            return torch.as_tensor(np.asarray(params[name]) if not torch.is_tensor(params[name]) else params[name],
+                                   dtype=torch.float32)
+        lo, hi = self.v_begin, self.v_end
+        W1 = t("enc.lin1.weight")            # [H,V]
+        assert W1.shape == (self.H, self.V), (W1.shape, self.H, self.V)
+        self.W1t.copy_(W1[:, lo:hi].t().contiguous())
+        Wd3 = t("dec.lin3.weight")           # [V,H]
+        self.Wd3.copy_(Wd3[lo:hi].contiguous())
+        self.bd3.copy_(t("dec.lin3.bias")[lo:hi])
+        for blk, sizes in ((self.enc, enc_block_sizes(self.H, self.C)), (self.dec, dec_block_sizes(self.H, self.Cp)),
+                           (self.disc, disc_block_sizes(self.H, self.C))):
+            off = 0
+            for name, sz in sizes:
+                v = t(name).reshape(-1)
+                assert v.numel() == sz, (name, v.numel(), sz)
+                blk[off:off + sz].copy_(v)
+                off += sz
+        for m in (self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2, self.Wd3_m, self.Wd3_v, self.bd3_m, self.bd3_v,
+                  self.enc_m1, self.enc_v1, self.enc_m2, self.enc_v2, self.dec_m, self.dec_v, self.disc_m, self.disc_v):
+            m.zero_()
+        call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
+        self.steps_done = 0
+
+    def _gather_items(self, local):
+        """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export only)."""
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        per = (self.V + self.world - 1) // self.world
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local[: self.Vloc]
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        return torch.cat(out, 0)[: self.V]
+
+    def state_dict(self):
+        """Weights in the reference's torch layout (full, gathered over shards), on the host."""
+        torch.cuda.synchronize(self.dev)
+        out = {}
+        out["enc.lin1.weight"] = self._gather_items(self.W1t[: self.Vloc]).t().contiguous().cpu()
+        out["dec.lin3.weight"] = self._gather_items(self.Wd3[: self.Vloc]).contiguous().cpu()
+        out["dec.lin3.bias"] = self._gather_items(self.bd3[: self.Vloc]).contiguous().cpu()
+        shapes = {"enc.lin2.weight": (self.H, self.H), "enc.lin3.weight": (self.C, self.H),
+                  "dec.lin1.weight": (self.H, self.Cp), "dec.lin2.weight": (self.H, self.H),
+                  "disc.lin1.weight": (self.H, self.C), "disc.lin2.weight": (self.H, self.H),
+                  "disc.lin3.weight": (1, self.H)}
+        for blk, sizes in ((self.enc, enc_block_sizes(self.H, self.C)), (self.dec, dec_block_sizes(self.H, self.Cp)),
+                           (self.disc, disc_block_sizes(self.H, self.C))):
+            off = 0
+            for name, sz in sizes:
+                v = blk[off:off + sz].cpu()
+                out[name] = v.reshape(shapes[name]) if name in shapes else v.clone()
+                off += sz
+        return out
+
+    # ------------------------------------------------------------------ batch staging
+    def upload_csr(self, indptr_np, indices_np, cond_np=None):
+        """Host CSR rows (int32, row-relative indptr starting at 0) -> device batch buffers,
+        through pinned staging; returns (B, nnz).  This is the H2D leg of the end-to-end path."""
+        B = int(indptr_np.shape[0]) - 1
+        nnz = int(indptr_np[-1])
+        self._ensure_ws(B, nnz)
+        slot = self._pin[self._pin_i]
+        self._pin_i = (self._pin_i + 1) % len(self._pin)
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()
+        slot["indptr"][: B + 1].numpy()[:] = indptr_np
+        slot["indices"][:nnz].numpy()[:] = indices_np[:nnz]
+        call("aae_upload_batch", ptr(slot["indptr"]), ptr(slot["indices"]), B, nnz, ptr(self.indptr),
+             ptr(self.indices), self._stream())
+        if self.D:
+            slot["cond"][:B].numpy()[:] = cond_np
+            self.cond[:B].copy_(slot["cond"][:B], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        slot["ev"] = ev
+        return B, nnz
+
+    def set_batch_device(self, indptr_dev, indices_dev, cond_dev=None):
+        """Batch already resident in HBM (bench 'value' leg): device-to-device into the fixed buffers."""
+        B = indptr_dev.numel() - 1
+        nnz = indices_dev.numel()
+        self._ensure_ws(B, nnz)
+        self.indptr[: B + 1].copy_(indptr_dev, non_blocking=True)
+        if nnz:
+            self.indices[:nnz].copy_(indices_dev, non_blocking=True)
+        if self.D:
+            self.cond[:B].copy_(cond_dev, non_blocking=True)
+        return B, nnz
+
+    def set_rng_draws(self, B, draws):
+        """Oracle-RNG mode: inject the 12 dropout masks and z_real drawn by torch in the reference's
+        order (``oracle.aae_oracle.draw_step_rng``)."""
+        order = [("ae_enc", 0), ("ae_enc", 1), ("ae_dec", 0), ("ae_dec", 1), ("disc_real", 0), ("disc_real", 1),
+                 ("disc_fake", 0), ("disc_fake", 1), ("gen_enc", 0), ("gen_enc", 1), ("gen_disc", 0), ("gen_disc", 1)]
+        have = False
+        for i, (k, j) in enumerate(order):
+            m = draws[k][j]
+            if m is not None:
+                self.masks[i, :B].copy_(torch.as_tensor(m, dtype=torch.float32), non_blocking=False)
+                have = True
+        self.z_real[:B].copy_(torch.as_tensor(draws["z_real"], dtype=torch.float32))
+        return have
+
+    # ------------------------------------------------------------------ one partial_fit
+    def _drops(self, B, injected):
+        p1, p2 = self.dropout
+        out = {}
+        for i, name in enumerate(_DROP_ORDER):
+            p = p1 if i % 2 == 0 else p2
+            if injected and p > 0:
+                out[name] = N.drop(self.masks[i, :B], p, i + 1)
+            else:
+                out[name] = N.drop(None, p, i + 1)
+        return out
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+
+    def launches_per_step(self):
+        """Kernels of ours launched by one train_step (counted while enqueueing; a graph replay
+        launches the same kernel nodes)."""
+        return self._launches_per_step
+
+    def _enqueue_step(self, B, injected):
+        n0 = N.launch_count()
+        self._enqueue_step_impl(B, injected)
+        self._launches_per_step = N.launch_count() - n0
+
+    def _enqueue_step_impl(self, B, injected):
+        s = self._stream
+        H, dims = self.H, AaeDims(B, self.H, self.C, self.D)
+        dr = self._drops(B, injected)
+        st = ptr(self.state)
+        lo, hi = self.v_begin, self.v_end
+        n_total = float(B) * float(self.V)
+        cap = self.uniq.numel()
+        cur = torch.cuda.current_stream(self.dev)
+        call("aae_step_tick", st, s())
+        self.loss_sums.zero_()
+        self.dh2[:B].zero_()
+        call("aae_batch_slots", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.slot_of), ptr(self.uniq),
+             ptr(self.n_uniq), s())
+        # rows that are not in the batch: both Adam states decay, on a side stream under the step
+        if self.overlap_sweep:
+            self._ev_fork.record(cur)
+            self.side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self.side):
+                call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
+                     ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
+                self._ev_join.record(self.side)
+        call("aae_zero_rows", ptr(self.G1), ptr(self.indptr), B, H, s())
+        call("aae_zero_rows", ptr(self.G2), ptr(self.indptr), B, H, s())
+        # ---- ae_step (aae.py:676-711)
+        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
+             lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
+        self._allreduce(self.h1pre[:B])
+        call("aae_ae_fwd", dims, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
+             dr["ae_e2"], dr["ae_d1"], dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1),
+             ptr(self.h2), s())
+        call("aae_dec_out_train", ptr(self.h2), B, H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m), ptr(self.Wd3_v),
+             ptr(self.bd3_m), ptr(self.bd3_v), lo, self.Vloc, ptr(self.indptr), ptr(self.indices), n_total, st,
+             ptr(self.dh2), ptr(self.loss_sums), self.impl, s())
+        if self.world > 1:
+            self._allreduce(self.dh2[:B])
+            self._allreduce(self.loss_sums[:1])
+        call("aae_ae_bwd", dims, ptr(self.dh2), ptr(self.enc), ptr(self.dec), dr["ae_e1"], dr["ae_e2"], dr["ae_d1"],
+             dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.dd1), ptr(self.h2), ptr(self.g_d2), ptr(self.g_d1),
+             ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), s())
+        call("aae_ae_wgrad", dims, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1), ptr(self.g_d2),
+             ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), ptr(self.g_enc), ptr(self.g_dec), s())
+        call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.g_h1), H, self.normalize,
+             ptr(self.slot_of), lo, hi, ptr(self.G1), s())
+        call("aae_adam_dense", ptr(self.dec), ptr(self.g_dec), ptr(self.dec_m), ptr(self.dec_v), self.n_dec, st, 0, s())
+        call("aae_adam_dense", ptr(self.enc), ptr(self.g_enc), ptr(self.enc_m1), ptr(self.enc_v1), self.n_enc, st, 0,
+             s())
+        call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G1), ptr(self.W1t), ptr(self.W1_m1),
+             ptr(self.W1_v1), H, st, 0, s())
+        # ---- disc_step (aae.py:713-732) and gen_step (734-743) share X.W1^T + b1 (same weights, same input)
+        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
+             lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
+        self._allreduce(self.h1pre2[:B])
+        call("aae_disc_phase", dims, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
+             C.c_float(self.prior_scale), ptr(self.enc), ptr(self.disc), dr["disc_r1"], dr["disc_r2"], dr["disc_f1"],
+             dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
+        call("aae_disc_wgrad", dims, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.g_disc), s())
+        call("aae_adam_dense", ptr(self.disc), ptr(self.g_disc), ptr(self.disc_m), ptr(self.disc_v), self.n_disc, st,
+             1, s())
+        call("aae_gen_phase", dims, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"], dr["gen_e2"],
+             dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
+             ptr(self.gg_h1), ptr(self.loss_sums[2:]), s())
+        call("aae_gen_wgrad", dims, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2), ptr(self.gg_h1),
+             ptr(self.g_enc), s())
+        call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.gg_h1), H, self.normalize,
+             ptr(self.slot_of), lo, hi, ptr(self.G2), s())
+        call("aae_adam_dense", ptr(self.enc), ptr(self.g_enc), ptr(self.enc_m2), ptr(self.enc_v2), self.n_enc, st, 1,
+             s())
+        call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G2), ptr(self.W1t), ptr(self.W1_m2),
+             ptr(self.W1_v2), H, st, 1, s())
+        if self.overlap_sweep:
+            cur.wait_event(self._ev_join)
+        else:
+            call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
+                 ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
+        call("aae_batch_slots_reset", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, s())
+        call("aae_finish_losses", ptr(self.loss_sums), n_total, B, ptr(self.losses), s())
+
+    def train_step(self, B, injected=False):
+        """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses
+        (R, D, G) land in ``self.losses`` (device float32[3])."""
+        if B <= 0:
+            return
+        if not self.use_graph:
+            self._enqueue_step(B, injected)
+        else:
+            key = (B, bool(injected))
+            g = self._graphs.get(key)
+            if g is None:
+                # warm up once eagerly so that lazy module loading / attribute setting is done
+                snap = self._snapshot()
+                self._enqueue_step(B, injected)
+                torch.cuda.synchronize(self.dev)
+                self._restore(snap)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.dev)):
+                    self._enqueue_step(B, injected)
+                self._restore(snap)
+                self._graphs[key] = g
+            g.replay()
+        self.steps_done += 1
+
+    def _snapshot(self):
+        names = ("W1t", "W1_m1", "W1_v1", "W1_m2", "W1_v2", "Wd3", "Wd3_m", "Wd3_v", "bd3", "bd3_m", "bd3_v",
+                 "enc", "enc_m1", "enc_v1", "enc_m2", "enc_v2", "dec", "dec_m", "dec_v", "disc", "disc_m", "disc_v",
+                 "state")
+        torch.cuda.synchronize(self.dev)
+        return {n: getattr(self, n).clone() for n in names}
+
+    def _restore(self, snap):
+        torch.cuda.synchronize(self.dev)
+        for n, v in snap.items():
+            getattr(self, n).copy_(v)
+        torch.cuda.synchronize(self.dev)
+
+    # ------------------------------------------------------------------ predict
+    def predict_h2(self, B):
+        """eval-mode encoder + condition + decoder head for the batch in the device buffers."""
+        dims = AaeDims(B, self.H, self.C, self.D)
+        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H,
+             self.normalize, self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(self.h1pre), self._stream())
+        self._allreduce(self.h1pre[:B])
+        call("aae_predict_tail", dims, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), ptr(self.h2),
+             self._stream())
+        return self.h2[:B]
+
+    def scores(self, B, out, apply_sigmoid=True):
+        """out[B, >=Vloc] <- sigmoid probabilities (reference predict) or logits of the local items."""
+        self.predict_h2(B)
+        call("aae_dec_out_scores", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), self.Vloc,
+             1 if apply_sigmoid else 0, ptr(out), out.stride(0), self.impl, self._stream())
+        return out
+
+    def topk(self, B, k, scratch=None, mask_known=True):
+        """Masked top-k of the batch in the device buffers: returns (idx int32 [B,k] global item ids,
+        val float32 [B,k] logits), descending.  Item-sharded: local top-k + all-gather + merge."""
+        if scratch is None or scratch.shape[0] < B or scratch.shape[1] < self.Vloc:
+            scratch = torch.empty(B, self.Vloc, dtype=torch.float32, device=self.dev)
+        self.scores(B, scratch, apply_sigmoid=False)
+        kl = min(k, self.Vloc)
+        idx = torch.empty(B, kl, dtype=torch.int32, device=self.dev)
+        val = torch.empty(B, kl, dtype=torch.float32, device=self.dev)
+        call("aae_masked_topk", ptr(scratch), scratch.stride(0), B, self.Vloc, self.v_begin,
+             ptr(self.indptr) if mask_known else None, ptr(self.indices) if mask_known else None, kl, ptr(idx),
+             ptr(val), None, self._stream())
+        if self.world == 1:
+            return idx, val
+        import torch.distributed as dist
+        kmax = min(k, (self.V + self.world - 1) // self.world)
+        pv = torch.full((B, kmax), -3.0e38, dtype=torch.float32, device=self.dev)
+        pi = torch.full((B, kmax), -1, dtype=torch.int32, device=self.dev)
+        pv[:, :kl] = val
+        pi[:, :kl] = idx
+        gv = [torch.empty_like(pv) for _ in range(self.world)]
+        gi = [torch.empty_like(pi) for _ in range(self.world)]
+        dist.all_gather(gv, pv, group=self.group)
+        dist.all_gather(gi, pi, group=self.group)
+        cv = torch.cat(gv, 1).contiguous()
+        ci = torch.cat(gi, 1).contiguous()
+        kk = min(k, self.V)
+        oi = torch.empty(B, kk, dtype=torch.int32, device=self.dev)
+        ov = torch.empty(B, kk, dtype=torch.float32, device=self.dev)
+        call("aae_topk_merge", ptr(cv), ptr(ci), B, cv.shape[1], kk, ptr(oi), ptr(ov), self._stream())
+        return oi, ov

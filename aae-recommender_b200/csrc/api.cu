@@ -1,0 +1,98 @@
+// C-ABI glue: error reporting, device check and the dispatchers of the decoder output layer.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace aae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  return AAE_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int dec_out_train_simt(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                       float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                       const aae_step_state* st, float* dh2, double* loss_sum, cudaStream_t s);
+int dec_out_scores_simt(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
+                        float* out, int64_t ldo, cudaStream_t s);
+int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
+                     int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                     const aae_step_state* st, float* dh2, double* loss_sum, int split, cudaStream_t s);
+int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
+                      float* out, int64_t ldo, int split, cudaStream_t s);
+
+}  // namespace aae
+
+using namespace aae;
+
+extern "C" {
+
+int aae_version(void) { return 100; }
+const char* aae_last_error(void) { return g_err; }
+
+int aae_device_check(int dev) {
+  int major = 0, minor = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (e != cudaSuccess) {
+    set_error("device_check: %s", cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libaae_b200 is built for sm_100a only", dev, major, minor);
+    return AAE_E_ARCH;
+  }
+  return AAE_OK;
+}
+
+int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                      float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                      const aae_step_state* st, float* dh2, double* loss_sum, int impl, void* stream) {
+  AAE_REQUIRE(h2 && Wd3 && bd3 && mW && vW && mb && vb && indptr && indices && st && dh2 && loss_sum, "null pointer");
+  AAE_REQUIRE(B > 0 && H > 0 && Vloc > 0 && n_total > 0, "bad size");
+  if (impl == 0)
+    return dec_out_train_simt(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
+                              loss_sum, as_stream(stream));
+  if (impl == 1 || impl == 2)
+    return dec_out_train_tc(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
+                            loss_sum, impl == 1 ? 3 : 1, as_stream(stream));
+  set_error("dec_out_train: unknown impl %d", impl);
+  return AAE_E_ARG;
+}
+
+int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
+                       float* out, int64_t ldo, int impl, void* stream) {
+  AAE_REQUIRE(h2 && Wd3 && bd3 && out, "null pointer");
+  AAE_REQUIRE(B > 0 && H > 0 && Vloc > 0 && ldo >= Vloc, "bad size");
+  if (impl == 0) return dec_out_scores_simt(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo, as_stream(stream));
+  if (impl == 1 || impl == 2)
+    return dec_out_scores_tc(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo, impl == 1 ? 3 : 1, as_stream(stream));
+  set_error("dec_out_scores: unknown impl %d", impl);
+  return AAE_E_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+// Ranking tail: masked top-k over the item vocabulary, one CTA per query row.
+// Replaces remove_non_missing + argtopk (aaerec/evaluation.py:183-199, 20-58) for the consumers
+// that only need the k best unknown items (metrics at k in {1,5,10,20}, MPD submission k=500,
+// eval/mpd/make_submission.py:36-53).  Min-max scaling is monotone per row, so ranking the raw
+// scores gives the same order; known items are pushed to the bottom (the reference sets them to
+// the row minimum, 0 after scaling).
+//
+// Algorithm (single HBM pass per row in the common case): sort a strided sample of the row in
+// shared memory, take its j-th largest value as a threshold that is expected to keep ~max(6k,2048)
+// elements, stream the row once collecting (key,index) pairs above the threshold, bitonic-sort
+// the candidates in shared memory, emit the first k.  Too few / too many candidates -> retry with
+// a lower / higher sample rank; pathological rows (huge tie groups) fall back to an exact
+// bit-by-bit radix bisection.
+#include <float.h>
+#include "common.cuh"
+
+namespace aae {
+
+constexpr int TK_THREADS = 1024;
+constexpr int TK_SAMPLE = 4096;
+constexpr int TK_CAP = 8192;
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+__global__ void mask_known_kernel(float* __restrict__ scores, int64_t lds, int B, int Vloc, int v_begin,
+                                  const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices) {
+  int nnz = indptr[B];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x) {
+    // row of entry e: binary search in indptr
+    int lo = 0, hi = B;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (indptr[mid + 1] <= e) lo = mid + 1; else hi = mid;
+    }
+    int i = indices[e] - v_begin;
+    if (i >= 0 && i < Vloc) scores[(size_t)lo * lds + i] = -FLT_MAX;
+  }
+}
+
+// descending bitonic sort of n (power of two) 64-bit composites in shared memory
+__device__ void bitonic_desc(unsigned long long* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        unsigned long long x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long compose(uint32_t key, uint32_t idx) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+// collect every element of the row with key > thr (or >= thr) into buf; returns the count in *cnt
+__device__ void collect(const float* __restrict__ row, int n, uint32_t thr, bool inclusive, unsigned long long* buf,
+                        int* cnt) {
+  int lane = threadIdx.x & 31;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    bool take = false;
+    uint32_t key = 0;
+    if (i < n) {
+      key = f2key(__ldcs(row + i));
+      take = inclusive ? (key >= thr) : (key > thr);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (bal) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(cnt, __popc(bal));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (take) {
+        int p = pos + __popc(bal & ((1u << lane) - 1));
+        if (p < TK_CAP) buf[p] = compose(key, (uint32_t)i);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ int block_count_ge(const float* __restrict__ row, int n, uint32_t thr, int* scratch) {
+  if (threadIdx.x == 0) *scratch = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (f2key(row[i]) >= thr);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(scratch, c);
+  __syncthreads();
+  int r = *scratch;
+  __syncthreads();
+  return r;
+}
+
+// idx_map == nullptr: candidates are row positions (+ idx_offset); else idx_out = idx_map[row, pos]
+__global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __restrict__ scores, int64_t lds, int n,
+                                                                 int k, int idx_offset,
+                                                                 const int32_t* __restrict__ idx_map,
+                                                                 int32_t* __restrict__ idx_out,
+                                                                 float* __restrict__ val_out) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(sm_raw);          // [TK_CAP]
+  uint32_t* samp = reinterpret_cast<uint32_t*>(buf + TK_CAP);                       // [TK_SAMPLE] (as u64 pairs)
+  __shared__ int cnt;
+  __shared__ int scratch;
+  const int rowi = blockIdx.x;
+  const float* row = scores + (size_t)rowi * lds;
+  const int kk = min(k, n);
+  int total = 0;
+  if (n <= TK_CAP) {
+    for (int i = threadIdx.x; i < TK_CAP; i += blockDim.x)
+      buf[i] = (i < n) ? compose(f2key(row[i]), (uint32_t)i) : 0ull;
+    total = n;
+    __syncthreads();
+  } else {
+    // ---- sample, sort, pick a threshold
+    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(samp);
+    double stride = (double)n / TK_SAMPLE;
+    for (int s = threadIdx.x; s < TK_SAMPLE; s += blockDim.x) {
+      int p = min(n - 1, (int)(s * stride));
+      sbuf[s] = compose(f2key(row[p]), 0u);
+    }
+    bitonic_desc(sbuf, TK_SAMPLE);
+    int target = max(6 * kk, 2048);
+    int j = max(2, (int)((double)target * TK_SAMPLE / n + 0.5));
+    j = min(j, TK_SAMPLE - 1);
+    bool ok = false;
+    for (int attempt = 0; attempt < 5 && !ok; ++attempt) {
+      uint32_t thr = (uint32_t)(sbuf[j] >> 32);
+      if (threadIdx.x == 0) cnt = 0;
+      __syncthreads();
+      collect(row, n, thr, false, buf, &cnt);
+      total = cnt;
+      __syncthreads();
+      if (total >= kk && total <= TK_CAP) ok = true;
+      else if (total > TK_CAP) j = max(0, j / 2 - (j <= 1));
+      else j = min(TK_SAMPLE - 1, 2 * j + 2);
+    }
+    if (!ok) {
+      // ---- exact fallback: largest threshold T with count(key >= T) >= kk, bit by bit
+      uint32_t T = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        uint32_t cand = T | (1u << bit);
+        if (block_count_ge(row, n, cand, &scratch) >= kk) T = cand;
+      }
+      if (threadIdx.x == 0) cnt = 0;
+      __syncthreads();
+      collect(row, n, T, false, buf, &cnt);          // strictly greater: fewer than kk of them
+      int gt = min(cnt, TK_CAP);
+      __syncthreads();
+      // fill with ties (== T) in index order (serial over chunks; ties are exempt from parity)
+      if (threadIdx.x == 0) {
+        int need = kk - gt, got = 0;
+        for (int i = 0; i < n && got < need; ++i)
+          if (f2key(row[i]) == T) { buf[gt + got] = compose(T, (uint32_t)i); ++got; }
+        cnt = gt + got;
+      }
+      __syncthreads();
+      total = cnt;
+    }
+    for (int i = total + threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = 0ull;
+    __syncthreads();
+  }
+  int npow = 1;
+  while (npow < total) npow <<= 1;
+  npow = max(npow, 2);
+  bitonic_desc(buf, npow);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    int32_t id = -1;
+    float val = -FLT_MAX;
+    if (i < kk) {
+      unsigned long long c = buf[i];
+      uint32_t pos = 0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull);
+      id = idx_map ? idx_map[(size_t)rowi * lds + pos] : (int32_t)pos + idx_offset;
+      val = key2f((uint32_t)(c >> 32));
+    }
+    idx_out[(size_t)rowi * k + i] = id;
+    if (val_out) val_out[(size_t)rowi * k + i] = val;
+  }
+}
+
+}  // namespace aae
+
+using namespace aae;
+
+extern "C" {
+
+int64_t aae_topk_work_bytes(int B, int k) { return 16; }
+
+static int launch_row_topk(const float* scores, int64_t lds, int B, int n, int k, int idx_offset,
+                           const int32_t* idx_map, int32_t* idx_out, float* val_out, cudaStream_t s) {
+  size_t smem = sizeof(unsigned long long) * (TK_CAP + TK_SAMPLE);
+  cudaError_t e = cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("row_topk: %s", cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  row_topk_kernel<<<B, TK_THREADS, smem, s>>>(scores, lds, n, k, idx_offset, idx_map, idx_out, val_out);
+  return check_launch("row_topk");
+}
+
+int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
+                    const int32_t* indices, int k, int32_t* idx_out, float* val_out, void* work, void* stream) {
+  AAE_REQUIRE(scores && idx_out, "null pointer");
+  AAE_REQUIRE(k > 0 && k <= TK_CAP / 2, "k outside the supported envelope (1..4096)");
+  AAE_REQUIRE(B > 0 && Vloc > 0, "bad size");
+  if (indptr && indices) {
+    mask_known_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv((int64_t)B * 32, 256))), 256, 0, as_stream(stream)>>>(
+        scores, lds, B, Vloc, v_begin, indptr, indices);
+    int rc = check_launch("mask_known");
+    if (rc) return rc;
+  }
+  return launch_row_topk(scores, lds, B, Vloc, k, v_begin, nullptr, idx_out, val_out, as_stream(stream));
+}
+
+int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
+                   float* val_out, void* stream) {
+  AAE_REQUIRE(cand_val && cand_idx && idx_out, "null pointer");
+  AAE_REQUIRE(k > 0 && k <= TK_CAP / 2 && n_cand > 0, "bad size");
+  return launch_row_topk(cand_val, n_cand, B, n_cand, k, 0, cand_idx, idx_out, val_out, as_stream(stream));
+}
+
+}  // extern "C"

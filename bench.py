@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- AAE train item-sets/s on the PubMed-shaped configuration (BASELINE.json configs[1]).
+
+A "step" is one ``partial_fit`` (reconstruction + discriminator + generator phases, all four Adam
+updates) over one batch of 100 synthetic item sets, V = 200,000 items, n_hidden 100, n_code 50.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pubmed|econbiz|mpd]
+
+Prints ONE JSON line.  ``value`` = sets/s with the batches already resident in HBM (device-timed, CUDA
+events, max over ranks); ``e2e`` = sets/s through the host-buffer API (pinned CSR batch H2D + losses D2H
+every step, inside the timed region); ``roofline`` = the dominant kernel's algorithmic bytes / its own
+CUDA-event time against MEASURED_PEAKS.json; ``cpu_baseline`` = the CPU port of the reference's algorithm
+(oracle/aae_oracle.py, dense like the reference) timed on this box's host cores on a bounded sample.
+``--impl reference`` times that CPU port alone (the reference is pure Python/torch and cannot travel to the
+GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "aae-recommender_b200"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (V, mean_len, min_len, max_len, data_seed, B)
+    "pubmed": (200000, 16, 2, 200, 1, 100),
+    "econbiz": (4587, 5, 2, 30, 0, 100),
+    "mpd": (2000000, 66, 5, 250, 3, 100),
+}
+H, C = 100, 50
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm, reasons, smax = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batches(workload, n_batches, cond_dim=0):
+    from aaerec_b200.synth import synth_sets, synth_condition
+    V, mean_len, lo, hi, seed, B = WORKLOADS[workload]
+    X = synth_sets(n_batches * B, V, mean_len, lo, hi, seed)
+    cond = synth_condition(n_batches * B, cond_dim) if cond_dim else None
+    batches = []
+    for i in range(n_batches):
+        s, e = int(X.indptr[i * B]), int(X.indptr[(i + 1) * B])
+        ip = (X.indptr[i * B:(i + 1) * B + 1] - s).astype(np.int32)
+        batches.append((ip, X.indices[s:e].astype(np.int32), cond[i * B:(i + 1) * B] if cond_dim else None))
+    return X, batches, V, B
+
+
+def cpu_port_run(workload, steps, warmup, threads=None):
+    """The reference's algorithm (dense, as aae.py does it) on the host cores: oracle port, all threads."""
+    import torch
+    from oracle import aae_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    V, mean_len, lo, hi, seed, B = WORKLOADS[workload]
+    _, batches, V, B = make_batches(workload, min(steps + warmup, 8))
+    params = O.init_params(V, H, C, seed=42)
+    model = O.OracleAAE(params, n_code=C, faithful_cost=True)
+    import scipy.sparse as sp
+
+    def dense(b):
+        ip, ii, _ = b
+        return sp.csr_matrix((np.ones(len(ii), dtype=np.float32), ii, ip), shape=(B, V)).toarray()
+    torch.manual_seed(0)
+    for i in range(warmup):
+        model.partial_fit(dense(batches[i % len(batches)]), None, O.draw_step_rng(B, H, C))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model.partial_fit(dense(batches[(warmup + i) % len(batches)]), None, O.draw_step_rng(B, H, C))
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    V, _, _, _, _, B = WORKLOADS[args.workload]
+    steps = min(args.steps, 40)
+    val, sec, threads = cpu_port_run(args.workload, steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": "AAE train item-sets/sec", "value": val, "unit": "sets/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s-shaped: V=%d items, batch %d, n_hidden %d, n_code %d, one partial_fit per step"
+                   % (args.workload, V, B, H, C)},
+        "cpu_baseline": {"value": val, "unit": "sets/s", "cores": threads, "kind": "port",
+                         "sample": "%d partial_fit steps of the same workload (dense CPU port of aae.py, torch %d threads)"
+                         % (steps, threads)},
+        "e2e": {"value": val, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def time_kernel(fn, iters, stream):
+    import torch
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record(stream)
+        fn()
+        b.record(stream)
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) * 1e-3 for a, b in evs]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from aaerec_b200 import _native as N
+    from aaerec_b200.engine import AAEEngine
+    from aaerec_b200._native import call, ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, max(args.warmup, 3)
+    n_batches = min(K + W, 64)
+    _, batches, V, B = make_batches(args.workload, n_batches)
+    eng = AAEEngine(V, H, C, rank=rank, world=world, impl=args.kernel, seed=1, max_batch=B,
+                    max_nnz=max(len(b[1]) for b in batches) + 8, use_graph=not args.no_graph)
+    # random-init weights of the reference architecture (same init law as nn.Linear)
+    g = torch.Generator().manual_seed(42)
+
+    def uni(shape, fan_in):
+        bound = 1.0 / np.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+    params = {"enc.lin1.weight": uni((H, V), V), "enc.lin1.bias": uni((H,), V),
+              "enc.lin2.weight": uni((H, H), H), "enc.lin2.bias": uni((H,), H),
+              "enc.lin3.weight": uni((C, H), H), "enc.lin3.bias": uni((C,), H),
+              "dec.lin1.weight": uni((H, C), C), "dec.lin1.bias": uni((H,), C),
+              "dec.lin2.weight": uni((H, H), H), "dec.lin2.bias": uni((H,), H),
+              "dec.lin3.weight": uni((V, H), H), "dec.lin3.bias": uni((V,), H),
+              "disc.lin1.weight": uni((H, C), C), "disc.lin1.bias": uni((H,), C),
+              "disc.lin2.weight": uni((H, H), H), "disc.lin2.bias": uni((H,), H),
+              "disc.lin3.weight": uni((1, H), H), "disc.lin3.bias": uni((1,), H)}
+    eng.load_params(params)
+    dev_batches = [(torch.as_tensor(ip, device=eng.dev), torch.as_tensor(ii, device=eng.dev)) for ip, ii, _ in batches]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: batches resident in HBM ----------------
+    for i in range(W):
+        eng.set_batch_device(*dev_batches[i % n_batches])
+        eng.train_step(B)
+    barrier()
+    N.reset_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        eng.set_batch_device(*dev_batches[(W + i) % n_batches])
+        eng.train_step(B)
+    e1.record(stream)
+    barrier()
+    sec = e0.elapsed_time(e1) * 1e-3
+    launches = eng.launches_per_step() * K
+    # ---------------- e2e: host CSR buffers in, losses out, every step ----------------
+    loss_pin = torch.zeros(4, 3, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    h2d = 0
+    t0.record(stream)
+    for i in range(K):
+        ip, ii, _ = batches[(W + i) % n_batches]
+        eng.upload_csr(ip, ii)
+        eng.train_step(B)
+        loss_pin[i % 4].copy_(eng.losses, non_blocking=True)
+        h2d += ip.nbytes + ii.nbytes
+        if i % 4 == 3:
+            stream.synchronize()       # the host consumes the losses (as the reference's .item() does)
+    t1.record(stream)
+    barrier()
+    sec_e2e = t0.elapsed_time(t1) * 1e-3
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([sec, sec_e2e], device=eng.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec, sec_e2e = t.tolist()
+    # ---------------- roofline of the dominant kernels (timed alone, on their stream) ----------------
+    hbm_peak, tf_peak, peak_kind = peaks()
+    Vl = eng.Vloc
+    st = ptr(eng.state)
+    eng.set_batch_device(*dev_batches[0])
+    torch.cuda.synchronize()
+
+    def k3():
+        call("aae_dec_out_train", ptr(eng.h2), B, H, ptr(eng.Wd3), ptr(eng.bd3), ptr(eng.Wd3_m), ptr(eng.Wd3_v),
+             ptr(eng.bd3_m), ptr(eng.bd3_v), eng.v_begin, Vl, ptr(eng.indptr), ptr(eng.indices), float(B) * V, st,
+             ptr(eng.dh2), ptr(eng.loss_sums), eng.impl, eng._stream())
+
+    def sweep():
+        call("aae_w1_sweep_untouched", ptr(eng.slot_of), 0, Vl, H, ptr(eng.W1t), ptr(eng.W1_m1), ptr(eng.W1_v1),
+             ptr(eng.W1_m2), ptr(eng.W1_v2), st, eng._stream())
+    kern = {}
+    for name, fn, alg_bytes in (("dec_out_train", k3, 24.0 * (Vl * H + Vl) + 8.0 * B * H),
+                                ("w1_sweep_untouched", sweep, 40.0 * Vl * H + 4.0 * Vl)):
+        for _ in range(3):
+            fn()
+        ts = time_kernel(fn, 10, stream)
+        kern[name] = {"sec": float(np.mean(ts)), "bytes": alg_bytes}
+    dom = max(kern, key=lambda k: kern[k]["sec"])
+    ach = kern[dom]["bytes"] / kern[dom]["sec"] / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                "kernels": {k: {"ms": v["sec"] * 1e3, "GBps": v["bytes"] / v["sec"] / 1e9,
+                                "frac": v["bytes"] / v["sec"] / 1e9 / hbm_peak} for k, v in kern.items()},
+                "step_algorithmic_bytes": 64.0 * Vl * H,
+                "step_frac": 64.0 * Vl * H / (sec / K) / 1e9 / hbm_peak}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        val, s_per, threads = cpu_port_run(args.workload, 12, 2)
+        cpu = {"value": val, "unit": "sets/s", "cores": threads, "kind": "port",
+               "sample": "12 partial_fit steps of the same workload after 2 warm-up steps (dense CPU port of "
+                         "aae.py incl. the discarded encoder backward of disc_step, %d torch threads)" % threads}
+    nnz_mean = float(np.mean([len(b[1]) for b in batches]))
+    line = {
+        "metric": "AAE train item-sets/sec", "value": B * K / sec, "unit": "sets/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s-shaped (BASELINE configs[1]): V=%d items, batch %d sets (mean %.0f items/set), "
+                               "n_hidden %d, n_code %d, dropout (.2,.2) in-kernel Philox, dense-Adam-equivalent W1 "
+                               "policy; one partial_fit (ae+disc+gen) per step" % (args.workload, V, B, nnz_mean / B, H, C),
+                   "parallelism": "item-sharded x%d" % world if world > 1 else "single GPU",
+                   "decoder_kernel": {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[eng.impl],
+                   "cuda_graph": eng.use_graph,
+                   "l2": "per-step working set %.2f GB >> 126 MB L2 (no flush needed)" % (64.0 * Vl * H / 1e9)},
+        "e2e": {"value": B * K / sec_e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 12,
+                "ms_per_step": sec_e2e / K * 1e3},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pubmed", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", help="decoder-output kernel: auto|simt|tc|tf32")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

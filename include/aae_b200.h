@@ -1,0 +1,198 @@
+/*
+ * aae_b200.h -- C ABI of the B200-native AAE hot path (libaae_b200.so).
+ *
+ * This is the drop-in boundary for the path named in BASELINE.json: the training step of
+ * aaerec's AdversarialAutoEncoder (partial_fit = ae_step + disc_step + gen_step) and its
+ * predict / masked top-k ranking.  The reference is pure Python on torch; a maintainer binds
+ * these entry points with ctypes from aaerec/aae.py.  Each function names
+ * the reference code it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all matrices are dense row-major float32; CSR index arrays are int32, column indices
+ *     sorted and unique inside a row (what BagsWithVocab.tocsr() yields, datasets.py:459-470);
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never
+ *     synchronise and never allocate (the caller owns every buffer);
+ *   - return value 0 = ok, negative = error (AAE_E_*), text via aae_last_error();
+ *   - the library refuses to run on anything but compute capability 10.x (no fallback path).
+ *
+ * Weight layout (fp32):  W1t [V,H] is enc.lin1.weight TRANSPOSED (one 4H-byte row per item, so
+ * the encoder's first layer is an embedding-bag gather); Wd3 [V,H] is dec.lin3.weight as torch
+ * stores it; every other layer keeps torch's [out,in] layout.
+ */
+#ifndef AAE_B200_H
+#define AAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AAE_OK 0
+#define AAE_E_ARG (-1)      /* bad argument (null pointer, size out of the supported envelope) */
+#define AAE_E_CUDA (-2)     /* a CUDA runtime call failed */
+#define AAE_E_ARCH (-3)     /* device is not sm_100 */
+#define AAE_E_UNSUPPORTED (-4)
+
+/* Adam hyper-parameters and the shared step counter, resident on the device so that a captured
+ * CUDA graph can be replayed: aae_step_tick() advances t and recomputes the bias corrections in
+ * double precision exactly like torch/optim/adam.py (lr/(1-b1^t), sqrt(1-b2^t)).
+ * The reference builds four torch.optim.Adam with default betas/eps (aae.py:798-804): enc_optim
+ * and dec_optim use gen_lr, gen_optim and disc_optim use reg_lr; all four step once per
+ * partial_fit, so they share t. */
+typedef struct {
+  int32_t t;               /* number of completed aae_step_tick calls (= Adam step index) */
+  uint32_t rng_step;       /* counter mixed into the in-kernel Philox streams */
+  float step_size_gen;     /* gen_lr / (1 - beta1^t) */
+  float step_size_reg;     /* reg_lr / (1 - beta1^t) */
+  float bc2_sqrt;          /* sqrt(1 - beta2^t) */
+  float beta1, beta2, eps;
+  float gen_lr, reg_lr;
+  uint64_t seed;           /* Philox key for dropout / prior sampling in native RNG mode */
+} aae_step_state;
+
+/* Dropout description for one dropout layer.  mask != NULL: use the given [B,width] mask whose
+ * entries are 0 or 1/(1-p) (oracle-RNG mode: draws made by torch in the reference's order, SURVEY
+ * 8(a) A11).  mask == NULL and p > 0: in-kernel Philox, stream id `stream_id`.  p == 0: identity. */
+typedef struct {
+  const float* mask;
+  float p;
+  uint32_t stream_id;
+} aae_drop;
+
+int aae_version(void);
+const char* aae_last_error(void);
+/* 0 if device `dev` is compute capability 10.x, AAE_E_ARCH otherwise. */
+int aae_device_check(int dev);
+
+/* ---- step bookkeeping ------------------------------------------------------------------- */
+int aae_step_state_init(aae_step_state* st, float gen_lr, float reg_lr, uint64_t seed, void* stream);
+int aae_step_tick(aae_step_state* st, void* stream);
+
+/* ---- K1: encoder first layer on the sparse multi-hot input ---------------------------------
+ * Replaces F.normalize(inp, 1) + Encoder.lin1 (aae.py:132-135): out[b,:] = b1 + sum_{i in set_b}
+ * W1t[i,:] * (normalize ? 1/|set_b| : 1).  Empty set -> b1.  Items outside [v_begin, v_end) are
+ * skipped and b1 is added only when add_bias != 0 (item-sharded partial sums). */
+int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const float* W1t, const float* b1,
+                int H, int normalize, int v_begin, int v_end, int add_bias, float* out, void* stream);
+
+/* ---- touched-row bookkeeping for the sparse first layer -------------------------------------
+ * slot_of[V] (all -1 between steps) maps an item of the current batch to a dense slot, uniq[]
+ * lists the items, n_uniq[0] their count.  Only items in [v_begin, v_end) get slots. */
+int aae_batch_slots(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end,
+                    int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, void* stream);
+int aae_batch_slots_reset(int32_t* slot_of, const int32_t* uniq, int32_t* n_uniq, int cap, void* stream);
+
+/* ---- K2: weight gradient of the sparse first layer ------------------------------------------
+ * Replaces the dense dW1 = dh1^T . Xhat that autograd builds (aae.py:703, 741):
+ * G[slot_of[i],:] += dh1[b,:] * (normalize ? 1/|set_b| : 1) for every i in set_b.  G must be zero
+ * on entry for the first n_uniq rows (aae_zero_rows). */
+int aae_bag_bwd(const int32_t* indptr, const int32_t* indices, int B, const float* dh1, int H, int normalize,
+                const int32_t* slot_of, int v_begin, int v_end, float* G, void* stream);
+int aae_zero_rows(float* G, const int32_t* indptr, int B, int H, void* stream);
+
+/* Adam on the touched rows only (rows uniq[0..n_uniq)) with gradient G[slot,:]; which = 0 uses
+ * step_size_gen (enc_optim), 1 uses step_size_reg (gen_optim). */
+int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const float* G, float* W, float* m,
+                  float* v, int H, const aae_step_state* st, int which, void* stream);
+
+/* Dense-Adam-equivalent sweep of W1t for rows NOT in the batch: torch's Adam moves every row every
+ * step even when its gradient is zero (momentum decay), once per optimizer state, enc_optim first
+ * (aae.py:706) then gen_optim (aae.py:741).  Rows with slot_of >= 0 are skipped (they are updated by
+ * aae_rows_adam with their gradients).  rows [r_begin, r_end) of the local shard. */
+int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
+                           float* m2, float* v2, const aae_step_state* st, void* stream);
+
+/* Elementwise Adam over a contiguous block of n parameters (the small replicated layers). */
+int aae_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, const aae_step_state* st,
+                   int which, void* stream);
+
+/* ---- K4: the small replicated layers ---------------------------------------------------------
+ * All small weights of a module live in one contiguous block; the structs give their shapes.
+ * enc block : [b1 (H) | We2 (H*H) | be2 (H) | We3 (C*H) | be3 (C)]        (Encoder.lin1.bias, lin2, lin3)
+ * dec block : [Wd1 (H*Cp) | bd1 (H) | Wd2 (H*H) | bd2 (H)]               (Decoder.lin1, lin2)
+ * disc block: [Wq1 (H*C) | bq1 (H) | Wq2 (H*H) | bq2 (H) | wq3 (H) | bq3 (1)]  (Discriminator)
+ * Cp = C + D where D is the width of the concatenated condition rows (0 if none). */
+typedef struct {
+  int B, H, C, D;
+} aae_dims;
+
+/* ae_step forward tail (aae.py:136-146, 688-690, 168-174): from h1pre = Xhat.W1^T + b1 to the
+ * decoder hidden h2.  Saves the post-activation values needed by the backward. */
+int aae_ae_fwd(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec,
+               aae_drop e1, aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st,
+               float* a1, float* a2, float* zc, float* dd1, float* h2, void* stream);
+/* ae_step backward tail: from dh2 = dL/dh2 to dL/dh1pre; writes the pre-activation gradients of
+ * every small layer (g_d2, g_d1, g_z, g_e2, g_h1), consumed by aae_small_wgrad / aae_bag_bwd. */
+int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec, aae_drop e1, aae_drop e2,
+               aae_drop d1, aae_drop d2, const aae_step_state* st, const float* a1, const float* a2,
+               const float* dd1, const float* h2, float* g_d2, float* g_d1, float* g_z, float* g_e2,
+               float* g_h1, void* stream);
+
+/* disc_step (aae.py:713-732): encoder tail in eval mode, discriminator on z_real and z_fake,
+ * loss, and the backward through the discriminator (the encoder backward the reference computes
+ * and discards is skipped).  z_real == NULL -> sampled in-kernel (Philox normal * prior_scale).
+ * Outputs: activations and pre-activation gradients for aae_disc_wgrad, loss_sum[0] += the summed
+ * per-row loss terms (caller divides by B). */
+int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float prior_scale, const float* enc,
+                   const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2,
+                   const aae_step_state* st, float* acts /* [B, 2*(C+2H)] */, float* grads /* [B, 2*(2H+1)] */,
+                   double* loss_sum, void* stream);
+/* gen_step (aae.py:734-743): encoder tail in train mode, discriminator, loss, backward through
+ * the discriminator into the encoder tail down to dL/dh1pre. */
+int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float* disc, aae_drop e1, aae_drop e2,
+                  aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
+                  float* g_e2, float* g_h1, double* loss_sum, void* stream);
+
+/* Weight/bias gradients of the small layers: block-shaped outputs matching the parameter blocks. */
+int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, const float* dd1,
+                 const float* g_d2, const float* g_d1, const float* g_z, const float* g_e2, const float* g_h1,
+                 float* g_enc, float* g_dec, void* stream);
+int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, void* stream);
+int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z, const float* g_e2,
+                  const float* g_h1, float* g_enc, void* stream);
+
+/* ---- K3: the n_items-wide decoder output layer, training ------------------------------------
+ * Replaces Decoder.lin3 + torch.sigmoid (aae.py:176-177), F.binary_cross_entropy(x+1e-12, t+1e-12)
+ * (aae.py:693-695), its backward (aae.py:703) and dec_optim's Adam on lin3 (aae.py:707) in ONE pass
+ * over Wd3: logits never reach HBM.  Targets are the batch's CSR rows.  For the local item range
+ * [v_begin, v_begin+Vloc): loss_sum[0] += sum of BCE terms, dh2[B,H] += dZ.Wd3 (old weights), then
+ * Wd3/bd3 and their Adam moments are updated in place.  n_total = B * V_global (the BCE mean).
+ * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 tensor-core kernel (3xTF32, fp32-accurate),
+ * 2 = tcgen05 single-pass TF32. */
+int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                      float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices,
+                      double n_total, const aae_step_state* st, float* dh2, double* loss_sum, int impl,
+                      void* stream);
+
+/* ---- predict (aae.py:840-870) --------------------------------------------------------------- */
+/* eval-mode forward tail: h1pre -> h2 (no dropout). */
+int aae_predict_tail(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec,
+                     float* h2, void* stream);
+/* out[b, v] = logit or sigmoid(logit) for local items; ldo = row pitch of out in floats. */
+int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc,
+                       int apply_sigmoid, float* out, int64_t ldo, int impl, void* stream);
+/* Ranking tail = remove_non_missing + argtopk (evaluation.py:183-199, 20-58) without the dense
+ * host matrix: known items (CSR rows, global ids, offset by v_begin) are excluded, the k best
+ * remaining local items per row are returned sorted by descending score (ties: lower id first).
+ * scores is overwritten (known items are set to -FLT_MAX).  idx_out holds GLOBAL item ids.
+ * work: caller-provided scratch of aae_topk_work_bytes(B,k) bytes. */
+int64_t aae_topk_work_bytes(int B, int k);
+int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
+                    const int32_t* indices, int k, int32_t* idx_out, float* val_out, void* work, void* stream);
+/* k-way merge of per-shard results: cand_val/cand_idx [B, n_cand] -> top k (descending). */
+int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
+                   float* val_out, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
+int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
+                     int32_t* indices, void* stream);
+
+/* finalise the three losses on device: out[0]=R/(n_total), out[1]=D/B, out[2]=G/B (float32). */
+int aae_finish_losses(const double* sums, double n_total, int B, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAE_B200_H */

@@ -1,0 +1,108 @@
+"""Host-side logic that needs no GPU: API surface, error conventions, condition protocol, batching."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+
+def test_constructor_defaults_and_str_match_reference():
+    # aae.py:592-606 defaults; __str__ is printed into logs (evaluation.py:355)
+    from aaerec_b200.aae import AdversarialAutoEncoder, AAERecommender
+    m = AdversarialAutoEncoder()
+    assert (m.n_hidden, m.n_code, m.gen_lr, m.reg_lr, m.batch_size, m.n_epochs) == (100, 50, 0.001, 0.001, 100, 500)
+    assert m.prior == "gauss" and m.optimizer == "adam" and m.dropout == (.2, .2) and m.normalize_inputs
+    s = str(m)
+    assert s.startswith("Adversarial Autoencoder (100, 100, 50, 100, 100) optimized by adam")
+    assert "Matching the gauss distribution by linear activation." in s
+    r = AAERecommender(n_hidden=7, verbose=False)
+    assert "Adversarial Autoencoder" in str(r) and "'n_hidden': 7" in str(r)
+    assert r.model_params == {"n_hidden": 7, "verbose": False} and r.adversarial
+
+
+def test_error_conventions():
+    from aaerec_b200.aae import AdversarialAutoEncoder
+    with pytest.raises(KeyError):          # unknown prior -> KeyError from the table lookup (aae.py:612-613)
+        AdversarialAutoEncoder(prior="nope")
+    with pytest.raises(KeyError):          # unknown optimizer (aae.py:798)
+        AdversarialAutoEncoder(optimizer="rmsprop")
+    with pytest.raises(NotImplementedError):
+        AdversarialAutoEncoder(activation="SELU")
+    m = AdversarialAutoEncoder(verbose=False)
+    X = sp.csr_matrix(np.eye(3, dtype=np.float32))
+    with pytest.raises(NotImplementedError):   # aae.py:748-749, 770-771
+        m.partial_fit(X, y=np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        m.fit(X, y=np.zeros(3))
+    with pytest.raises(AssertionError):        # condition mismatch, condition.py:53-55
+        m.fit(X, condition_data=[np.zeros((3, 2))])
+    X2 = sp.csr_matrix(np.array([[2.0, 0], [0, 1]]))
+    with pytest.raises(RuntimeError):          # non-binary targets (torch BCE's error in the reference)
+        m._csr_batch(X2)
+
+
+def test_csr_batch_from_dense_and_unsorted():
+    from aaerec_b200.aae import AdversarialAutoEncoder
+    dense = np.array([[0, 1, 1, 0], [0, 0, 0, 0], [1, 0, 0, 1]], dtype=np.float64)
+    ip, ii = AdversarialAutoEncoder._csr_batch(dense)
+    assert ip.tolist() == [0, 2, 2, 4] and ii.tolist() == [1, 2, 0, 3] and ip.dtype == np.int32
+    X = sp.csr_matrix((np.ones(3), np.array([3, 0, 1]), np.array([0, 2, 3])), shape=(2, 4))
+    ip, ii = AdversarialAutoEncoder._csr_batch(X)
+    assert ii.tolist() == [0, 3, 1]
+
+
+def test_condition_protocol_shape_contract():
+    # reference tests/test_condition.py:28-78: conditioned.size(1) == code.size(1) + size_increment()
+    from aaerec_b200.condition import (ConditionList, PrecomputedEmbeddingCondition, ConcatenationBasedConditioning,
+                                       ConditionBase, _check_conditions)
+    c = PrecomputedEmbeddingCondition(5)
+    assert isinstance(c, ConcatenationBasedConditioning) and isinstance(c, ConditionBase)
+    code = np.zeros((4, 3), dtype=np.float32)
+    rows = np.ones((4, 5))
+    out = c.encode_impose(code, rows)
+    assert out.shape == (4, 3 + c.size_increment())
+    cl = ConditionList([("title", c), ("abstract", PrecomputedEmbeddingCondition(2))])
+    assert list(cl.keys()) == ["title", "abstract"] and cl.size_increment() == 7
+    out = cl.encode_impose(code, [rows, np.ones((4, 2))])
+    assert out.shape == (4, 10)
+    assert cl.fused_rows([rows, 2 * np.ones((4, 2))]).shape == (4, 7)
+    assert cl.zero_grad() is cl and cl.step() is cl
+    assert _check_conditions(None, None) is False
+    assert _check_conditions(cl, [rows, rows]) is True
+    with pytest.raises(AssertionError):
+        _check_conditions(cl, [rows])
+    with pytest.raises(AssertionError):
+        _check_conditions([("x", c)], [rows])
+
+
+def test_unfusable_condition_is_rejected():
+    from aaerec_b200.condition import ConditionList, ConcatenationBasedConditioning
+
+    class Trainable(ConcatenationBasedConditioning):
+        def encode(self, inputs):
+            return inputs
+
+        def size_increment(self):
+            return 2
+    cl = ConditionList([("t", Trainable())])
+    with pytest.raises(NotImplementedError):
+        cl.fused_rows([np.zeros((2, 2))])
+
+
+def test_shard_ranges_cover_vocabulary():
+    from aaerec_b200.engine import shard_range
+    for V in (1, 7, 100, 200000, 2000001):
+        for world in (1, 2, 3, 4, 8):
+            parts = [shard_range(V, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == V
+            for a, b in zip(parts, parts[1:]):
+                assert a[1] == b[0]
+            assert all(lo <= hi for lo, hi in parts)
+
+
+def test_synth_sets_are_binary_sorted_unique():
+    from aaerec_b200.synth import synth_sets
+    X = synth_sets(200, 1000, 8, seed=0)
+    assert X.shape == (200, 1000) and X.data.min() == 1 and X.data.max() == 1
+    for r in range(200):
+        row = X.indices[X.indptr[r]:X.indptr[r + 1]]
+        assert np.all(np.diff(row) > 0)
+    assert (np.diff(X.indptr) >= 1).all()
