@@ -59,6 +59,7 @@ _SIGS = {
     "aae_topk_work_bytes": (I64, [I, I]),
     "aae_masked_topk": (I, [P, I64, I, I, I, P, P, I, P, P, P, P]),
     "aae_topk_merge": (I, [P, P, I, I, I, P, P, P]),
+    "aae_tc_selftest": (I, [I, P, P, P, I, P]),
     "aae_upload_batch": (I, [P, P, I, I, P, P, P]),
     "aae_finish_losses": (I, [P, D, I, P, P]),
 }

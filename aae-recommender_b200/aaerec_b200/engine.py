@@ -27,11 +27,7 @@ _DROP_ORDER = ("ae_e1", "ae_e2", "ae_d1", "ae_d2", "disc_r1", "disc_r2", "disc_f
                "gen_e1", "gen_e2", "gen_q1", "gen_q2")
 
 
-def shard_range(V, rank, world):
-    """Contiguous item range of ``rank``: ceil-divided so every rank but the last is equal."""
-    per = (V + world - 1) // world
-    lo = min(V, rank * per)
-    return lo, min(V, lo + per)
+from .dist import shard_range, gather_item_shards, gather_topk_candidates  # noqa: E402,F401
 
 
 def enc_block_sizes(H, C_):
@@ -174,16 +170,8 @@ class AAEEngine(object):
         self.steps_done = 0
 
     def _gather_items(self, local):
-        """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export only)."""
-        if self.world == 1:
-            return local
-        import torch.distributed as dist
-        per = (self.V + self.world - 1) // self.world
-        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        pad[: local.shape[0]] = local[: self.Vloc]
-        out = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(out, pad, group=self.group)
-        return torch.cat(out, 0)[: self.V]
+        """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export / dense predict)."""
+        return gather_item_shards(local[: self.Vloc], self.V, self.world, self.group)
 
     def state_dict(self):
         """Weights in the reference's torch layout (full, gathered over shards), on the host."""
@@ -428,18 +416,8 @@ class AAEEngine(object):
              ptr(val), None, self._stream())
         if self.world == 1:
             return idx, val
-        import torch.distributed as dist
         kmax = min(k, (self.V + self.world - 1) // self.world)
-        pv = torch.full((B, kmax), -3.0e38, dtype=torch.float32, device=self.dev)
-        pi = torch.full((B, kmax), -1, dtype=torch.int32, device=self.dev)
-        pv[:, :kl] = val
-        pi[:, :kl] = idx
-        gv = [torch.empty_like(pv) for _ in range(self.world)]
-        gi = [torch.empty_like(pi) for _ in range(self.world)]
-        dist.all_gather(gv, pv, group=self.group)
-        dist.all_gather(gi, pi, group=self.group)
-        cv = torch.cat(gv, 1).contiguous()
-        ci = torch.cat(gi, 1).contiguous()
+        cv, ci = gather_topk_candidates(val, idx, kmax, self.world, self.group)
         kk = min(k, self.V)
         oi = torch.empty(B, kk, dtype=torch.int32, device=self.dev)
         ov = torch.empty(B, kk, dtype=torch.float32, device=self.dev)

@@ -1,14 +1,632 @@
-// K3/K5 tensor-core variant (tcgen05 + TMEM) -- placeholder until the kernel lands.
+// K3/K5 tensor-core variant: the n_items-wide decoder output layer on tcgen05 (5th-gen tensor
+// cores, accumulators in TMEM), fp32-accurate through a 3xTF32 split.
+//
+// Per tile of TN=32 items and a batch chunk of up to 128 rows, three GEMMs share three shared-memory
+// operands (each kept as a tf32 "hi" part and an fp32 remainder "lo"; x = hi + lo exactly):
+//   G1  Z   [b,v]  = H2'[b,:] . W'[v,:]            M=128(b) N=32(v)  K=H+1    A=Hb (K-major)  B=Wb (K-major)
+//   G2  dh2 [b,k] += dZ[b,:]  . W'[:,k]            M=128(b) N=Np(k)  K=32(v)  A=Db (K-major)  B=Wb (MN-major)
+//   G3  dW'^T[k,v] = H2'[:,k] . dZ[:,v]            M=128(k) N=32(v)  K=128(b) A=Hb (MN-major) B=Db (MN-major)
+// with H2' = [h2 | 1] and W' = [Wd3 | bd3], so the bias rides inside the MMA (logit = G1, bias
+// gradient = row H of G3).  Every operand lives in the no-swizzle core-matrix layout (8 rows x 16
+// bytes contiguous per core matrix), which is simultaneously a valid K-major view (MN = row) and a
+// valid MN-major view (MN = column) of the same bytes, so no operand is stored twice.
+// Each product is issued as hi*hi + lo*hi + hi*lo (the dropped lo*lo term is 2^-22 relative).
+// Epilogues: (E1) TMEM -> registers, sigmoid + BCE + dZ exactly as the fp32 kernel (common.cuh), dZ
+// split and stored as the next MMA operand; (E2) TMEM lane = hidden unit k, so each warp reads/writes
+// 128-byte coalesced segments of W/m/v rows and applies Adam in registers.  Logits never reach HBM.
+//
+// Reference: aaerec/aae.py:176-177 (lin3 + sigmoid), :693-695 (BCE), :703 (backward), :707 (dec_optim).
 #include "common.cuh"
+
 namespace aae {
-int dec_out_train_tc(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
-                     const int32_t*, double, const aae_step_state*, float*, double*, int, cudaStream_t) {
-  set_error("dec_out_train: tensor-core kernel not built");
-  return AAE_E_UNSUPPORTED;
+namespace tc {
+
+constexpr int TN = 32;          // items per tile
+constexpr int BM = 128;         // batch rows per chunk (MMA M)
+constexpr int NT = 256;         // threads
+constexpr int CORE = 128;       // bytes of one core matrix (8 rows x 16 B)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, Blackwell version bit
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
 }
-int dec_out_scores_tc(const float*, int, int, const float*, const float*, int, int, float*, int64_t, int,
-                      cudaStream_t) {
-  set_error("dec_out_scores: tensor-core kernel not built");
-  return AAE_E_UNSUPPORTED;
+// instruction descriptor for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    if (++spins > (1u << 26)) __trap();   // a lost MMA completion must not hang the device
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// byte offset of element (r, c) in a core-matrix-tiled buffer whose row groups are `s_r` bytes apart
+__device__ __forceinline__ uint32_t core_off(int r, int c, uint32_t s_r) {
+  return (uint32_t)(r >> 3) * s_r + (uint32_t)(c >> 2) * CORE + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 3) * 4u;
+}
+// store 4 consecutive columns (one 16-byte chunk) of row r as hi / lo
+__device__ __forceinline__ void store_split4(unsigned char* hi, unsigned char* lo, int r, int cg, uint32_t s_r,
+                                             float4 x, bool with_lo) {
+  uint32_t off = (uint32_t)(r >> 3) * s_r + (uint32_t)cg * CORE + (uint32_t)(r & 7) * 16u;
+  float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+  *reinterpret_cast<float4*>(hi + off) = h;
+  if (with_lo) *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+}
+
+// One GEMM = `ksteps` k-steps x (1 or 3) tcgen05.mma.  a_step / b_step: byte advance of the start
+// address per k-step (8 tf32 along K).  `first_acc`: accumulate flag of the very first MMA.
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo,
+                                           uint32_t a_sbo, uint32_t a_step, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps, uint32_t idesc,
+                                           uint32_t first_acc, int split) {
+  uint32_t acc = first_acc;
+  for (int k = 0; k < ksteps; ++k) {
+    uint64_t ah = make_desc(a_hi + k * a_step, a_lbo, a_sbo);
+    uint64_t bh = make_desc(b_hi + k * b_step, b_lbo, b_sbo);
+    if (split == 3) {
+      uint64_t al = make_desc(a_lo + k * a_step, a_lbo, a_sbo);
+      uint64_t bl = make_desc(b_lo + k * b_step, b_lbo, b_sbo);
+      mma_tf32(d_tmem, al, bh, idesc, acc);
+      mma_tf32(d_tmem, ah, bl, idesc, 1u);
+      acc = 1u;
+    }
+    mma_tf32(d_tmem, ah, bh, idesc, acc);
+    acc = 1u;
+  }
+}
+
+struct Geom {
+  int H, Kp, Np;             // hidden, K padded to 8 (H+1 -> Kp), N of G2 padded to 16
+  uint32_t hb_sr, wb_sr, db_sr;     // row-group strides (bytes)
+  uint32_t hb_bytes, wb_bytes, db_bytes;
+};
+__host__ __device__ inline Geom make_geom(int H) {
+  Geom g;
+  g.H = H;
+  g.Kp = (H + 1 + 7) & ~7;
+  g.Np = (g.Kp + 15) & ~15;
+  g.hb_sr = (uint32_t)(g.Kp / 4) * CORE;
+  g.wb_sr = (uint32_t)(g.Np / 4) * CORE;
+  g.db_sr = (uint32_t)(TN / 4) * CORE;
+  g.hb_bytes = (BM / 8) * g.hb_sr + 1024;   // + overshoot pad: the MN-major view of G3 reads 32 column groups
+  g.wb_bytes = (TN / 8) * g.wb_sr;
+  g.db_bytes = (BM / 8) * g.db_sr;
+  return g;
+}
+__host__ __device__ inline size_t smem_bytes(const Geom& g) {
+  return 2 * (size_t)g.hb_bytes + 2 * (size_t)g.wb_bytes + 2 * (size_t)g.db_bytes + 256;
+}
+
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TM_Z = 0, TM_DW = 32, TM_DH = 64;   // column offsets: Z (32), dW'^T (32), dh2 (<=128)
+
+// H2' chunk -> Hb hi/lo (rows >= nb and columns > H are zero, column H is the ones column)
+__device__ __forceinline__ void fill_hb(unsigned char* hb_hi, unsigned char* hb_lo, const Geom& g,
+                                        const float* __restrict__ h2, int b0, int nb, bool with_lo) {
+  const int ncg = g.Kp / 4;
+  for (int q = threadIdx.x; q < BM * ncg; q += NT) {
+    int r = q / ncg, cg = q - r * ncg;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nb) {
+      int c = cg * 4;
+      if (c + 3 < g.H) x = *reinterpret_cast<const float4*>(h2 + (size_t)(b0 + r) * g.H + c);
+      else if (c == g.H) x.x = 1.0f;
+    }
+    store_split4(hb_hi, hb_lo, r, cg, g.hb_sr, x, with_lo);
+  }
+}
+
+// registers holding the next W' tile (prefetch): chunk q = tid + NT*j of the [TN x Np/4] chunk grid
+constexpr int WCH = 4;   // ceil(TN * 32 / NT) chunks per thread (Np/4 <= 32)
+__device__ __forceinline__ void load_w_regs(float4* wr, const Geom& g, const float* __restrict__ Wd3,
+                                            const float* __restrict__ bd3, int v0, int nv) {
+  const int ncg = g.Np / 4;
+#pragma unroll
+  for (int j = 0; j < WCH; ++j) {
+    int q = threadIdx.x + NT * j;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < TN * ncg) {
+      int r = q / ncg, cg = q - r * ncg;
+      if (r < nv) {
+        int c = cg * 4;
+        if (c + 3 < g.H) x = __ldcs(reinterpret_cast<const float4*>(Wd3 + (size_t)(v0 + r) * g.H + c));
+        else if (c == g.H) x.x = __ldg(bd3 + v0 + r);
+      }
+    }
+    wr[j] = x;
+  }
+}
+__device__ __forceinline__ void store_w_regs(const float4* wr, unsigned char* wb_hi, unsigned char* wb_lo,
+                                             const Geom& g, bool with_lo) {
+  const int ncg = g.Np / 4;
+#pragma unroll
+  for (int j = 0; j < WCH; ++j) {
+    int q = threadIdx.x + NT * j;
+    if (q < TN * ncg) {
+      int r = q / ncg, cg = q - r * ncg;
+      store_split4(wb_hi, wb_lo, r, cg, g.wb_sr, wr[j], with_lo);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t tile_targets(const int32_t* __restrict__ indices, int s, int e, int v0g) {
+  int lo = s, hi = e;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (indices[mid] < v0g) lo = mid + 1; else hi = mid;
+  }
+  uint32_t m = 0;
+  while (lo < e) {
+    int d = indices[lo] - v0g;
+    if (d >= TN) break;
+    m |= 1u << d;
+    ++lo;
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training kernel (B <= 128: the whole batch is one chunk, dh2 accumulates in TMEM over all tiles)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
+    const float* __restrict__ h2, int B, int H, float* __restrict__ Wd3, float* __restrict__ bd3,
+    float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
+    int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
+    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum, int split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[NT / 32];
+  const Geom g = make_geom(H);
+  unsigned char* hb_hi = smem;
+  unsigned char* hb_lo = hb_hi + g.hb_bytes;
+  unsigned char* wb_hi = hb_lo + g.hb_bytes;
+  unsigned char* wb_lo = wb_hi + g.wb_bytes;
+  unsigned char* db_hi = wb_lo + g.wb_bytes;
+  unsigned char* db_lo = db_hi + g.db_bytes;
+  const bool with_lo = (split == 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;       // TMEM lane quarter, column half
+  const int n_tiles = (Vloc + TN - 1) / TN;
+  const AdamK ak = adam_load(st, 0);
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fill_hb(hb_hi, hb_lo, g, h2, 0, B, with_lo);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  uint32_t phase = 0;
+
+  const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
+  const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 1);
+  const uint32_t idesc_g3 = make_idesc(BM, TN, 1, 1);
+  const uint32_t a_hb_hi = smem_u32(hb_hi), a_hb_lo = smem_u32(hb_lo);
+  const uint32_t a_wb_hi = smem_u32(wb_hi), a_wb_lo = smem_u32(wb_lo);
+  const uint32_t a_db_hi = smem_u32(db_hi), a_db_lo = smem_u32(db_lo);
+
+  // this thread's CSR row (E1 lane = batch row)
+  const int brow = q4 * 32 + lane;
+  int rs = 0, re = 0;
+  if (brow < B) { rs = indptr[brow]; re = indptr[brow + 1]; }
+
+  float loss_local = 0.f;
+  float4 wr[WCH];
+  int tile = blockIdx.x;
+  if (tile < n_tiles) load_w_regs(wr, g, Wd3, bd3, tile * TN, min(TN, Vloc - tile * TN));
+  bool dh_started = false;
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int v0 = tile * TN;
+    const int nv = min(TN, Vloc - v0);
+    // ---- W' tile (prefetched registers) -> operand buffers; prefetch the next tile
+    store_w_regs(wr, wb_hi, wb_lo, g, with_lo);
+    {
+      int nt = tile + gridDim.x;
+      if (nt < n_tiles) load_w_regs(wr, g, Wd3, bd3, nt * TN, min(TN, Vloc - nt * TN));
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- G1: logits
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem + TM_Z, a_hb_hi, a_hb_lo, CORE, g.hb_sr, 2 * CORE, a_wb_hi, a_wb_lo, CORE, g.wb_sr, 2 * CORE,
+                 g.Kp / 8, idesc_g1, 0u, split);
+      mma_commit(&bar_mma);
+    }
+    // targets of this tile for this thread's row while the MMAs run
+    uint32_t tmask = (brow < B) ? tile_targets(indices, rs, re, v_begin + v0) : 0u;
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- E1: sigmoid + BCE + dZ for (row brow, columns 16*half .. +15)
+    {
+      float z[16];
+      tmem_ld16(lane_addr + TM_Z + half * 16, z);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        float dz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int v = half * 16 + j4 * 4 + j;
+          float d = 0.f;
+          if (brow < B && v < nv) loss_local += bce_term(z[j4 * 4 + j], (tmask >> v) & 1u, inv_n, d);
+          dz[j] = d;
+        }
+        store_split4(db_hi, db_lo, brow, half * 4 + j4, g.db_sr, make_float4(dz[0], dz[1], dz[2], dz[3]), with_lo);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G2 (dh2 accumulates over tiles) and G3 (dW'^T)
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem + TM_DH, a_db_hi, a_db_lo, CORE, g.db_sr, 2 * CORE, a_wb_hi, a_wb_lo, g.wb_sr, CORE, g.wb_sr,
+                 TN / 8, idesc_g2, dh_started ? 1u : 0u, split);
+      issue_gemm(tmem + TM_DW, a_hb_hi, a_hb_lo, g.hb_sr, CORE, g.hb_sr, a_db_hi, a_db_lo, g.db_sr, CORE, g.db_sr,
+                 BM / 8, idesc_g3, 0u, split);
+      mma_commit(&bar_mma);
+    }
+    dh_started = true;
+    // ---- E2 operands (W, m, v of this thread's hidden unit k for 16 items) while the MMAs run
+    const int k = q4 * 32 + lane;
+    float pw[16], pm[16], pv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int v = half * 16 + j;
+      pw[j] = pm[j] = pv[j] = 0.f;
+      if (v < nv) {
+        if (k < H) {
+          size_t off = (size_t)(v0 + v) * H + k;
+          pw[j] = Wd3[off]; pm[j] = __ldcs(mW + off); pv[j] = __ldcs(vW + off);
+        } else if (k == H) {
+          pw[j] = bd3[v0 + v]; pm[j] = mb[v0 + v]; pv[j] = vb[v0 + v];
+        }
+      }
+    }
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      float gw[16];
+      tmem_ld16(lane_addr + TM_DW + half * 16, gw);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int v = half * 16 + j;
+        if (v < nv && k <= H) {
+          float p = pw[j], m = pm[j], vv = pv[j];
+          adam_update(ak, gw[j], p, m, vv);
+          if (k < H) {
+            size_t off = (size_t)(v0 + v) * H + k;
+            Wd3[off] = p; __stcs(mW + off, m); __stcs(vW + off, vv);
+          } else {
+            bd3[v0 + v] = p; mb[v0 + v] = m; vb[v0 + v] = vv;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // TMEM Z / dW and the operand buffers are free again
+  }
+  // ---- flush dh2 (lane = batch row, columns = hidden unit)
+  tc_fence_after();
+  if (dh_started) {
+    const int nchunks = g.Np / 16;
+    for (int c = half; c < nchunks; c += 2) {
+      float d[16];
+      tmem_ld16(lane_addr + TM_DH + c * 16, d);
+      if (brow < B) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int kk = c * 16 + j;
+          if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
+        }
+      }
+    }
+  }
+  float s = warp_sum(loss_local);
+  if (lane == 0) red[warp] = s;
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+    atomicAdd(loss_sum, tot);
+  }
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scores kernel (predict): out[b, v] = logit or sigmoid(logit); loops over batch chunks per tile
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* __restrict__ h2, int B, int H,
+                                                                  const float* __restrict__ Wd3,
+                                                                  const float* __restrict__ bd3, int Vloc,
+                                                                  int apply_sigmoid, float* __restrict__ out,
+                                                                  int64_t ldo, int split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const Geom g = make_geom(H);
+  unsigned char* hb_hi = smem;
+  unsigned char* hb_lo = hb_hi + g.hb_bytes;
+  unsigned char* wb_hi = hb_lo + g.hb_bytes;
+  unsigned char* wb_lo = wb_hi + g.wb_bytes;
+  const bool with_lo = (split == 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+  const int n_tiles = (Vloc + TN - 1) / TN;
+  const int n_chunks = (B + BM - 1) / BM;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 32);
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  uint32_t phase = 0;
+  const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
+  // batch chunks are the outer loop of a CTA (blockIdx.y strides over them): the H2' chunk is built once
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int b0 = chunk * BM, nb = min(BM, B - b0);
+    __syncthreads();
+    fill_hb(hb_hi, hb_lo, g, h2, b0, nb, with_lo);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int v0 = tile * TN, nv = min(TN, Vloc - v0);
+      float4 wr[WCH];
+      load_w_regs(wr, g, Wd3, bd3, v0, nv);
+      store_w_regs(wr, wb_hi, wb_lo, g, with_lo);
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
+                   CORE, g.wb_sr, 2 * CORE, g.Kp / 8, idesc_g1, 0u, split);
+        mma_commit(&bar_mma);
+      }
+      mbar_wait(&bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+      float z[16];
+      tmem_ld16(lane_addr + half * 16, z);
+      const int brow = q4 * 32 + lane;
+      if (brow < nb) {
+        float* orow = out + (size_t)(b0 + brow) * ldo + v0 + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (half * 16 + j < nv) {
+            float s = z[j];
+            if (apply_sigmoid) s = 1.0f / (1.0f + expf(-s));
+            orow[j] = s;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test kernel: one GEMM view at a time, operands filled from global, TMEM dumped to global
+//   mode 1: D[128,32]  = A[128,Kc] . Bm[32,Kc]^T            (G1 views; Kc = 104)
+//   mode 2: D[128,112] = A[128,32] . Bm[32,112]             (G2 views)
+//   mode 3: D[128,32]  = A[128,104]^T(k,b) . Bm[128,32]     (G3 views; rows k >= 104 undefined)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const float* __restrict__ A,
+                                                            const float* __restrict__ Bm, float* __restrict__ D,
+                                                            int split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const Geom g = make_geom(100);
+  unsigned char* hb_hi = smem;
+  unsigned char* hb_lo = hb_hi + g.hb_bytes;
+  unsigned char* wb_hi = hb_lo + g.hb_bytes;
+  unsigned char* wb_lo = wb_hi + g.wb_bytes;
+  unsigned char* db_hi = wb_lo + g.wb_bytes;
+  unsigned char* db_lo = db_hi + g.db_bytes;
+  const bool with_lo = (split == 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Hb <- A (modes 1, 3: [128, Kp]); Db <- A (mode 2: [128, 32]) or Bm (mode 3: [128, 32]); Wb <- Bm (modes 1, 2: [32, Np])
+  for (int q = tid; q < (int)(2 * g.hb_bytes + 2 * g.wb_bytes + 2 * g.db_bytes) / 16; q += NT)
+    reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
+  __syncthreads();
+  if (mode == 1 || mode == 3) {
+    for (int q = tid; q < BM * (g.Kp / 4); q += NT) {
+      int r = q / (g.Kp / 4), cg = q - r * (g.Kp / 4);
+      store_split4(hb_hi, hb_lo, r, cg, g.hb_sr, *reinterpret_cast<const float4*>(A + (size_t)r * g.Kp + cg * 4), with_lo);
+    }
+  }
+  if (mode == 2 || mode == 3) {
+    const float* src = (mode == 2) ? A : Bm;
+    for (int q = tid; q < BM * (TN / 4); q += NT) {
+      int r = q / (TN / 4), cg = q - r * (TN / 4);
+      store_split4(db_hi, db_lo, r, cg, g.db_sr, *reinterpret_cast<const float4*>(src + (size_t)r * TN + cg * 4), with_lo);
+    }
+  }
+  if (mode == 1 || mode == 2) {
+    int cols = (mode == 1) ? g.Kp : g.Np;
+    for (int q = tid; q < TN * (cols / 4); q += NT) {
+      int r = q / (cols / 4), cg = q - r * (cols / 4);
+      store_split4(wb_hi, wb_lo, r, cg, g.wb_sr, *reinterpret_cast<const float4*>(Bm + (size_t)r * cols + cg * 4), with_lo);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    if (mode == 1)
+      issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo), CORE,
+                 g.wb_sr, 2 * CORE, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u, split);
+    else if (mode == 2)
+      issue_gemm(tmem, smem_u32(db_hi), smem_u32(db_lo), CORE, g.db_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
+                 g.wb_sr, CORE, g.wb_sr, TN / 8, make_idesc(BM, g.Np, 0, 1), 0u, split);
+    else
+      issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), g.hb_sr, CORE, g.hb_sr, smem_u32(db_hi), smem_u32(db_lo),
+                 g.db_sr, CORE, g.db_sr, BM / 8, make_idesc(BM, TN, 1, 1), 0u, split);
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  const int ncols = (mode == 2) ? g.Np : TN;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  for (int c = half; c < ncols / 16; c += 2) {
+    float d[16];
+    tmem_ld16(lane_addr + c * 16, d);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[(size_t)(q4 * 32 + lane) * ncols + c * 16 + j] = d[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace tc
+
+static bool tc_supported(int B, int H, const char* what) {
+  if ((H & 3) != 0 || H + 1 > 128) {
+    set_error("%s: tensor-core kernel needs n_hidden %% 4 == 0 and n_hidden <= 124 (got %d); use impl=simt", what, H);
+    return false;
+  }
+  return true;
+}
+
+int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
+                     int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                     const aae_step_state* st, float* dh2, double* loss_sum, int split, cudaStream_t s) {
+  if (!tc_supported(B, H, "dec_out_train")) return AAE_E_UNSUPPORTED;
+  if (B > tc::BM) {
+    set_error("dec_out_train: tensor-core kernel handles batch <= %d (got %d); use impl=simt", tc::BM, B);
+    return AAE_E_UNSUPPORTED;
+  }
+  tc::Geom g = tc::make_geom(H);
+  size_t smem = tc::smem_bytes(g);
+  cudaError_t e = cudaFuncSetAttribute(tc::dec_out_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("dec_out_train(tc): smem %zu: %s", smem, cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
+  int grid = std::min(n_tiles, sm_count());
+  tc::dec_out_train_tc_kernel<<<grid, tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr,
+                                                          indices, (float)(1.0 / n_total), st, dh2, loss_sum, split);
+  return check_launch("dec_out_train(tc)");
+}
+
+int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
+                      float* out, int64_t ldo, int split, cudaStream_t s) {
+  if (!tc_supported(B, H, "dec_out_scores")) return AAE_E_UNSUPPORTED;
+  tc::Geom g = tc::make_geom(H);
+  size_t smem = 2 * (size_t)g.hb_bytes + 2 * (size_t)g.wb_bytes + 256;
+  cudaError_t e = cudaFuncSetAttribute(tc::dec_out_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("dec_out_scores(tc): smem %zu: %s", smem, cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
+  int n_chunks = (B + tc::BM - 1) / tc::BM;
+  int gy = std::min(n_chunks, sm_count());
+  int gx = std::max(1, std::min(n_tiles, sm_count() / gy));
+  tc::dec_out_scores_tc_kernel<<<dim3(gx, gy), tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo,
+                                                                  split);
+  return check_launch("dec_out_scores(tc)");
+}
+
 }  // namespace aae
+
+extern "C" int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int split, void* stream) {
+  using namespace aae;
+  tc::Geom g = tc::make_geom(100);
+  size_t smem = tc::smem_bytes(g);
+  cudaError_t e = cudaFuncSetAttribute(tc::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("tc_selftest: %s", cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  tc::tc_selftest_kernel<<<1, tc::NT, smem, as_stream(stream)>>>(mode, A, Bm, D, split);
+  return check_launch("tc_selftest");
+}

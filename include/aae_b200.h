@@ -185,6 +185,11 @@ int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, co
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
                    float* val_out, void* stream);
 
+/* Self-test of the tcgen05 operand views used by the tensor-core kernel (one GEMM, one CTA):
+ * mode 1: D[128,32] = A[128,104].Bm[32,104]^T; mode 2: D[128,112] = A[128,32].Bm[32,112];
+ * mode 3: D[128,32] = A[128,104]^T.Bm[128,32] (rows >= 104 undefined).  split = 3 (3xTF32) or 1. */
+int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int split, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);
