@@ -109,11 +109,38 @@ def launch_count():
     return _launches
 
 
+_timing = None   # list of (name, start_event, end_event) while timing is enabled
+
+
+def enable_timing(on=True):
+    """Per-entry-point device timing (CUDA events on the current stream) for eager, non-graph runs."""
+    global _timing
+    _timing = [] if on else None
+
+
+def timing_report():
+    """{entry point: (calls, mean microseconds)} since enable_timing(); synchronises."""
+    import torch
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in _timing or []:
+        agg.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
+    return {k: (len(v), sum(v) / len(v)) for k, v in agg.items()}
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; non-zero status raises with the library's message."""
     global _launches
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timing is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _timing.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     _launches += KERNELS.get(name, 1)
     if rc != 0:
         raise NativeError("%s failed (%d): %s" % (name, rc, last_error()))

@@ -95,10 +95,23 @@ class AAEEngine(object):
     def _pick_impl(self, impl):
         names = {"simt": 0, "fp32": 0, "tc": 1, "tc3": 1, "parity": 1, "tf32": 2, "fast": 2}
         if impl == "auto":
-            return 0
+            return -1          # resolved per batch: tensor-core kernel when the shape is inside its envelope
         if isinstance(impl, int):
             return impl
         return names[impl]
+
+    def impl_for(self, B):
+        """Decoder-output kernel for a batch of B rows: 1 = tcgen05 3xTF32 (n_hidden % 4 == 0, n_hidden <= 124;
+        training additionally needs B <= 128), 0 = fp32 CUDA cores (any shape up to n_hidden 512)."""
+        if self.impl >= 0:
+            return self.impl
+        ok = self.H % 4 == 0 and self.H <= 124
+        return 1 if (ok and B <= 128) else 0
+
+    def impl_for_scores(self):
+        if self.impl >= 0:
+            return self.impl
+        return 1 if (self.H % 4 == 0 and self.H <= 124) else 0
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -302,7 +315,7 @@ class AAEEngine(object):
              ptr(self.h2), s())
         call("aae_dec_out_train", ptr(self.h2), B, H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m), ptr(self.Wd3_v),
              ptr(self.bd3_m), ptr(self.bd3_v), lo, self.Vloc, ptr(self.indptr), ptr(self.indices), n_total, st,
-             ptr(self.dh2), ptr(self.loss_sums), self.impl, s())
+             ptr(self.dh2), ptr(self.loss_sums), self.impl_for(B), s())
         if self.world > 1:
             self._allreduce(self.dh2[:B])
             self._allreduce(self.loss_sums[:1])
@@ -399,7 +412,7 @@ class AAEEngine(object):
         """out[B, >=Vloc] <- sigmoid probabilities (reference predict) or logits of the local items."""
         self.predict_h2(B)
         call("aae_dec_out_scores", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), self.Vloc,
-             1 if apply_sigmoid else 0, ptr(out), out.stride(0), self.impl, self._stream())
+             1 if apply_sigmoid else 0, ptr(out), out.stride(0), self.impl_for_scores(), self._stream())
         return out
 
     def topk(self, B, k, scratch=None, mask_known=True):

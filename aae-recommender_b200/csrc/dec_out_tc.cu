@@ -1,19 +1,23 @@
 // K3/K5 tensor-core variant: the n_items-wide decoder output layer on tcgen05 (5th-gen tensor
 // cores, accumulators in TMEM), fp32-accurate through a 3xTF32 split.
 //
-// Per tile of TN=32 items and a batch chunk of up to 128 rows, three GEMMs share three shared-memory
-// operands (each kept as a tf32 "hi" part and an fp32 remainder "lo"; x = hi + lo exactly):
-//   G1  Z   [b,v]  = H2'[b,:] . W'[v,:]            M=128(b) N=32(v)  K=H+1    A=Hb (K-major)  B=Wb (K-major)
-//   G2  dh2 [b,k] += dZ[b,:]  . W'[:,k]            M=128(b) N=Np(k)  K=32(v)  A=Db (K-major)  B=Wb (MN-major)
-//   G3  dW'^T[k,v] = H2'[:,k] . dZ[:,v]            M=128(k) N=32(v)  K=128(b) A=Hb (MN-major) B=Db (MN-major)
+// Per tile of TN=32 items and a batch of up to 128 rows, three GEMMs (each operand kept as a tf32
+// "hi" part and an fp32 remainder "lo"; x = hi + lo exactly; products issued as hi*hi + lo*hi + hi*lo,
+// the dropped lo*lo term is 2^-22 relative):
+//   G1  Z   [b,v]  = H2'[b,:] . W'[v,:]     M=128(b) N=32(v) K=H+1   A = Hb  smem [b][k]    B = Wb  smem [v][k]
+//   G2  dh2 [b,k] += dZ[b,:]  . W'[:,k]     M=128(b) N=Np(k) K=32(v) A = dZ  TMEM (b,v)     B = Wtb smem [k][v]
+//   G3  dW'^T[k,v] = H2'[:,k] . dZ[:,v]     M=128(k) N=32(v) K=B(b)  A = H2'^T TMEM (k,b)   B = Dtb smem [v][b]
 // with H2' = [h2 | 1] and W' = [Wd3 | bd3], so the bias rides inside the MMA (logit = G1, bias
-// gradient = row H of G3).  Every operand lives in the no-swizzle core-matrix layout (8 rows x 16
-// bytes contiguous per core matrix), which is simultaneously a valid K-major view (MN = row) and a
-// valid MN-major view (MN = column) of the same bytes, so no operand is stored twice.
-// Each product is issued as hi*hi + lo*hi + hi*lo (the dropped lo*lo term is 2^-22 relative).
+// gradient = row H of G3).  tf32 operands are only usable K-major without the special 32-byte-base
+// swizzle, so every shared-memory operand is stored K-major in the no-swizzle core-matrix layout
+// (8 rows x 16 bytes per core matrix) and the two operands that would need a transposed view are
+// instead fed from TMEM (A operand of G2 and G3): dZ is written back to TMEM by the epilogue that
+// computes it, H2'^T is loaded into TMEM once per CTA.  TMEM budget (512 columns): Z 32, dW'^T 32,
+// dh2 128, dZ hi/lo 64, H2'^T hi/lo 256.
 // Epilogues: (E1) TMEM -> registers, sigmoid + BCE + dZ exactly as the fp32 kernel (common.cuh), dZ
-// split and stored as the next MMA operand; (E2) TMEM lane = hidden unit k, so each warp reads/writes
-// 128-byte coalesced segments of W/m/v rows and applies Adam in registers.  Logits never reach HBM.
+// split into hi/lo and stored to TMEM (A of G2) and transposed to shared memory (B of G3);
+// (E2) TMEM lane = hidden unit k, so each warp reads/writes 128-byte coalesced segments of W/m/v rows
+// and applies Adam in registers.  Logits never reach HBM.
 //
 // Reference: aaerec/aae.py:176-177 (lin3 + sigmoid), :693-695 (BCE), :703 (backward), :707 (dec_optim).
 #include "common.cuh"
@@ -50,6 +54,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand from TMEM (lanes = M, columns = K), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -102,6 +117,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// store 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // byte offset of element (r, c) in a core-matrix-tiled buffer whose row groups are `s_r` bytes apart
@@ -139,30 +166,57 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
   }
 }
 
+// One GEMM with the A operand in TMEM: k-step s reads A columns [8s, 8s+8).
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi,
+                                              uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
+                                              int ksteps, uint32_t idesc, uint32_t first_acc, int split) {
+  uint32_t acc = first_acc;
+  for (int k = 0; k < ksteps; ++k) {
+    uint64_t bh = make_desc(b_hi + k * b_step, b_lbo, b_sbo);
+    if (split == 3) {
+      uint64_t bl = make_desc(b_lo + k * b_step, b_lbo, b_sbo);
+      mma_tf32_ts(d_tmem, a_lo_t + 8 * k, bh, idesc, acc);
+      mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bl, idesc, 1u);
+      acc = 1u;
+    }
+    mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bh, idesc, acc);
+    acc = 1u;
+  }
+}
+
+// Shared-memory operand geometry (all K-major, no swizzle; LBO = stride between 16-byte column
+// groups along K, SBO = stride between 8-row groups along M/N).
 struct Geom {
-  int H, Kp, Np;             // hidden, K padded to 8 (H+1 -> Kp), N of G2 padded to 16
-  uint32_t hb_sr, wb_sr, db_sr;     // row-group strides (bytes)
-  uint32_t hb_bytes, wb_bytes, db_bytes;
+  int H, Kp, Np;             // hidden, K of G1 padded to 8 (H+1 -> Kp), N of G2 padded to 16
+  uint32_t hb_sbo, wb_sbo;   // Hb [128][Kp], Wb [32][Kp]: LBO = CORE
+  uint32_t wt_lbo, wt_sbo;   // Wtb [Np][32]  (rows = hidden unit, cols = item)
+  uint32_t dt_lbo, dt_sbo;   // Dtb [32][128] (rows = item, cols = batch row)
+  uint32_t hb_bytes, wb_bytes, wt_bytes, dt_bytes;
 };
 __host__ __device__ inline Geom make_geom(int H) {
   Geom g;
   g.H = H;
   g.Kp = (H + 1 + 7) & ~7;
   g.Np = (g.Kp + 15) & ~15;
-  g.hb_sr = (uint32_t)(g.Kp / 4) * CORE;
-  g.wb_sr = (uint32_t)(g.Np / 4) * CORE;
-  g.db_sr = (uint32_t)(TN / 4) * CORE;
-  g.hb_bytes = (BM / 8) * g.hb_sr + 1024;   // + overshoot pad: the MN-major view of G3 reads 32 column groups
-  g.wb_bytes = (TN / 8) * g.wb_sr;
-  g.db_bytes = (BM / 8) * g.db_sr;
+  g.hb_sbo = (uint32_t)(g.Kp / 4) * CORE;
+  g.wb_sbo = (uint32_t)(g.Kp / 4) * CORE;
+  g.wt_lbo = CORE;
+  g.wt_sbo = (TN / 4) * CORE + 16;          // +16: spreads the transposing stores over the banks
+  g.dt_lbo = CORE + 16;                     // +16: the E1 transposing stores become conflict-free
+  g.dt_sbo = (BM / 4) * g.dt_lbo;
+  g.hb_bytes = (BM / 8) * g.hb_sbo;
+  g.wb_bytes = (TN / 8) * g.wb_sbo;
+  g.wt_bytes = (uint32_t)(g.Np / 8) * g.wt_sbo;
+  g.dt_bytes = (TN / 8) * g.dt_sbo;
   return g;
 }
 __host__ __device__ inline size_t smem_bytes(const Geom& g) {
-  return 2 * (size_t)g.hb_bytes + 2 * (size_t)g.wb_bytes + 2 * (size_t)g.db_bytes + 256;
+  return 2 * ((size_t)g.hb_bytes + g.wb_bytes + g.wt_bytes + g.dt_bytes) + 256;
 }
 
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t TM_Z = 0, TM_DW = 32, TM_DH = 64;   // column offsets: Z (32), dW'^T (32), dh2 (<=128)
+constexpr uint32_t TMEM_COLS = 512;
+// TMEM column map: Z, dW'^T, dZ hi, dZ lo, dh2, H2'^T hi, H2'^T lo
+constexpr uint32_t TM_Z = 0, TM_DW = 32, TM_DZH = 64, TM_DZL = 96, TM_DH = 128, TM_HTH = 256, TM_HTL = 384;
 
 // H2' chunk -> Hb hi/lo (rows >= nb and columns > H are zero, column H is the ones column)
 __device__ __forceinline__ void fill_hb(unsigned char* hb_hi, unsigned char* hb_lo, const Geom& g,
@@ -176,15 +230,33 @@ __device__ __forceinline__ void fill_hb(unsigned char* hb_hi, unsigned char* hb_
       if (c + 3 < g.H) x = *reinterpret_cast<const float4*>(h2 + (size_t)(b0 + r) * g.H + c);
       else if (c == g.H) x.x = 1.0f;
     }
-    store_split4(hb_hi, hb_lo, r, cg, g.hb_sr, x, with_lo);
+    store_split4(hb_hi, hb_lo, r, cg, g.hb_sbo, x, with_lo);
   }
 }
+// H2'^T -> TMEM (lane = hidden unit k, column = batch row), hi and lo halves
+__device__ __forceinline__ void fill_ht_tmem(uint32_t lane_addr, int k, int half, const Geom& g,
+                                             const float* __restrict__ h2, int B, bool with_lo) {
+  for (int c = half; c < BM / 16; c += 2) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int b = c * 16 + j;
+      float x = 0.f;
+      if (b < B) x = (k < g.H) ? h2[(size_t)b * g.H + k] : (k == g.H ? 1.0f : 0.f);
+      hi[j] = tf32_hi(x);
+      lo[j] = x - hi[j];
+    }
+    tmem_st16(lane_addr + TM_HTH + c * 16, hi);
+    if (with_lo) tmem_st16(lane_addr + TM_HTL + c * 16, lo);
+  }
+  tmem_st_wait();
+}
 
-// registers holding the next W' tile (prefetch): chunk q = tid + NT*j of the [TN x Np/4] chunk grid
-constexpr int WCH = 4;   // ceil(TN * 32 / NT) chunks per thread (Np/4 <= 32)
+// registers holding the next W' tile (prefetch): chunk q = tid + NT*j of the [TN x Kp/4] chunk grid
+constexpr int WCH = 4;   // ceil(TN * 32 / NT) chunks per thread (Kp/4 <= 32)
 __device__ __forceinline__ void load_w_regs(float4* wr, const Geom& g, const float* __restrict__ Wd3,
                                             const float* __restrict__ bd3, int v0, int nv) {
-  const int ncg = g.Np / 4;
+  const int ncg = g.Kp / 4;
 #pragma unroll
   for (int j = 0; j < WCH; ++j) {
     int q = threadIdx.x + NT * j;
@@ -200,15 +272,28 @@ __device__ __forceinline__ void load_w_regs(float4* wr, const Geom& g, const flo
     wr[j] = x;
   }
 }
+// W' tile -> Wb ([v][k], G1) and, transposed, Wtb ([k][v], G2)
 __device__ __forceinline__ void store_w_regs(const float4* wr, unsigned char* wb_hi, unsigned char* wb_lo,
-                                             const Geom& g, bool with_lo) {
-  const int ncg = g.Np / 4;
+                                             unsigned char* wt_hi, unsigned char* wt_lo, const Geom& g, bool with_lo) {
+  const int ncg = g.Kp / 4;
 #pragma unroll
   for (int j = 0; j < WCH; ++j) {
     int q = threadIdx.x + NT * j;
     if (q < TN * ncg) {
       int r = q / ncg, cg = q - r * ncg;
-      store_split4(wb_hi, wb_lo, r, cg, g.wb_sr, wr[j], with_lo);
+      store_split4(wb_hi, wb_lo, r, cg, g.wb_sbo, wr[j], with_lo);
+      if (wt_hi) {
+        float x[4] = {wr[j].x, wr[j].y, wr[j].z, wr[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int k = cg * 4 + e;
+          uint32_t off = (uint32_t)(k >> 3) * g.wt_sbo + (uint32_t)(r >> 2) * g.wt_lbo + (uint32_t)(k & 7) * 16u +
+                         (uint32_t)(r & 3) * 4u;
+          float h = tf32_hi(x[e]);
+          *reinterpret_cast<float*>(wt_hi + off) = h;
+          if (with_lo) *reinterpret_cast<float*>(wt_lo + off) = x[e] - h;
+        }
+      }
     }
   }
 }
@@ -246,8 +331,10 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   unsigned char* hb_lo = hb_hi + g.hb_bytes;
   unsigned char* wb_hi = hb_lo + g.hb_bytes;
   unsigned char* wb_lo = wb_hi + g.wb_bytes;
-  unsigned char* db_hi = wb_lo + g.wb_bytes;
-  unsigned char* db_lo = db_hi + g.db_bytes;
+  unsigned char* wt_hi = wb_lo + g.wb_bytes;
+  unsigned char* wt_lo = wt_hi + g.wt_bytes;
+  unsigned char* dt_hi = wt_lo + g.wt_bytes;
+  unsigned char* dt_lo = dt_hi + g.dt_bytes;
   const bool with_lo = (split == 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, half = warp >> 2;       // TMEM lane quarter, column half
@@ -259,24 +346,27 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     mbar_init(&bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // zero the transposed W' buffers once (rows Kp..Np stay zero), build Hb
+  for (int q = tid; q < (int)(2 * g.wt_bytes) / 16; q += NT) reinterpret_cast<float4*>(wt_hi)[q] = make_float4(0, 0, 0, 0);
   fill_hb(hb_hi, hb_lo, g, h2, 0, B, with_lo);
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  const int brow = q4 * 32 + lane;                 // E1: batch row of this thread; E2: hidden unit
+  fill_ht_tmem(lane_addr, brow, half, g, h2, B, with_lo);
   uint32_t phase = 0;
 
   const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
-  const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 1);
-  const uint32_t idesc_g3 = make_idesc(BM, TN, 1, 1);
+  const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
+  const uint32_t idesc_g3 = make_idesc(BM, TN, 0, 0);
   const uint32_t a_hb_hi = smem_u32(hb_hi), a_hb_lo = smem_u32(hb_lo);
   const uint32_t a_wb_hi = smem_u32(wb_hi), a_wb_lo = smem_u32(wb_lo);
-  const uint32_t a_db_hi = smem_u32(db_hi), a_db_lo = smem_u32(db_lo);
+  const uint32_t a_wt_hi = smem_u32(wt_hi), a_wt_lo = smem_u32(wt_lo);
+  const uint32_t a_dt_hi = smem_u32(dt_hi), a_dt_lo = smem_u32(dt_lo);
+  const int ksteps_b = (B + 7) / 8;
 
-  // this thread's CSR row (E1 lane = batch row)
-  const int brow = q4 * 32 + lane;
   int rs = 0, re = 0;
   if (brow < B) { rs = indptr[brow]; re = indptr[brow + 1]; }
 
@@ -290,17 +380,18 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     const int v0 = tile * TN;
     const int nv = min(TN, Vloc - v0);
     // ---- W' tile (prefetched registers) -> operand buffers; prefetch the next tile
-    store_w_regs(wr, wb_hi, wb_lo, g, with_lo);
+    store_w_regs(wr, wb_hi, wb_lo, wt_hi, wt_lo, g, with_lo);
     {
       int nt = tile + gridDim.x;
       if (nt < n_tiles) load_w_regs(wr, g, Wd3, bd3, nt * TN, min(TN, Vloc - nt * TN));
     }
     fence_async_smem();
+    tc_fence_before();
     __syncthreads();
     // ---- G1: logits
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem + TM_Z, a_hb_hi, a_hb_lo, CORE, g.hb_sr, 2 * CORE, a_wb_hi, a_wb_lo, CORE, g.wb_sr, 2 * CORE,
+      issue_gemm(tmem + TM_Z, a_hb_hi, a_hb_lo, CORE, g.hb_sbo, 2 * CORE, a_wb_hi, a_wb_lo, CORE, g.wb_sbo, 2 * CORE,
                  g.Kp / 8, idesc_g1, 0u, split);
       mma_commit(&bar_mma);
     }
@@ -311,20 +402,24 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     tc_fence_after();
     // ---- E1: sigmoid + BCE + dZ for (row brow, columns 16*half .. +15)
     {
-      float z[16];
+      float z[16], dzh[16], dzl[16];
       tmem_ld16(lane_addr + TM_Z + half * 16, z);
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        float dz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int v = half * 16 + j4 * 4 + j;
-          float d = 0.f;
-          if (brow < B && v < nv) loss_local += bce_term(z[j4 * 4 + j], (tmask >> v) & 1u, inv_n, d);
-          dz[j] = d;
-        }
-        store_split4(db_hi, db_lo, brow, half * 4 + j4, g.db_sr, make_float4(dz[0], dz[1], dz[2], dz[3]), with_lo);
+      for (int j = 0; j < 16; ++j) {
+        int v = half * 16 + j;
+        float d = 0.f;
+        if (brow < B && v < nv) loss_local += bce_term(z[j], (tmask >> v) & 1u, inv_n, d);
+        float h = tf32_hi(d);
+        dzh[j] = h;
+        dzl[j] = d - h;
+        uint32_t off = (uint32_t)(v >> 3) * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(v & 7) * 16u +
+                       (uint32_t)(brow & 3) * 4u;
+        *reinterpret_cast<float*>(dt_hi + off) = h;
+        if (with_lo) *reinterpret_cast<float*>(dt_lo + off) = d - h;
       }
+      tmem_st16(lane_addr + TM_DZH + half * 16, dzh);
+      if (with_lo) tmem_st16(lane_addr + TM_DZL + half * 16, dzl);
+      tmem_st_wait();
     }
     fence_async_smem();
     tc_fence_before();
@@ -332,15 +427,15 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     // ---- G2 (dh2 accumulates over tiles) and G3 (dW'^T)
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem + TM_DH, a_db_hi, a_db_lo, CORE, g.db_sr, 2 * CORE, a_wb_hi, a_wb_lo, g.wb_sr, CORE, g.wb_sr,
-                 TN / 8, idesc_g2, dh_started ? 1u : 0u, split);
-      issue_gemm(tmem + TM_DW, a_hb_hi, a_hb_lo, g.hb_sr, CORE, g.hb_sr, a_db_hi, a_db_lo, g.db_sr, CORE, g.db_sr,
-                 BM / 8, idesc_g3, 0u, split);
+      issue_gemm_ts(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, a_wt_hi, a_wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo,
+                    TN / 8, idesc_g2, dh_started ? 1u : 0u, split);
+      issue_gemm_ts(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, a_dt_hi, a_dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo,
+                    ksteps_b, idesc_g3, 0u, split);
       mma_commit(&bar_mma);
     }
     dh_started = true;
     // ---- E2 operands (W, m, v of this thread's hidden unit k for 16 items) while the MMAs run
-    const int k = q4 * 32 + lane;
+    const int k = brow;
     float pw[16], pm[16], pv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -377,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
       }
     }
     tc_fence_before();
-    __syncthreads();   // TMEM Z / dW and the operand buffers are free again
+    __syncthreads();   // TMEM Z / dW / dZ and the operand buffers are free again
   }
   // ---- flush dh2 (lane = batch row, columns = hidden unit)
   tc_fence_after();
@@ -449,13 +544,13 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
       const int v0 = tile * TN, nv = min(TN, Vloc - v0);
       float4 wr[WCH];
       load_w_regs(wr, g, Wd3, bd3, v0, nv);
-      store_w_regs(wr, wb_hi, wb_lo, g, with_lo);
+      store_w_regs(wr, wb_hi, wb_lo, nullptr, nullptr, g, with_lo);
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
-                   CORE, g.wb_sr, 2 * CORE, g.Kp / 8, idesc_g1, 0u, split);
+        issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sbo, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
+                   CORE, g.wb_sbo, 2 * CORE, g.Kp / 8, idesc_g1, 0u, split);
         mma_commit(&bar_mma);
       }
       mbar_wait(&bar_mma, phase);
@@ -483,10 +578,10 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// self-test kernel: one GEMM view at a time, operands filled from global, TMEM dumped to global
-//   mode 1: D[128,32]  = A[128,Kc] . Bm[32,Kc]^T            (G1 views; Kc = 104)
-//   mode 2: D[128,112] = A[128,32] . Bm[32,112]             (G2 views)
-//   mode 3: D[128,32]  = A[128,104]^T(k,b) . Bm[128,32]     (G3 views; rows k >= 104 undefined)
+// self-test kernel: one GEMM form at a time, operands filled from global, TMEM dumped to global
+//   mode 1 (G1 form, A and B in smem):  D[128,32]  = A[128,104]      . Bm[32,104]^T
+//   mode 2 (G2 form, A in TMEM):        D[128,112] = A[128,32]       . Bm[112,32]^T
+//   mode 3 (G3 form, A in TMEM):        D[128,32]  = A[128,128]      . Bm[32,128]^T
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const float* __restrict__ A,
                                                             const float* __restrict__ Bm, float* __restrict__ D,
@@ -499,8 +594,10 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   unsigned char* hb_lo = hb_hi + g.hb_bytes;
   unsigned char* wb_hi = hb_lo + g.hb_bytes;
   unsigned char* wb_lo = wb_hi + g.wb_bytes;
-  unsigned char* db_hi = wb_lo + g.wb_bytes;
-  unsigned char* db_lo = db_hi + g.db_bytes;
+  unsigned char* wt_hi = wb_lo + g.wb_bytes;
+  unsigned char* wt_lo = wt_hi + g.wt_bytes;
+  unsigned char* dt_hi = wt_lo + g.wt_bytes;
+  unsigned char* dt_lo = dt_hi + g.dt_bytes;
   const bool with_lo = (split == 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, half = warp >> 2;
@@ -509,56 +606,67 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
     mbar_init(&bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Hb <- A (modes 1, 3: [128, Kp]); Db <- A (mode 2: [128, 32]) or Bm (mode 3: [128, 32]); Wb <- Bm (modes 1, 2: [32, Np])
-  for (int q = tid; q < (int)(2 * g.hb_bytes + 2 * g.wb_bytes + 2 * g.db_bytes) / 16; q += NT)
-    reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
-  __syncthreads();
-  if (mode == 1 || mode == 3) {
-    for (int q = tid; q < BM * (g.Kp / 4); q += NT) {
-      int r = q / (g.Kp / 4), cg = q - r * (g.Kp / 4);
-      store_split4(hb_hi, hb_lo, r, cg, g.hb_sr, *reinterpret_cast<const float4*>(A + (size_t)r * g.Kp + cg * 4), with_lo);
-    }
-  }
-  if (mode == 2 || mode == 3) {
-    const float* src = (mode == 2) ? A : Bm;
-    for (int q = tid; q < BM * (TN / 4); q += NT) {
-      int r = q / (TN / 4), cg = q - r * (TN / 4);
-      store_split4(db_hi, db_lo, r, cg, g.db_sr, *reinterpret_cast<const float4*>(src + (size_t)r * TN + cg * 4), with_lo);
-    }
-  }
-  if (mode == 1 || mode == 2) {
-    int cols = (mode == 1) ? g.Kp : g.Np;
-    for (int q = tid; q < TN * (cols / 4); q += NT) {
-      int r = q / (cols / 4), cg = q - r * (cols / 4);
-      store_split4(wb_hi, wb_lo, r, cg, g.wb_sr, *reinterpret_cast<const float4*>(Bm + (size_t)r * cols + cg * 4), with_lo);
-    }
-  }
-  fence_async_smem();
+  for (int q = tid; q < (int)(smem_bytes(g) - 256) / 16; q += NT) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
-    if (mode == 1)
-      issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo), CORE,
-                 g.wb_sr, 2 * CORE, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u, split);
-    else if (mode == 2)
-      issue_gemm(tmem, smem_u32(db_hi), smem_u32(db_lo), CORE, g.db_sr, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
-                 g.wb_sr, CORE, g.wb_sr, TN / 8, make_idesc(BM, g.Np, 0, 1), 0u, split);
+  const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  const int row = q4 * 32 + lane;
+  auto split_store = [&](unsigned char* hi, unsigned char* lo, int r, int c, uint32_t lbo, uint32_t sbo, float x) {
+    uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)(c >> 2) * lbo + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 3) * 4u;
+    float h = tf32_hi(x);
+    *reinterpret_cast<float*>(hi + off) = h;
+    if (with_lo) *reinterpret_cast<float*>(lo + off) = x - h;
+  };
+  if (mode == 1) {
+    for (int q = tid; q < BM * g.Kp; q += NT) split_store(hb_hi, hb_lo, q / g.Kp, q % g.Kp, CORE, g.hb_sbo, A[q]);
+    for (int q = tid; q < TN * g.Kp; q += NT) split_store(wb_hi, wb_lo, q / g.Kp, q % g.Kp, CORE, g.wb_sbo, Bm[q]);
+  } else {
+    const int acols = (mode == 2) ? TN : BM;
+    const uint32_t th = (mode == 2) ? TM_DZH : TM_HTH, tl = (mode == 2) ? TM_DZL : TM_HTL;
+    for (int c = half; c < acols / 16; c += 2) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = A[(size_t)row * acols + c * 16 + j];
+        hi[j] = tf32_hi(x);
+        lo[j] = x - hi[j];
+      }
+      tmem_st16(lane_addr + th + c * 16, hi);
+      if (with_lo) tmem_st16(lane_addr + tl + c * 16, lo);
+    }
+    tmem_st_wait();
+    if (mode == 2)
+      for (int q = tid; q < g.Np * TN; q += NT) split_store(wt_hi, wt_lo, q / TN, q % TN, g.wt_lbo, g.wt_sbo, Bm[q]);
     else
-      issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), g.hb_sr, CORE, g.hb_sr, smem_u32(db_hi), smem_u32(db_lo),
-                 g.db_sr, CORE, g.db_sr, BM / 8, make_idesc(BM, TN, 1, 1), 0u, split);
+      for (int q = tid; q < TN * BM; q += NT) split_store(dt_hi, dt_lo, q / BM, q % BM, g.dt_lbo, g.dt_sbo, Bm[q]);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    if (mode == 1)
+      issue_gemm(tmem + TM_Z, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sbo, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
+                 CORE, g.wb_sbo, 2 * CORE, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u, split);
+    else if (mode == 2)
+      issue_gemm_ts(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, smem_u32(wt_hi), smem_u32(wt_lo), g.wt_lbo, g.wt_sbo,
+                    2 * g.wt_lbo, TN / 8, make_idesc(BM, g.Np, 0, 0), 0u, split);
+    else
+      issue_gemm_ts(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, smem_u32(dt_hi), smem_u32(dt_lo), g.dt_lbo, g.dt_sbo,
+                    2 * g.dt_lbo, BM / 8, make_idesc(BM, TN, 0, 0), 0u, split);
     mma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
   const int ncols = (mode == 2) ? g.Np : TN;
-  const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+  const uint32_t tsrc = (mode == 1) ? TM_Z : (mode == 2 ? TM_DH : TM_DW);
   for (int c = half; c < ncols / 16; c += 2) {
     float d[16];
-    tmem_ld16(lane_addr + c * 16, d);
+    tmem_ld16(lane_addr + tsrc + c * 16, d);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) D[(size_t)(q4 * 32 + lane) * ncols + c * 16 + j] = d[j];
+    for (int j = 0; j < 16; ++j) D[(size_t)row * ncols + c * 16 + j] = d[j];
   }
   tc_fence_before();
   __syncthreads();
@@ -601,7 +709,7 @@ int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const flo
                       float* out, int64_t ldo, int split, cudaStream_t s) {
   if (!tc_supported(B, H, "dec_out_scores")) return AAE_E_UNSUPPORTED;
   tc::Geom g = tc::make_geom(H);
-  size_t smem = 2 * (size_t)g.hb_bytes + 2 * (size_t)g.wb_bytes + 256;
+  size_t smem = 2 * ((size_t)g.hb_bytes + g.wb_bytes) + 256;
   cudaError_t e = cudaFuncSetAttribute(tc::dec_out_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("dec_out_scores(tc): smem %zu: %s", smem, cudaGetErrorString(e));

@@ -241,6 +241,23 @@ def run_ours(args):
         t = torch.tensor([sec, sec_e2e], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec, sec_e2e = t.tolist()
+    if args.kernel_times and world == 1:
+        # eager (non-graph) pass with CUDA events around every entry point: warm per-kernel times
+        eng2_graph = eng.use_graph
+        eng.use_graph = False
+        eng.overlap_sweep = False
+        N.enable_timing(True)
+        for i in range(20):
+            eng.set_batch_device(*dev_batches[i % n_batches])
+            eng.train_step(B)
+        rep = N.timing_report()
+        N.enable_timing(False)
+        eng.use_graph = eng2_graph
+        eng.overlap_sweep = True
+        tot = sum(c * us for c, us in rep.values()) / 20.0
+        sys.stderr.write("per-entry-point device time per step (eager, warm): total %.1f us\n" % tot)
+        for k, (c, us) in sorted(rep.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            sys.stderr.write("  %-28s x%.1f  %8.1f us each  %5.1f%%\n" % (k, c / 20.0, us, 100 * c * us / 20.0 / tot))
     # ---------------- roofline of the dominant kernels (timed alone, on their stream) ----------------
     hbm_peak, tf_peak, peak_kind = peaks()
     Vl = eng.Vloc
@@ -251,7 +268,7 @@ def run_ours(args):
     def k3():
         call("aae_dec_out_train", ptr(eng.h2), B, H, ptr(eng.Wd3), ptr(eng.bd3), ptr(eng.Wd3_m), ptr(eng.Wd3_v),
              ptr(eng.bd3_m), ptr(eng.bd3_v), eng.v_begin, Vl, ptr(eng.indptr), ptr(eng.indices), float(B) * V, st,
-             ptr(eng.dh2), ptr(eng.loss_sums), eng.impl, eng._stream())
+             ptr(eng.dh2), ptr(eng.loss_sums), eng.impl_for(B), eng._stream())
 
     def sweep():
         call("aae_w1_sweep_untouched", ptr(eng.slot_of), 0, Vl, H, ptr(eng.W1t), ptr(eng.W1_m1), ptr(eng.W1_v1),
@@ -290,7 +307,7 @@ def run_ours(args):
                                "n_hidden %d, n_code %d, dropout (.2,.2) in-kernel Philox, dense-Adam-equivalent W1 "
                                "policy; one partial_fit (ae+disc+gen) per step" % (args.workload, V, B, nnz_mean / B, H, C),
                    "parallelism": "item-sharded x%d" % world if world > 1 else "single GPU",
-                   "decoder_kernel": {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[eng.impl],
+                   "decoder_kernel": {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[eng.impl_for(B)],
                    "cuda_graph": eng.use_graph,
                    "l2": "per-step working set %.2f GB >> 126 MB L2 (no flush needed)" % (64.0 * Vl * H / 1e9)},
         "e2e": {"value": B * K / sec_e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 12,
@@ -315,6 +332,7 @@ def main():
     ap.add_argument("--kernel", default="auto", help="decoder-output kernel: auto|simt|tc|tf32")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--kernel-times", action="store_true", help="print warm per-kernel device times to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

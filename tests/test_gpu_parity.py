@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-4      # stated tolerance of the north star: 1e-4 relative on losses ...
 WEIGHT_RTOL = 1e-4    # ... and on every weight tensor (relative Frobenius norm) after N steps
-IMPLS = ["simt"]
+IMPLS = ["simt", "tc"]
 
 
 def _make_model(g, impl, **kw):

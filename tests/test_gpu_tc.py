@@ -24,17 +24,17 @@ def test_tc_operand_views(split, tol):
     D = _selftest(1, A.cuda(), Bm.cuda(), (128, 32), split)
     want = A.double() @ Bm.double().t()
     assert (D - want).abs().max() / want.abs().max() < tol
-    # mode 2: K-major A [128,32], MN-major B [32 (K), 112 (N)]
+    # mode 2 (G2 form): A [128,32] from TMEM, B [112,32] K-major in smem with padded strides
     A = torch.randn(128, 32, generator=g)
-    Bm = torch.randn(32, 112, generator=g)
+    Bm = torch.randn(112, 32, generator=g)
     D = _selftest(2, A.cuda(), Bm.cuda(), (128, 112), split)
-    want = A.double() @ Bm.double()
+    want = A.double() @ Bm.double().t()
     assert (D - want).abs().max() / want.abs().max() < tol
-    # mode 3: MN-major A [128 (K=b), 104 (M=k)], MN-major B [128 (K=b), 32 (N=v)]
-    A = torch.randn(128, 104, generator=g)
-    Bm = torch.randn(128, 32, generator=g)
-    D = _selftest(3, A.cuda(), Bm.cuda(), (128, 32), split)[:104]
-    want = A.double().t() @ Bm.double()
+    # mode 3 (G3 form): A [128,128] from TMEM, B [32,128] K-major in smem with padded strides
+    A = torch.randn(128, 128, generator=g)
+    Bm = torch.randn(32, 128, generator=g)
+    D = _selftest(3, A.cuda(), Bm.cuda(), (128, 32), split)
+    want = A.double() @ Bm.double().t()
     assert (D - want).abs().max() / want.abs().max() < tol
 
 
