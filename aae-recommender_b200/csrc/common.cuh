@@ -40,18 +40,25 @@ __device__ __forceinline__ AdamK adam_load(const aae_step_state* st, int which) 
   k.inv_bc2_sqrt = 1.0f / st->bc2_sqrt;
   return k;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));   // max relative error 2^-23
+  return r;
+}
+// m/denom uses the 2-ulp fast division, sqrt the approximate instruction: both far inside the 1e-4
+// parity tolerance (the update is lr * O(1)), and they keep the fused epilogues off the slow paths.
 __device__ __forceinline__ void adam_update(const AdamK& k, float g, float& p, float& m, float& v) {
   m = fmaf(k.w1, g - m, m);
-  v = v * k.beta2 + (k.w2 * g) * g;
-  float denom = sqrtf(v) * k.inv_bc2_sqrt + k.eps;
-  p = p - k.step_size * (m / denom);
+  v = fmaf(k.w2 * g, g, v * k.beta2);
+  float denom = fmaf(sqrt_approx(v), k.inv_bc2_sqrt, k.eps);
+  p = fmaf(-k.step_size, __fdividef(m, denom), p);
 }
 // zero-gradient update (rows that are not in the batch)
 __device__ __forceinline__ void adam_update_zero(const AdamK& k, float& p, float& m, float& v) {
   m = fmaf(k.w1, -m, m);
   v = v * k.beta2;
-  float denom = sqrtf(v) * k.inv_bc2_sqrt + k.eps;
-  p = p - k.step_size * (m / denom);
+  float denom = fmaf(sqrt_approx(v), k.inv_bc2_sqrt, k.eps);
+  p = fmaf(-k.step_size, __fdividef(m, denom), p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,25 +108,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float bce_term(float z, bool positive, float inv_n, float& dz) {
   // stable sigmoid: u = exp(-|z|), x = 1/(1+u) or u/(1+u)  (ATen: 1/(1+exp(-z)); same to ~1 ulp)
   float u = __expf(-fabsf(z));
-  float r = 1.0f / (1.0f + u);
+  float r = __fdividef(1.0f, 1.0f + u);
   float x = (z >= 0.f) ? r : u * r;
   float xp = x + 1e-12f;
   float om = 1.0f - xp;
-  float l;
-  if (positive) {
+  // -log1p(-x) = softplus(z) = max(z,0) + log1p(u); x' rounded to 1 -> log1p(-1) = -inf, clamped at
+  // -100 by ATen.  (The reference's extra 1e-12*log(x') term, <= 1e-10, is dropped.)
+  float poly = u * (1.0f - u * (0.5f - u * (0.33333334f - u * (0.25f - 0.2f * u))));
+  float l1p = (u < 0.0625f) ? poly : __logf(1.0f + u);
+  float l = fminf(fmaxf(z, 0.f) + l1p, 100.0f);
+  l = (om <= 0.f) ? 100.0f : l;
+  float t = 1e-12f;
+  if (positive) {           // rare: the few items of the set that fall into this tile
     l = fminf(-__logf(xp), 100.0f);
-  } else if (om <= 0.f) {
-    l = 100.0f;  // x' rounded to 1: log1p(-1) = -inf, clamped at -100 by ATen
-  } else {
-    // -log1p(-x) = softplus(z) = max(z,0) + log1p(u).  (The reference's extra 1e-12*log(x') term,
-    // <= 1e-10, is dropped.)
-    float l1p = (u < 0.0625f) ? u * (1.0f - u * (0.5f - u * (0.33333334f - u * (0.25f - 0.2f * u))))
-                              : __logf(1.0f + u);
-    l = fminf(fmaxf(z, 0.f) + l1p, 100.0f);
+    t = 1.0f;
   }
-  float t = positive ? 1.0f : 1e-12f;
   float den = fmaxf(om * xp, 1e-12f);
-  dz = (xp - t) / den * (x * (1.0f - x)) * inv_n;
+  dz = __fdividef((xp - t) * (x * (1.0f - x)), den) * inv_n;
   return l;
 }
 

@@ -27,7 +27,8 @@ namespace tc {
 
 constexpr int TN = 32;          // items per tile
 constexpr int BM = 128;         // batch rows per chunk (MMA M)
-constexpr int NT = 256;         // threads
+constexpr int NT = 512;         // threads: 16 warps = 4 TMEM lane quarters x 4 column parts
+constexpr int CW = 8;           // accumulator columns per thread in the epilogues
 constexpr int CORE = 128;       // bytes of one core matrix (8 rows x 16 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +91,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,6 +141,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // byte offset of element (r, c) in a core-matrix-tiled buffer whose row groups are `s_r` bytes apart
@@ -144,43 +173,57 @@ __device__ __forceinline__ void store_split4(unsigned char* hi, unsigned char* l
   if (with_lo) *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
 }
 
-// One GEMM = `ksteps` k-steps x (1 or 3) tcgen05.mma.  a_step / b_step: byte advance of the start
-// address per k-step (8 tf32 along K).  `first_acc`: accumulate flag of the very first MMA.
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo,
-                                           uint32_t a_sbo, uint32_t a_step, uint32_t b_hi, uint32_t b_lo,
-                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps, uint32_t idesc,
-                                           uint32_t first_acc, int split) {
-  uint32_t acc = first_acc;
-  for (int k = 0; k < ksteps; ++k) {
-    uint64_t ah = make_desc(a_hi + k * a_step, a_lbo, a_sbo);
-    uint64_t bh = make_desc(b_hi + k * b_step, b_lbo, b_sbo);
-    if (split == 3) {
-      uint64_t al = make_desc(a_lo + k * a_step, a_lbo, a_sbo);
-      uint64_t bl = make_desc(b_lo + k * b_step, b_lbo, b_sbo);
-      mma_tf32(d_tmem, al, bh, idesc, acc);
-      mma_tf32(d_tmem, ah, bl, idesc, 1u);
-      acc = 1u;
+// Descriptors of one operand (hi and lo parts) with the per-k-step increment of the start-address
+// field (units of 16 bytes); built once per kernel.
+struct SmemOp {
+  uint64_t hi, lo;
+  uint32_t step16;
+};
+__device__ __forceinline__ SmemOp make_op(const void* hi, const void* lo, uint32_t lbo, uint32_t sbo, uint32_t step) {
+  SmemOp o;
+  o.hi = make_desc(smem_u32(hi), lbo, sbo);
+  o.lo = make_desc(smem_u32(lo), lbo, sbo);
+  o.step16 = step >> 4;
+  return o;
+}
+// One GEMM, both operands in shared memory: up to 16 k-steps x (1 or 3) tcgen05.mma.  Fully unrolled with a
+// warp-uniform bound so that the descriptor arithmetic stays on constants (the issuing lane executes a few
+// instructions per MMA instead of rebuilding descriptors).
+template <int SPLIT>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const SmemOp& a, const SmemOp& b, int ksteps,
+                                           uint32_t idesc, uint32_t first_acc) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k < ksteps) {
+      const uint32_t acc = (k == 0) ? first_acc : 1u;
+      const uint64_t ah = a.hi + (uint64_t)(k * a.step16), bh = b.hi + (uint64_t)(k * b.step16);
+      if (SPLIT == 3) {
+        mma_tf32(d_tmem, a.lo + (uint64_t)(k * a.step16), bh, idesc, acc);
+        mma_tf32(d_tmem, ah, b.lo + (uint64_t)(k * b.step16), idesc, 1u);
+        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+      } else {
+        mma_tf32(d_tmem, ah, bh, idesc, acc);
+      }
     }
-    mma_tf32(d_tmem, ah, bh, idesc, acc);
-    acc = 1u;
   }
 }
-
 // One GEMM with the A operand in TMEM: k-step s reads A columns [8s, 8s+8).
-__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi,
-                                              uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
-                                              int ksteps, uint32_t idesc, uint32_t first_acc, int split) {
-  uint32_t acc = first_acc;
-  for (int k = 0; k < ksteps; ++k) {
-    uint64_t bh = make_desc(b_hi + k * b_step, b_lbo, b_sbo);
-    if (split == 3) {
-      uint64_t bl = make_desc(b_lo + k * b_step, b_lbo, b_sbo);
-      mma_tf32_ts(d_tmem, a_lo_t + 8 * k, bh, idesc, acc);
-      mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bl, idesc, 1u);
-      acc = 1u;
+template <int SPLIT>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, const SmemOp& b,
+                                              int ksteps, uint32_t idesc, uint32_t first_acc) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k < ksteps) {
+      const uint32_t acc = (k == 0) ? first_acc : 1u;
+      const uint64_t bh = b.hi + (uint64_t)(k * b.step16);
+      if (SPLIT == 3) {
+        mma_tf32_ts(d_tmem, a_lo_t + 8 * k, bh, idesc, acc);
+        mma_tf32_ts(d_tmem, a_hi_t + 8 * k, b.lo + (uint64_t)(k * b.step16), idesc, 1u);
+        mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bh, idesc, 1u);
+      } else {
+        mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bh, idesc, acc);
+      }
     }
-    mma_tf32_ts(d_tmem, a_hi_t + 8 * k, bh, idesc, acc);
-    acc = 1u;
   }
 }
 
@@ -200,8 +243,8 @@ __host__ __device__ inline Geom make_geom(int H) {
   g.Np = (g.Kp + 15) & ~15;
   g.hb_sbo = (uint32_t)(g.Kp / 4) * CORE;
   g.wb_sbo = (uint32_t)(g.Kp / 4) * CORE;
-  g.wt_lbo = CORE;
-  g.wt_sbo = (TN / 4) * CORE + 16;          // +16: spreads the transposing stores over the banks
+  g.wt_lbo = CORE + 16;                     // +16: the transposing stores of the W' tile are conflict-free
+  g.wt_sbo = (TN / 4) * g.wt_lbo;
   g.dt_lbo = CORE + 16;                     // +16: the E1 transposing stores become conflict-free
   g.dt_sbo = (BM / 4) * g.dt_lbo;
   g.hb_bytes = (BM / 8) * g.hb_sbo;
@@ -234,82 +277,96 @@ __device__ __forceinline__ void fill_hb(unsigned char* hb_hi, unsigned char* hb_
   }
 }
 // H2'^T -> TMEM (lane = hidden unit k, column = batch row), hi and lo halves
-__device__ __forceinline__ void fill_ht_tmem(uint32_t lane_addr, int k, int half, const Geom& g,
+__device__ __forceinline__ void fill_ht_tmem(uint32_t lane_addr, int k, int cpart, const Geom& g,
                                              const float* __restrict__ h2, int B, bool with_lo) {
-  for (int c = half; c < BM / 16; c += 2) {
-    float hi[16], lo[16];
+  for (int c = cpart; c < BM / CW; c += NT / 128) {
+    float hi[CW], lo[CW];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      int b = c * 16 + j;
+    for (int j = 0; j < CW; ++j) {
+      int b = c * CW + j;
       float x = 0.f;
       if (b < B) x = (k < g.H) ? h2[(size_t)b * g.H + k] : (k == g.H ? 1.0f : 0.f);
       hi[j] = tf32_hi(x);
       lo[j] = x - hi[j];
     }
-    tmem_st16(lane_addr + TM_HTH + c * 16, hi);
-    if (with_lo) tmem_st16(lane_addr + TM_HTL + c * 16, lo);
+    tmem_st8(lane_addr + TM_HTH + c * CW, hi);
+    if (with_lo) tmem_st8(lane_addr + TM_HTL + c * CW, lo);
   }
   tmem_st_wait();
 }
 
-// registers holding the next W' tile (prefetch): chunk q = tid + NT*j of the [TN x Kp/4] chunk grid
-constexpr int WCH = 4;   // ceil(TN * 32 / NT) chunks per thread (Kp/4 <= 32)
-__device__ __forceinline__ void load_w_regs(float4* wr, const Geom& g, const float* __restrict__ Wd3,
-                                            const float* __restrict__ bd3, int v0, int nv) {
+// This thread's share of the W' tile: lane = item row r, warp w owns the 16-byte column groups cg = w and
+// w + 16 (Kp/4 <= 32): with this mapping both the K-major store into Wb and the transposing store into Wtb
+// are bank-conflict free; all index arithmetic is tile-invariant and done once.
+constexpr int WCH = 2;
+struct WChunk {
+  int goff;            // float offset inside the tile's rows of Wd3 (r*H + 4cg); -1 bias column, -2 unused, -3 zero pad
+  uint32_t wb_off;     // byte offset in Wb (16-byte chunk)
+  uint32_t wt_off;     // byte offset in Wtb of element 0 (elements e at +16e)
+};
+__device__ __forceinline__ void make_wchunks(WChunk* wc, const Geom& g) {
   const int ncg = g.Kp / 4;
+  const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < WCH; ++j) {
-    int q = threadIdx.x + NT * j;
+    int cg = w + 16 * j;
+    wc[j].goff = -2;
+    if (cg < ncg) {
+      int c = cg * 4;
+      wc[j].goff = (c + 3 < g.H) ? r * g.H + c : (c == g.H ? -1 : -3);
+    }
+    wc[j].wb_off = (uint32_t)(r >> 3) * g.wb_sbo + (uint32_t)cg * CORE + (uint32_t)(r & 7) * 16u;
+    wc[j].wt_off = (uint32_t)(cg >> 1) * g.wt_sbo + (uint32_t)(r >> 2) * g.wt_lbo + (uint32_t)(cg & 1) * 64u +
+                   (uint32_t)(r & 3) * 4u;
+  }
+}
+__device__ __forceinline__ void load_w_regs(float4* wr, const WChunk* wc, const float* __restrict__ Wd3,
+                                            const float* __restrict__ bd3, int H, int v0, int nv) {
+  const int r = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < WCH; ++j) {
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < TN * ncg) {
-      int r = q / ncg, cg = q - r * ncg;
-      if (r < nv) {
-        int c = cg * 4;
-        if (c + 3 < g.H) x = __ldcs(reinterpret_cast<const float4*>(Wd3 + (size_t)(v0 + r) * g.H + c));
-        else if (c == g.H) x.x = __ldg(bd3 + v0 + r);
-      }
+    if (r < nv) {
+      if (wc[j].goff >= 0) x = __ldcs(reinterpret_cast<const float4*>(Wd3 + (size_t)v0 * H + wc[j].goff));
+      else if (wc[j].goff == -1) x.x = __ldg(bd3 + v0 + r);
     }
     wr[j] = x;
   }
 }
 // W' tile -> Wb ([v][k], G1) and, transposed, Wtb ([k][v], G2)
-__device__ __forceinline__ void store_w_regs(const float4* wr, unsigned char* wb_hi, unsigned char* wb_lo,
-                                             unsigned char* wt_hi, unsigned char* wt_lo, const Geom& g, bool with_lo) {
-  const int ncg = g.Kp / 4;
+__device__ __forceinline__ void store_w_regs(const float4* wr, const WChunk* wc, unsigned char* wb_hi,
+                                             unsigned char* wb_lo, unsigned char* wt_hi, unsigned char* wt_lo,
+                                             bool with_lo) {
 #pragma unroll
   for (int j = 0; j < WCH; ++j) {
-    int q = threadIdx.x + NT * j;
-    if (q < TN * ncg) {
-      int r = q / ncg, cg = q - r * ncg;
-      store_split4(wb_hi, wb_lo, r, cg, g.wb_sbo, wr[j], with_lo);
-      if (wt_hi) {
-        float x[4] = {wr[j].x, wr[j].y, wr[j].z, wr[j].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int k = cg * 4 + e;
-          uint32_t off = (uint32_t)(k >> 3) * g.wt_sbo + (uint32_t)(r >> 2) * g.wt_lbo + (uint32_t)(k & 7) * 16u +
-                         (uint32_t)(r & 3) * 4u;
-          float h = tf32_hi(x[e]);
-          *reinterpret_cast<float*>(wt_hi + off) = h;
-          if (with_lo) *reinterpret_cast<float*>(wt_lo + off) = x[e] - h;
-        }
+    if (wc[j].goff == -2) continue;
+    float4 x = wr[j];
+    float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+    *reinterpret_cast<float4*>(wb_hi + wc[j].wb_off) = h;
+    if (with_lo) *reinterpret_cast<float4*>(wb_lo + wc[j].wb_off) = l;
+    if (wt_hi) {
+      float* th = reinterpret_cast<float*>(wt_hi + wc[j].wt_off);
+      th[0] = h.x; th[4] = h.y; th[8] = h.z; th[12] = h.w;
+      if (with_lo) {
+        float* tl = reinterpret_cast<float*>(wt_lo + wc[j].wt_off);
+        tl[0] = l.x; tl[4] = l.y; tl[8] = l.z; tl[12] = l.w;
       }
     }
   }
 }
 
-__device__ __forceinline__ uint32_t tile_targets(const int32_t* __restrict__ indices, int s, int e, int v0g) {
-  int lo = s, hi = e;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (indices[mid] < v0g) lo = mid + 1; else hi = mid;
-  }
+// Positives of a tile for one batch row, from a cursor into the row's sorted CSR columns (tiles are
+// visited in increasing item order, so the cursor only moves forward; `nxt` caches indices[pos]).
+struct RowCursor {
+  int pos, end, nxt;
+};
+__device__ __forceinline__ uint32_t tile_targets(RowCursor& c, const int32_t* __restrict__ indices, int v0g) {
   uint32_t m = 0;
-  while (lo < e) {
-    int d = indices[lo] - v0g;
-    if (d >= TN) break;
-    m |= 1u << d;
-    ++lo;
+  while (c.nxt < v0g + TN) {
+    if (c.nxt >= v0g) m |= 1u << (c.nxt - v0g);
+    ++c.pos;
+    c.nxt = (c.pos < c.end) ? indices[c.pos] : 0x7fffffff;
   }
   return m;
 }
@@ -317,15 +374,17 @@ __device__ __forceinline__ uint32_t tile_targets(const int32_t* __restrict__ ind
 // ---------------------------------------------------------------------------------------------
 // training kernel (B <= 128: the whole batch is one chunk, dh2 accumulates in TMEM over all tiles)
 // ---------------------------------------------------------------------------------------------
+template <int SPLIT>
 __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     const float* __restrict__ h2, int B, int H, float* __restrict__ Wd3, float* __restrict__ bd3,
     float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
     int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
-    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum, int split) {
+    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_mma;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[NT / 32];
+  constexpr int split = SPLIT;
   const Geom g = make_geom(H);
   unsigned char* hb_hi = smem;
   unsigned char* hb_lo = hb_hi + g.hb_bytes;
@@ -337,7 +396,7 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   unsigned char* dt_lo = dt_hi + g.dt_bytes;
   const bool with_lo = (split == 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, half = warp >> 2;       // TMEM lane quarter, column half
+  const int q4 = warp & 3, cpart = warp >> 2;      // TMEM lane quarter, 8-column part of the 32-wide tile
   const int n_tiles = (Vloc + TN - 1) / TN;
   const AdamK ak = adam_load(st, 0);
 
@@ -355,91 +414,72 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   const uint32_t tmem = tmem_base_s;
   const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
   const int brow = q4 * 32 + lane;                 // E1: batch row of this thread; E2: hidden unit
-  fill_ht_tmem(lane_addr, brow, half, g, h2, B, with_lo);
+  fill_ht_tmem(lane_addr, brow, cpart, g, h2, B, with_lo);
   uint32_t phase = 0;
 
   const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
   const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
-  const uint32_t idesc_g3 = make_idesc(BM, TN, 0, 0);
-  const uint32_t a_hb_hi = smem_u32(hb_hi), a_hb_lo = smem_u32(hb_lo);
-  const uint32_t a_wb_hi = smem_u32(wb_hi), a_wb_lo = smem_u32(wb_lo);
-  const uint32_t a_wt_hi = smem_u32(wt_hi), a_wt_lo = smem_u32(wt_lo);
-  const uint32_t a_dt_hi = smem_u32(dt_hi), a_dt_lo = smem_u32(dt_lo);
+  const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
+  const SmemOp op_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
+  const SmemOp op_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
+  const SmemOp op_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
   const int ksteps_b = (B + 7) / 8;
+  // E1 transposing-store base of this thread: element (v = 8*cpart + j, b = brow) at +16j
+  const uint32_t dt_off = (uint32_t)cpart * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
 
-  int rs = 0, re = 0;
-  if (brow < B) { rs = indptr[brow]; re = indptr[brow + 1]; }
+  RowCursor cur;
+  cur.pos = cur.end = 0;
+  cur.nxt = 0x7fffffff;
+  if (brow < B) {
+    cur.pos = indptr[brow];
+    cur.end = indptr[brow + 1];
+    // first tile of this CTA: skip the row's items below it
+    int first = v_begin + (int)blockIdx.x * TN;
+    while (cur.pos < cur.end && indices[cur.pos] < first) ++cur.pos;
+    if (cur.pos < cur.end) cur.nxt = indices[cur.pos];
+  }
 
+  WChunk wc[WCH];
+  make_wchunks(wc, g);
   float loss_local = 0.f;
   float4 wr[WCH];
   int tile = blockIdx.x;
-  if (tile < n_tiles) load_w_regs(wr, g, Wd3, bd3, tile * TN, min(TN, Vloc - tile * TN));
+  if (tile < n_tiles) load_w_regs(wr, wc, Wd3, bd3, H, tile * TN, min(TN, Vloc - tile * TN));
   bool dh_started = false;
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const int v0 = tile * TN;
     const int nv = min(TN, Vloc - v0);
     // ---- W' tile (prefetched registers) -> operand buffers; prefetch the next tile
-    store_w_regs(wr, wb_hi, wb_lo, wt_hi, wt_lo, g, with_lo);
+    store_w_regs(wr, wc, wb_hi, wb_lo, wt_hi, wt_lo, with_lo);
     {
       int nt = tile + gridDim.x;
-      if (nt < n_tiles) load_w_regs(wr, g, Wd3, bd3, nt * TN, min(TN, Vloc - nt * TN));
+      if (nt < n_tiles) load_w_regs(wr, wc, Wd3, bd3, H, nt * TN, min(TN, Vloc - nt * TN));
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     // ---- G1: logits
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      issue_gemm(tmem + TM_Z, a_hb_hi, a_hb_lo, CORE, g.hb_sbo, 2 * CORE, a_wb_hi, a_wb_lo, CORE, g.wb_sbo, 2 * CORE,
-                 g.Kp / 8, idesc_g1, 0u, split);
-      mma_commit(&bar_mma);
-    }
-    // targets of this tile for this thread's row while the MMAs run
-    uint32_t tmask = (brow < B) ? tile_targets(indices, rs, re, v_begin + v0) : 0u;
-    mbar_wait(&bar_mma, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- E1: sigmoid + BCE + dZ for (row brow, columns 16*half .. +15)
-    {
-      float z[16], dzh[16], dzl[16];
-      tmem_ld16(lane_addr + TM_Z + half * 16, z);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        int v = half * 16 + j;
-        float d = 0.f;
-        if (brow < B && v < nv) loss_local += bce_term(z[j], (tmask >> v) & 1u, inv_n, d);
-        float h = tf32_hi(d);
-        dzh[j] = h;
-        dzl[j] = d - h;
-        uint32_t off = (uint32_t)(v >> 3) * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(v & 7) * 16u +
-                       (uint32_t)(brow & 3) * 4u;
-        *reinterpret_cast<float*>(dt_hi + off) = h;
-        if (with_lo) *reinterpret_cast<float*>(dt_lo + off) = d - h;
+      if (elect_one()) {
+        issue_gemm<SPLIT>(tmem + TM_Z, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
+        mma_commit(&bar_mma);
       }
-      tmem_st16(lane_addr + TM_DZH + half * 16, dzh);
-      if (with_lo) tmem_st16(lane_addr + TM_DZL + half * 16, dzl);
-      tmem_st_wait();
+      __syncwarp();
     }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- G2 (dh2 accumulates over tiles) and G3 (dW'^T)
-    if (tid == 0) {
-      tc_fence_after();
-      issue_gemm_ts(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, a_wt_hi, a_wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo,
-                    TN / 8, idesc_g2, dh_started ? 1u : 0u, split);
-      issue_gemm_ts(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, a_dt_hi, a_dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo,
-                    ksteps_b, idesc_g3, 0u, split);
-      mma_commit(&bar_mma);
+    // targets of this tile for this thread's row, and the E2 operands, while the MMAs run
+    // skip items of the tiles other CTAs own, then collect this tile's positives
+    while (cur.nxt < v_begin + v0) {
+      ++cur.pos;
+      cur.nxt = (cur.pos < cur.end) ? indices[cur.pos] : 0x7fffffff;
     }
-    dh_started = true;
-    // ---- E2 operands (W, m, v of this thread's hidden unit k for 16 items) while the MMAs run
+    uint32_t tmask = tile_targets(cur, indices, v_begin + v0);
     const int k = brow;
-    float pw[16], pm[16], pv[16];
+    float pw[CW], pm[CW], pv[CW];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      int v = half * 16 + j;
+    for (int j = 0; j < CW; ++j) {
+      int v = cpart * CW + j;
       pw[j] = pm[j] = pv[j] = 0.f;
       if (v < nv) {
         if (k < H) {
@@ -453,12 +493,49 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
     mbar_wait(&bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
+    // ---- E1: sigmoid + BCE + dZ for (row brow, columns 8*cpart .. +7)
     {
-      float gw[16];
-      tmem_ld16(lane_addr + TM_DW + half * 16, gw);
+      float z[CW], dzh[CW], dzl[CW];
+      tmem_ld8(lane_addr + TM_Z + cpart * CW, z);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        int v = half * 16 + j;
+      for (int j = 0; j < CW; ++j) {
+        int v = cpart * CW + j;
+        float d = 0.f;
+        if (brow < B && v < nv) loss_local += bce_term(z[j], (tmask >> v) & 1u, inv_n, d);
+        float h = tf32_hi(d);
+        dzh[j] = h;
+        dzl[j] = d - h;
+        *reinterpret_cast<float*>(dt_hi + dt_off + 16 * j) = h;
+        if (with_lo) *reinterpret_cast<float*>(dt_lo + dt_off + 16 * j) = d - h;
+      }
+      tmem_st8(lane_addr + TM_DZH + cpart * CW, dzh);
+      if (with_lo) tmem_st8(lane_addr + TM_DZL + cpart * CW, dzl);
+      tmem_st_wait();
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G2 (dh2 accumulates over tiles) and G3 (dW'^T)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm_ts<SPLIT>(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, op_dt, ksteps_b, idesc_g1, 0u);
+        issue_gemm_ts<SPLIT>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, op_wt, TN / 8, idesc_g2, dh_started ? 1u : 0u);
+        mma_commit(&bar_mma);
+      }
+      __syncwarp();
+    }
+    dh_started = true;
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- E2: Adam on (hidden unit k, items 8*cpart .. +7): coalesced over k
+    {
+      float gw[CW];
+      tmem_ld8(lane_addr + TM_DW + cpart * CW, gw);
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        int v = cpart * CW + j;
         if (v < nv && k <= H) {
           float p = pw[j], m = pm[j], vv = pv[j];
           adam_update(ak, gw[j], p, m, vv);
@@ -477,14 +554,13 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   // ---- flush dh2 (lane = batch row, columns = hidden unit)
   tc_fence_after();
   if (dh_started) {
-    const int nchunks = g.Np / 16;
-    for (int c = half; c < nchunks; c += 2) {
-      float d[16];
-      tmem_ld16(lane_addr + TM_DH + c * 16, d);
+    for (int c = cpart; c < g.Np / CW; c += NT / 128) {
+      float d[CW];
+      tmem_ld8(lane_addr + TM_DH + c * CW, d);
       if (brow < B) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int kk = c * 16 + j;
+        for (int j = 0; j < CW; ++j) {
+          int kk = c * CW + j;
           if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
         }
       }
@@ -505,11 +581,13 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
 // ---------------------------------------------------------------------------------------------
 // scores kernel (predict): out[b, v] = logit or sigmoid(logit); loops over batch chunks per tile
 // ---------------------------------------------------------------------------------------------
+template <int SPLIT>
 __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* __restrict__ h2, int B, int H,
                                                                   const float* __restrict__ Wd3,
                                                                   const float* __restrict__ bd3, int Vloc,
                                                                   int apply_sigmoid, float* __restrict__ out,
-                                                                  int64_t ldo, int split) {
+                                                                  int64_t ldo) {
+  constexpr int split = SPLIT;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_mma;
   __shared__ uint32_t tmem_base_s;
@@ -520,7 +598,7 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
   unsigned char* wb_lo = wb_hi + g.wb_bytes;
   const bool with_lo = (split == 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, half = warp >> 2;
+  const int q4 = warp & 3, cpart = warp >> 2;
   const int n_tiles = (Vloc + TN - 1) / TN;
   const int n_chunks = (B + BM - 1) / BM;
   if (warp == 0) tmem_alloc(&tmem_base_s, 32);
@@ -535,6 +613,10 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
   const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
   uint32_t phase = 0;
   const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
+  const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
+  const SmemOp op_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
+  WChunk wc[WCH];
+  make_wchunks(wc, g);
   // batch chunks are the outer loop of a CTA (blockIdx.y strides over them): the H2' chunk is built once
   for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
     const int b0 = chunk * BM, nb = min(BM, B - b0);
@@ -543,27 +625,29 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int v0 = tile * TN, nv = min(TN, Vloc - v0);
       float4 wr[WCH];
-      load_w_regs(wr, g, Wd3, bd3, v0, nv);
-      store_w_regs(wr, wb_hi, wb_lo, nullptr, nullptr, g, with_lo);
+      load_w_regs(wr, wc, Wd3, bd3, H, v0, nv);
+      store_w_regs(wr, wc, wb_hi, wb_lo, nullptr, nullptr, with_lo);
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
-        issue_gemm(tmem, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sbo, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
-                   CORE, g.wb_sbo, 2 * CORE, g.Kp / 8, idesc_g1, 0u, split);
-        mma_commit(&bar_mma);
+        if (elect_one()) {
+          issue_gemm<SPLIT>(tmem, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
+          mma_commit(&bar_mma);
+        }
+        __syncwarp();
       }
       mbar_wait(&bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
-      float z[16];
-      tmem_ld16(lane_addr + half * 16, z);
+      float z[CW];
+      tmem_ld8(lane_addr + cpart * CW, z);
       const int brow = q4 * 32 + lane;
       if (brow < nb) {
-        float* orow = out + (size_t)(b0 + brow) * ldo + v0 + half * 16;
+        float* orow = out + (size_t)(b0 + brow) * ldo + v0 + cpart * CW;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (half * 16 + j < nv) {
+        for (int j = 0; j < CW; ++j) {
+          if (cpart * CW + j < nv) {
             float s = z[j];
             if (apply_sigmoid) s = 1.0f / (1.0f + expf(-s));
             orow[j] = s;
@@ -600,7 +684,7 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   unsigned char* dt_lo = dt_hi + g.dt_bytes;
   const bool with_lo = (split == 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, half = warp >> 2;
+  const int q4 = warp & 3, cpart = warp >> 2;
   if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_mma, 1);
@@ -625,16 +709,16 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   } else {
     const int acols = (mode == 2) ? TN : BM;
     const uint32_t th = (mode == 2) ? TM_DZH : TM_HTH, tl = (mode == 2) ? TM_DZL : TM_HTL;
-    for (int c = half; c < acols / 16; c += 2) {
-      float hi[16], lo[16];
+    for (int c = cpart; c < acols / CW; c += NT / 128) {
+      float hi[CW], lo[CW];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = A[(size_t)row * acols + c * 16 + j];
+      for (int j = 0; j < CW; ++j) {
+        float x = A[(size_t)row * acols + c * CW + j];
         hi[j] = tf32_hi(x);
         lo[j] = x - hi[j];
       }
-      tmem_st16(lane_addr + th + c * 16, hi);
-      if (with_lo) tmem_st16(lane_addr + tl + c * 16, lo);
+      tmem_st8(lane_addr + th + c * CW, hi);
+      if (with_lo) tmem_st8(lane_addr + tl + c * CW, lo);
     }
     tmem_st_wait();
     if (mode == 2)
@@ -645,28 +729,34 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    if (mode == 1)
-      issue_gemm(tmem + TM_Z, smem_u32(hb_hi), smem_u32(hb_lo), CORE, g.hb_sbo, 2 * CORE, smem_u32(wb_hi), smem_u32(wb_lo),
-                 CORE, g.wb_sbo, 2 * CORE, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u, split);
-    else if (mode == 2)
-      issue_gemm_ts(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, smem_u32(wt_hi), smem_u32(wt_lo), g.wt_lbo, g.wt_sbo,
-                    2 * g.wt_lbo, TN / 8, make_idesc(BM, g.Np, 0, 0), 0u, split);
-    else
-      issue_gemm_ts(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, smem_u32(dt_hi), smem_u32(dt_lo), g.dt_lbo, g.dt_sbo,
-                    2 * g.dt_lbo, BM / 8, make_idesc(BM, TN, 0, 0), 0u, split);
-    mma_commit(&bar_mma);
+    const SmemOp o_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE), o_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
+    const SmemOp o_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
+    const SmemOp o_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
+    if (elect_one()) {
+      if (split == 3) {
+        if (mode == 1) issue_gemm<3>(tmem + TM_Z, o_hb, o_wb, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u);
+        else if (mode == 2) issue_gemm_ts<3>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, o_wt, TN / 8, make_idesc(BM, g.Np, 0, 0), 0u);
+        else issue_gemm_ts<3>(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, o_dt, BM / 8, make_idesc(BM, TN, 0, 0), 0u);
+      } else {
+        if (mode == 1) issue_gemm<1>(tmem + TM_Z, o_hb, o_wb, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u);
+        else if (mode == 2) issue_gemm_ts<1>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, o_wt, TN / 8, make_idesc(BM, g.Np, 0, 0), 0u);
+        else issue_gemm_ts<1>(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, o_dt, BM / 8, make_idesc(BM, TN, 0, 0), 0u);
+      }
+      mma_commit(&bar_mma);
+    }
+    __syncwarp();
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
   const int ncols = (mode == 2) ? g.Np : TN;
   const uint32_t tsrc = (mode == 1) ? TM_Z : (mode == 2 ? TM_DH : TM_DW);
-  for (int c = half; c < ncols / 16; c += 2) {
-    float d[16];
-    tmem_ld16(lane_addr + tsrc + c * 16, d);
+  for (int c = cpart; c < ncols / CW; c += NT / 128) {
+    float d[CW];
+    tmem_ld8(lane_addr + tsrc + c * CW, d);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) D[(size_t)row * ncols + c * 16 + j] = d[j];
+    for (int j = 0; j < CW; ++j) D[(size_t)row * ncols + c * CW + j] = d[j];
   }
   tc_fence_before();
   __syncthreads();
@@ -693,15 +783,16 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
   }
   tc::Geom g = tc::make_geom(H);
   size_t smem = tc::smem_bytes(g);
-  cudaError_t e = cudaFuncSetAttribute(tc::dec_out_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = (split == 3) ? tc::dec_out_train_tc_kernel<3> : tc::dec_out_train_tc_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("dec_out_train(tc): smem %zu: %s", smem, cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
   int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
   int grid = std::min(n_tiles, sm_count());
-  tc::dec_out_train_tc_kernel<<<grid, tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr,
-                                                          indices, (float)(1.0 / n_total), st, dh2, loss_sum, split);
+  kern<<<grid, tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+                                  (float)(1.0 / n_total), st, dh2, loss_sum);
   return check_launch("dec_out_train(tc)");
 }
 
@@ -710,7 +801,8 @@ int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const flo
   if (!tc_supported(B, H, "dec_out_scores")) return AAE_E_UNSUPPORTED;
   tc::Geom g = tc::make_geom(H);
   size_t smem = 2 * ((size_t)g.hb_bytes + g.wb_bytes) + 256;
-  cudaError_t e = cudaFuncSetAttribute(tc::dec_out_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = (split == 3) ? tc::dec_out_scores_tc_kernel<3> : tc::dec_out_scores_tc_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("dec_out_scores(tc): smem %zu: %s", smem, cudaGetErrorString(e));
     return AAE_E_CUDA;
@@ -719,8 +811,7 @@ int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const flo
   int n_chunks = (B + tc::BM - 1) / tc::BM;
   int gy = std::min(n_chunks, sm_count());
   int gx = std::max(1, std::min(n_tiles, sm_count() / gy));
-  tc::dec_out_scores_tc_kernel<<<dim3(gx, gy), tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo,
-                                                                  split);
+  kern<<<dim3(gx, gy), tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo);
   return check_launch("dec_out_scores(tc)");
 }
 
