@@ -25,6 +25,11 @@ class AaeDrop(C.Structure):
     _fields_ = [("mask", P), ("p", F), ("stream_id", C.c_uint32)]
 
 
+class AdamBlock(C.Structure):
+    """Mirror of ``aae_adam_block``: a packed parameter block with its Adam moments (p NULL: gradient only)."""
+    _fields_ = [("p", P), ("m", P), ("v", P), ("which", I)]
+
+
 class StepState(C.Structure):
     """Mirror of ``aae_step_state`` (device resident; used for size and for debugging reads)."""
     _fields_ = [("t", C.c_int32), ("rng_step", C.c_uint32), ("step_size_gen", F), ("step_size_reg", F),
@@ -39,7 +44,9 @@ _SIGS = {
     "aae_step_state_init": (I, [P, F, F, C.c_uint64, P]),
     "aae_step_tick": (I, [P, P]),
     "aae_bag_fwd": (I, [P, P, I, P, P, I, I, I, I, I, P, P]),
-    "aae_batch_slots": (I, [P, P, I, I, I, P, P, P, P]),
+    "aae_step_begin": (I, [P, P, I, P, P, I64, P, P, P, I, I, P]),
+    "aae_step_end": (I, [P, P, P, I, P, D, I, P, P]),
+    "aae_batch_slots": (I, [P, P, I, I, I, P, P, P, I, P]),
     "aae_batch_slots_reset": (I, [P, P, P, I, P]),
     "aae_bag_bwd": (I, [P, P, I, P, I, I, P, I, I, P, P]),
     "aae_zero_rows": (I, [P, P, I, I, P]),
@@ -50,9 +57,9 @@ _SIGS = {
     "aae_ae_bwd": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P, P, P, P]),
     "aae_disc_phase": (I, [AaeDims, P, P, F, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P]),
     "aae_gen_phase": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
-    "aae_ae_wgrad": (I, [AaeDims, P, P, P, P, P, P, P, P, P, P, P, P]),
-    "aae_disc_wgrad": (I, [AaeDims, P, P, P, P]),
-    "aae_gen_wgrad": (I, [AaeDims, P, P, P, P, P, P, P]),
+    "aae_ae_wgrad": (I, [AaeDims, P, P, P, P, P, P, P, P, P, P, P, AdamBlock, AdamBlock, P, P]),
+    "aae_disc_wgrad": (I, [AaeDims, P, P, P, AdamBlock, P, P]),
+    "aae_gen_wgrad": (I, [AaeDims, P, P, P, P, P, P, AdamBlock, P, P]),
     "aae_dec_out_train": (I, [P, I, I, P, P, P, P, P, P, I, I, P, P, D, P, P, P, I, P]),
     "aae_predict_tail": (I, [AaeDims, P, P, P, P, P, P]),
     "aae_dec_out_scores": (I, [P, I, I, P, P, I, I, P, I64, I, P]),
@@ -96,7 +103,7 @@ def last_error():
 
 
 # kernels launched per entry point (for the bench's gpu_launches claim); memcpy-only calls count 0
-KERNELS = {"aae_batch_slots": 2, "aae_upload_batch": 0, "aae_masked_topk": 2}
+KERNELS = {"aae_upload_batch": 0, "aae_masked_topk": 2}
 _launches = 0
 
 
@@ -156,6 +163,12 @@ def require_device(dev=0):
 
 def drop(mask=None, p=0.0, stream_id=0):
     return AaeDrop(P(mask.data_ptr()) if mask is not None else None, float(p), int(stream_id))
+
+
+def adam_block(p=None, m=None, v=None, which=0):
+    if p is None:
+        return AdamBlock(None, None, None, 0)
+    return AdamBlock(P(p.data_ptr()), P(m.data_ptr()), P(v.data_ptr()), int(which))
 
 
 def ptr(t):

@@ -291,11 +291,10 @@ class AAEEngine(object):
         n_total = float(B) * float(self.V)
         cap = self.uniq.numel()
         cur = torch.cuda.current_stream(self.dev)
-        call("aae_step_tick", st, s())
-        self.loss_sums.zero_()
-        self.dh2[:B].zero_()
+        call("aae_step_begin", st, ptr(self.loss_sums), 3, ptr(self.n_uniq), ptr(self.dh2), B * H, ptr(self.G1),
+             ptr(self.G2), ptr(self.indptr), B, H, s())
         call("aae_batch_slots", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.slot_of), ptr(self.uniq),
-             ptr(self.n_uniq), s())
+             ptr(self.n_uniq), 1, s())
         # rows that are not in the batch: both Adam states decay, on a side stream under the step
         if self.overlap_sweep:
             self._ev_fork.record(cur)
@@ -304,8 +303,6 @@ class AAEEngine(object):
                 call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
                      ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
                 self._ev_join.record(self.side)
-        call("aae_zero_rows", ptr(self.G1), ptr(self.indptr), B, H, s())
-        call("aae_zero_rows", ptr(self.G2), ptr(self.indptr), B, H, s())
         # ---- ae_step (aae.py:676-711)
         call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
              lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
@@ -323,12 +320,11 @@ class AAEEngine(object):
              dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.dd1), ptr(self.h2), ptr(self.g_d2), ptr(self.g_d1),
              ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), s())
         call("aae_ae_wgrad", dims, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1), ptr(self.g_d2),
-             ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), ptr(self.g_enc), ptr(self.g_dec), s())
+             ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), None, None,
+             N.adam_block(self.enc, self.enc_m1, self.enc_v1, 0), N.adam_block(self.dec, self.dec_m, self.dec_v, 0),
+             st, s())       # enc_optim.step() / dec_optim.step() fused into the reduction
         call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.g_h1), H, self.normalize,
              ptr(self.slot_of), lo, hi, ptr(self.G1), s())
-        call("aae_adam_dense", ptr(self.dec), ptr(self.g_dec), ptr(self.dec_m), ptr(self.dec_v), self.n_dec, st, 0, s())
-        call("aae_adam_dense", ptr(self.enc), ptr(self.g_enc), ptr(self.enc_m1), ptr(self.enc_v1), self.n_enc, st, 0,
-             s())
         call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G1), ptr(self.W1t), ptr(self.W1_m1),
              ptr(self.W1_v1), H, st, 0, s())
         # ---- disc_step (aae.py:713-732) and gen_step (734-743) share X.W1^T + b1 (same weights, same input)
@@ -338,18 +334,15 @@ class AAEEngine(object):
         call("aae_disc_phase", dims, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
              C.c_float(self.prior_scale), ptr(self.enc), ptr(self.disc), dr["disc_r1"], dr["disc_r2"], dr["disc_f1"],
              dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
-        call("aae_disc_wgrad", dims, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.g_disc), s())
-        call("aae_adam_dense", ptr(self.disc), ptr(self.g_disc), ptr(self.disc_m), ptr(self.disc_v), self.n_disc, st,
-             1, s())
+        call("aae_disc_wgrad", dims, ptr(self.disc_acts), ptr(self.disc_grads), None,
+             N.adam_block(self.disc, self.disc_m, self.disc_v, 1), st, s())
         call("aae_gen_phase", dims, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"], dr["gen_e2"],
              dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
              ptr(self.gg_h1), ptr(self.loss_sums[2:]), s())
         call("aae_gen_wgrad", dims, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2), ptr(self.gg_h1),
-             ptr(self.g_enc), s())
+             None, N.adam_block(self.enc, self.enc_m2, self.enc_v2, 1), st, s())
         call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.gg_h1), H, self.normalize,
              ptr(self.slot_of), lo, hi, ptr(self.G2), s())
-        call("aae_adam_dense", ptr(self.enc), ptr(self.g_enc), ptr(self.enc_m2), ptr(self.enc_v2), self.n_enc, st, 1,
-             s())
         call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G2), ptr(self.W1t), ptr(self.W1_m2),
              ptr(self.W1_v2), H, st, 1, s())
         if self.overlap_sweep:
@@ -357,8 +350,8 @@ class AAEEngine(object):
         else:
             call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
                  ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
-        call("aae_batch_slots_reset", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, s())
-        call("aae_finish_losses", ptr(self.loss_sums), n_total, B, ptr(self.losses), s())
+        call("aae_step_end", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), n_total, B,
+             ptr(self.losses), s())
 
     def train_step(self, B, injected=False):
         """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses

@@ -41,7 +41,7 @@ int dec_out_scores_simt(const float* h2, int B, int H, const float* Wd3, const f
                         float* out, int64_t ldo, cudaStream_t s);
 int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
                      int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
-                     const aae_step_state* st, float* dh2, double* loss_sum, int split, cudaStream_t s);
+                     const aae_step_state* st, float* dh2, double* loss_sum, int split, bool pipelined, cudaStream_t s);
 int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
                       float* out, int64_t ldo, int split, cudaStream_t s);
 
@@ -77,9 +77,9 @@ int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, flo
   if (impl == 0)
     return dec_out_train_simt(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
                               loss_sum, as_stream(stream));
-  if (impl == 1 || impl == 2)
+  if (impl >= 1 && impl <= 4)   // 1/2: pipelined when the shape allows it; 3/4: the non-pipelined kernel
     return dec_out_train_tc(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
-                            loss_sum, impl == 1 ? 3 : 1, as_stream(stream));
+                            loss_sum, (impl & 1) ? 3 : 1, impl <= 2, as_stream(stream));
   set_error("dec_out_train: unknown impl %d", impl);
   return AAE_E_ARG;
 }

@@ -34,6 +34,47 @@ __global__ void step_tick_kernel(aae_step_state* st) {
   st->bc2_sqrt = (float)sqrt(bc2);
 }
 
+// Start of one partial_fit in a single launch: Adam step counter / bias corrections, loss accumulators,
+// the touched-row counter, and the zero fill of the accumulation buffers (dh2 and the two compact
+// first-layer gradient buffers, nnz*H floats each).
+__global__ void __launch_bounds__(256) step_begin_kernel(aae_step_state* st, double* sums, int n_sums, int32_t* counter,
+                                                         float* z0, int64_t n0, float* z1, float* z2,
+                                                         const int32_t* __restrict__ indptr, int B, int H) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int t = st->t + 1;
+    st->t = t;
+    st->rng_step += 1;
+    double bc1 = 1.0 - pow(0.9, (double)t);
+    double bc2 = 1.0 - pow(0.999, (double)t);
+    st->step_size_gen = (float)((double)st->gen_lr / bc1);
+    st->step_size_reg = (float)((double)st->reg_lr / bc1);
+    st->bc2_sqrt = (float)sqrt(bc2);
+    for (int i = 0; i < n_sums; ++i) sums[i] = 0.0;
+    if (counter) *counter = 0;
+  }
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n0; i += nth) z0[i] = 0.f;
+  if (z1 || z2) {
+    const int64_t n = (int64_t)indptr[B] * H;
+    for (int64_t i = tid; i < n; i += nth) {
+      if (z1) z1[i] = 0.f;
+      if (z2) z2[i] = 0.f;
+    }
+  }
+}
+// End of one partial_fit: release the touched-row slots and finalise the three losses.
+__global__ void __launch_bounds__(256) step_end_kernel(int32_t* slot_of, const int32_t* __restrict__ uniq,
+                                                       const int32_t* __restrict__ n_uniq, int cap, const double* sums,
+                                                       double n_total, int B, float* out) {
+  int n = min(*n_uniq, cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) slot_of[uniq[s]] = -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = (float)(sums[0] / n_total);
+    out[1] = (float)(sums[1] / (double)B);
+    out[2] = (float)(sums[2] / (double)B);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: one warp per set, lanes stride over the float4 columns of each gathered row.
 // H % 4 == 0 fast path (400-byte rows, 16-byte aligned); scalar path otherwise.
@@ -136,27 +177,30 @@ __global__ void zero_rows_kernel(float* G, const int32_t* __restrict__ indptr, i
 
 // ---------------------------------------------------------------------------------------------
 // K2: scatter-add of the first layer's weight gradient into the compact touched-row buffer.
-// One warp per (set, item) pair; red.global.add.f32 (rows of popular items are shared by sets).
+// One warp per (set, item) pair (the set of a CSR entry is found by bisection of indptr); lanes over the
+// hidden units, red.global.add.f32 (rows of popular items are shared by several sets).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bag_bwd_kernel(const int32_t* __restrict__ indptr,
                                                       const int32_t* __restrict__ indices, int B,
                                                       const float* __restrict__ dh1, int H, int normalize,
                                                       const int32_t* __restrict__ slot_of, int v_begin, int v_end,
                                                       float* __restrict__ G) {
-  int lane = threadIdx.x & 31;
-  int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
-    int s = indptr[b], e = indptr[b + 1];
-    float scale = normalize ? 1.0f / fmaxf((float)(e - s), 1e-12f) : 1.0f;
-    for (int c = lane; c < H; c += 32) {
-      float g = dh1[(size_t)b * H + c] * scale;
-      for (int j = s; j < e; ++j) {
-        int i = indices[j];
-        if (i < v_begin || i >= v_end) continue;
-        int slot = slot_of[i - v_begin];
-        atomicAdd(G + (size_t)slot * H + c, g);
-      }
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nnz = indptr[B];
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nnz; e += warps) {
+    const int i = indices[e];
+    if (i < v_begin || i >= v_end) continue;
+    int lo = 0, hi = B;                       // largest b with indptr[b] <= e
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (indptr[mid] <= e) lo = mid; else hi = mid;
     }
+    const int b = lo;
+    const float scale = normalize ? 1.0f / fmaxf((float)(indptr[b + 1] - indptr[b]), 1e-12f) : 1.0f;
+    float* grow = G + (size_t)slot_of[i - v_begin] * H;
+    const float* drow = dh1 + (size_t)b * H;
+    for (int c = lane; c < H; c += 32) atomicAdd(grow + c, drow[c] * scale);
   }
 }
 
@@ -264,6 +308,22 @@ int aae_step_tick(aae_step_state* st, void* stream) {
   return check_launch("step_tick");
 }
 
+int aae_step_begin(aae_step_state* st, double* loss_sums, int n_sums, int32_t* n_uniq, float* dh2, int64_t n_dh2,
+                   float* G1, float* G2, const int32_t* indptr, int B, int H, void* stream) {
+  AAE_REQUIRE(st && loss_sums && n_sums >= 0, "null pointer");
+  AAE_REQUIRE((!G1 && !G2) || indptr, "indptr missing");
+  step_begin_kernel<<<2 * sm_count(), 256, 0, as_stream(stream)>>>(st, loss_sums, n_sums, n_uniq, dh2, dh2 ? n_dh2 : 0,
+                                                                  G1, G2, indptr, B, H);
+  return check_launch("step_begin");
+}
+int aae_step_end(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, const double* sums,
+                 double n_total, int B, float* losses, void* stream) {
+  AAE_REQUIRE(slot_of && uniq && n_uniq && sums && losses, "null pointer");
+  step_end_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(cap, 256))), 256, 0, as_stream(stream)>>>(
+      slot_of, uniq, n_uniq, cap, sums, n_total, B, losses);
+  return check_launch("step_end");
+}
+
 int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const float* W1t, const float* b1, int H,
                 int normalize, int v_begin, int v_end, int add_bias, float* out, void* stream) {
   AAE_REQUIRE(indptr && indices && W1t && b1 && out, "null pointer");
@@ -279,9 +339,9 @@ int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const floa
 }
 
 int aae_batch_slots(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end, int32_t* slot_of,
-                    int32_t* uniq, int32_t* n_uniq, void* stream) {
+                    int32_t* uniq, int32_t* n_uniq, int counter_is_zero, void* stream) {
   AAE_REQUIRE(indptr && indices && slot_of && uniq && n_uniq, "null pointer");
-  zero_counter_kernel<<<1, 1, 0, as_stream(stream)>>>(n_uniq);
+  if (!counter_is_zero) zero_counter_kernel<<<1, 1, 0, as_stream(stream)>>>(n_uniq);
   batch_slots_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv((int64_t)B * 16, 256))), 256, 0, as_stream(stream)>>>(
       indptr, indices, B, v_begin, v_end, slot_of, uniq, n_uniq);
   return check_launch("batch_slots");
@@ -300,7 +360,7 @@ int aae_zero_rows(float* G, const int32_t* indptr, int B, int H, void* stream) {
 int aae_bag_bwd(const int32_t* indptr, const int32_t* indices, int B, const float* dh1, int H, int normalize,
                 const int32_t* slot_of, int v_begin, int v_end, float* G, void* stream) {
   AAE_REQUIRE(indptr && indices && dh1 && slot_of && G, "null pointer");
-  int blocks = std::min(8 * sm_count(), cdiv((int64_t)B * 32, 256));
+  int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)B * 16 * 32, 256)));   // ~one warp per entry
   bag_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(indptr, indices, B, dh1, H, normalize, slot_of, v_begin,
                                                        v_end, G);
   return check_launch("bag_bwd");

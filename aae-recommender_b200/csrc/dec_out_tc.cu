@@ -263,9 +263,9 @@ constexpr uint32_t TM_Z = 0, TM_DW = 32, TM_DZH = 64, TM_DZL = 96, TM_DH = 128, 
 
 // H2' chunk -> Hb hi/lo (rows >= nb and columns > H are zero, column H is the ones column)
 __device__ __forceinline__ void fill_hb(unsigned char* hb_hi, unsigned char* hb_lo, const Geom& g,
-                                        const float* __restrict__ h2, int b0, int nb, bool with_lo) {
+                                        const float* __restrict__ h2, int b0, int nb, bool with_lo, int nthreads = NT) {
   const int ncg = g.Kp / 4;
-  for (int q = threadIdx.x; q < BM * ncg; q += NT) {
+  for (int q = threadIdx.x; q < BM * ncg; q += nthreads) {
     int r = q / ncg, cg = q - r * ncg;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nb) {
@@ -579,6 +579,347 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pipelined training kernel (the default for the reference's shapes).  Same three GEMMs and epilogues as
+// above, but the tile loop is software-pipelined around ONE dedicated MMA-issuing warp:
+//
+//   warp 16 (issuer), per iteration i : wait named barrier -> G3(i), G2(i), G1(i+1) -> tcgen05.commit
+//   warps 0-15 (epilogue/loader)      : wait commit(i-1) [G1(i), G23(i-1) done]
+//                                       E1(i): Z[i&1] -> dZ (TMEM + transposed smem)
+//                                       W'(i) -> Wtb, W'(i+1) -> Wb[(i+1)&1], arrive on the named barrier
+//                                       E2(i-1): dW'^T[(i-1)&1] -> Adam -> global     (overlaps the MMAs of i)
+//                                       prefetch: W'(i+2) rows, and W/m/v of tile i in the E2 layout
+//
+// Z and dW'^T are double-buffered in TMEM, Wb in shared memory, so the tensor core works on tile i's
+// backward GEMMs and tile i+1's logits while the CUDA cores finish tile i-1; the only block-wide
+// synchronisation per tile is one mbarrier wait and one non-blocking named-barrier arrive.
+// TMEM (512 columns): Z 2x32 | dW'^T 2x32 | dZ hi,lo 2x32 | dh2 Np | H2'^T hi,lo 2x round8(B)
+//   -> needs Np + 2*round8(B) <= 320 (n_hidden 100: batch <= 104).
+// Bias: lane k == H of dW'^T holds the bias gradients; they are handed to lanes H+1..H+8 of the same warp,
+// which run the same Adam code on bd3/mb/vb (one element each) -- no divergent bias path.
+// ---------------------------------------------------------------------------------------------
+constexpr int NT2 = NT + 32;
+constexpr uint32_t T2_Z = 0, T2_DW = 64, T2_DZH = 128, T2_DZL = 160, T2_DH = 192;
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// target 0 and |z| < 16: ATen's clamped formula (common.cuh bce_term) equals softplus(z) / sigmoid(z)/N to
+// far below 1e-6 relative; everything else goes through bce_term.
+__device__ __forceinline__ float bce_neg_fast(float z, float inv_n, float& dz) {
+  float u = __expf(-fabsf(z));
+  float r = __fdividef(1.0f, 1.0f + u);
+  float x = (z >= 0.f) ? r : u * r;
+  float poly = u * (1.0f - u * (0.5f - u * (0.33333334f - u * (0.25f - 0.2f * u))));
+  float l1p = (u < 0.0625f) ? poly : __logf(1.0f + u);
+  dz = x * inv_n;
+  return fmaxf(z, 0.f) + l1p;
+}
+
+__device__ __forceinline__ void store_wb_regs(const float4* wr, const WChunk* wc, unsigned char* wb_hi,
+                                              unsigned char* wb_lo, bool with_lo) {
+#pragma unroll
+  for (int j = 0; j < WCH; ++j) {
+    if (wc[j].goff == -2) continue;
+    float4 x = wr[j];
+    float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    *reinterpret_cast<float4*>(wb_hi + wc[j].wb_off) = h;
+    if (with_lo) *reinterpret_cast<float4*>(wb_lo + wc[j].wb_off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  }
+}
+__device__ __forceinline__ void store_wt_regs(const float4* wr, const WChunk* wc, unsigned char* wt_hi,
+                                              unsigned char* wt_lo, bool with_lo) {
+#pragma unroll
+  for (int j = 0; j < WCH; ++j) {
+    if (wc[j].goff == -2) continue;
+    float4 x = wr[j];
+    float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    float* th = reinterpret_cast<float*>(wt_hi + wc[j].wt_off);
+    th[0] = h.x; th[4] = h.y; th[8] = h.z; th[12] = h.w;
+    if (with_lo) {
+      float* tl = reinterpret_cast<float*>(wt_lo + wc[j].wt_off);
+      tl[0] = x.x - h.x; tl[4] = x.y - h.y; tl[8] = x.z - h.z; tl[12] = x.w - h.w;
+    }
+  }
+}
+
+template <int SPLIT, int HC>
+__global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
+    const float* __restrict__ h2, int B, int Hrt, float* __restrict__ Wd3, float* __restrict__ bd3,
+    float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
+    int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
+    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[NT / 32];
+  const int H = HC ? HC : Hrt;
+  const Geom g = make_geom(H);
+  constexpr bool with_lo = (SPLIT == 3);
+  unsigned char* hb_hi = smem;
+  unsigned char* hb_lo = hb_hi + g.hb_bytes;
+  unsigned char* wb0_hi = hb_lo + g.hb_bytes;
+  unsigned char* wb0_lo = wb0_hi + g.wb_bytes;
+  unsigned char* wb1_hi = wb0_lo + g.wb_bytes;
+  unsigned char* wb1_lo = wb1_hi + g.wb_bytes;
+  unsigned char* wt_hi = wb1_lo + g.wb_bytes;
+  unsigned char* wt_lo = wt_hi + g.wt_bytes;
+  unsigned char* dt_hi = wt_lo + g.wt_bytes;
+  unsigned char* dt_lo = dt_hi + g.dt_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (Vloc + TN - 1) / TN;
+  const int G = gridDim.x;
+  const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;     // tiles blockIdx.x, +G, ... (grid <= n_tiles)
+  const int BK = (B + 7) & ~7;
+  const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
+
+  if (warp == NT / 32) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int q = tid; q < (int)(2 * g.wt_bytes) / 16; q += NT2) reinterpret_cast<float4*>(wt_hi)[q] = make_float4(0, 0, 0, 0);
+  fill_hb(hb_hi, hb_lo, g, h2, 0, B, with_lo, NT2);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
+  const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
+
+  if (warp == NT / 32) {
+    // ================= MMA issuer =================
+    const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
+    const SmemOp op_wb0 = make_op(wb0_hi, wb0_lo, CORE, g.wb_sbo, 2 * CORE);
+    const SmemOp op_wb1 = make_op(wb1_hi, wb1_lo, CORE, g.wb_sbo, 2 * CORE);
+    const SmemOp op_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
+    const SmemOp op_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
+    const int ksteps_b = BK / 8;
+    for (int it = 0; it <= n_my; ++it) {
+      named_bar_sync(1, NT2);
+      tc_fence_after();
+      if (elect_one()) {
+        if (it > 0) {
+          const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
+          issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g1, 0u);
+          issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2, it > 1 ? 1u : 0u);
+        }
+        if (it < n_my) {
+          if (it & 1) issue_gemm<SPLIT>(tmem + T2_Z + 32u, op_hb, op_wb1, g.Kp / 8, idesc_g1, 0u);
+          else issue_gemm<SPLIT>(tmem + T2_Z, op_hb, op_wb0, g.Kp / 8, idesc_g1, 0u);
+        }
+        mma_commit(&bar_mma);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue / loader warps =================
+    const int q4 = warp & 3, cpart = warp >> 2;      // TMEM lane quarter, 8-column part of the 32-wide tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int brow = q4 * 32 + lane;                 // E1: batch row of this thread; E2: hidden unit
+    const AdamK ak = adam_load(st, 0);
+    // H2'^T -> TMEM (lane = hidden unit, column = batch row), BK columns
+    for (int c = cpart; c < BK / CW; c += NT / 128) {
+      float hi[CW], lo[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        int b = c * CW + j;
+        float x = 0.f;
+        if (b < B) x = (brow < H) ? h2[(size_t)b * H + brow] : (brow == H ? 1.0f : 0.f);
+        hi[j] = tf32_hi(x);
+        lo[j] = x - hi[j];
+      }
+      tmem_st8(lane_addr + T2_HTH + c * CW, hi);
+      if (with_lo) tmem_st8(lane_addr + T2_HTL + c * CW, lo);
+    }
+    tmem_st_wait();
+    const uint32_t dt_off = (uint32_t)cpart * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
+    const float inv_n_row = (brow < B) ? inv_n : 0.f;
+    const float rvf = (brow < B) ? 1.0f : 0.f;
+    RowCursor cur;
+    cur.pos = cur.end = 0;
+    cur.nxt = 0x7fffffff;
+    if (brow < B) {
+      cur.pos = indptr[brow];
+      cur.end = indptr[brow + 1];
+      int first = v_begin + (int)blockIdx.x * TN;
+      while (cur.pos < cur.end && indices[cur.pos] < first) ++cur.pos;
+      if (cur.pos < cur.end) cur.nxt = indices[cur.pos];
+    }
+    WChunk wc[WCH];
+    make_wchunks(wc, g);
+    float4 wA[WCH], wB[WCH];
+    {
+      const int t0 = blockIdx.x;
+      load_w_regs(wA, wc, Wd3, bd3, H, t0 * TN, min(TN, Vloc - t0 * TN));
+      store_wb_regs(wA, wc, wb0_hi, wb0_lo, with_lo);
+      if (n_my > 1) load_w_regs(wB, wc, Wd3, bd3, H, (t0 + G) * TN, min(TN, Vloc - (t0 + G) * TN));
+    }
+    fence_async_smem();
+    tc_fence_before();
+    named_bar_arrive(1, NT2);
+
+    // E2 addressing: normal lanes (k < H) walk 8 item rows of Wd3/mW/vW at pitch H; lanes H+1..H+8 own one
+    // bias element each; all use the same immediate offsets j*H (bias lanes only ever touch j = 0).
+    const int kb = H & 31;                           // lane of hidden unit H inside its warp
+    const bool bias_warp = (q4 == (H >> 5));
+    const int jb = brow - (H + 1);                   // bias lanes: 0..7
+    const bool is_bias = (jb >= 0 && jb < CW);
+    float* const eW = is_bias ? bd3 : Wd3;
+    float* const eM = is_bias ? mb : mW;
+    float* const eV = is_bias ? vb : vW;
+    float pw[CW], pm[CW], pv[CW];
+    size_t eoff = 0;
+    int ecnt = 0;
+    uint32_t phase = 0;
+    float loss_local = 0.f;
+
+    auto e2_apply = [&](int i_done) {
+      float gw[CW];
+      tmem_ld8(lane_addr + T2_DW + (uint32_t)(i_done & 1) * 32u + cpart * CW, gw);
+      if (bias_warp) {
+        float gb = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          float t = __shfl_sync(0xffffffffu, gw[j], kb);
+          if (jb == j) gb = t;
+        }
+        if (is_bias) gw[0] = gb;
+      }
+      float* pW = eW + eoff;
+      float* pM = eM + eoff;
+      float* pV = eV + eoff;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        if (j < ecnt) {
+          float p = pw[j], m = pm[j], vv = pv[j];
+          adam_update(ak, gw[j], p, m, vv);
+          pW[(size_t)j * H] = p;
+          __stcs(pM + (size_t)j * H, m);
+          __stcs(pV + (size_t)j * H, vv);
+        }
+      }
+    };
+
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = blockIdx.x + i * G;
+      const int v0 = tile * TN;
+      const int nv = min(TN, Vloc - v0);
+      // positives of this tile for this thread's row (cursor over the row's sorted CSR columns)
+      while (cur.nxt < v_begin + v0) {
+        ++cur.pos;
+        cur.nxt = (cur.pos < cur.end) ? indices[cur.pos] : 0x7fffffff;
+      }
+      const uint32_t tb = (tile_targets(cur, indices, v_begin + v0) >> (cpart * CW)) & 0xffu;
+      const int vm = nv - cpart * CW;                 // valid columns of this thread's 8 (>= 8: all)
+
+      mbar_wait(&bar_mma, phase);                     // G1(i) and G2/G3(i-1) have completed
+      phase ^= 1;
+      tc_fence_after();
+      // ---- E1(i)
+      {
+        float z[CW], dzh[CW], dzl[CW];
+        tmem_ld8(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, z);
+        float zmax = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) zmax = fmaxf(zmax, fabsf(z[j]));
+        if (tb == 0u && vm >= CW && zmax < 16.0f) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            float d;
+            float l = bce_neg_fast(z[j], inv_n_row, d);
+            loss_local = fmaf(l, rvf, loss_local);
+            float h = tf32_hi(d);
+            dzh[j] = h;
+            dzl[j] = d - h;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            float d = 0.f;
+            if (brow < B && j < vm) loss_local += bce_term(z[j], (tb >> j) & 1u, inv_n, d);
+            float h = tf32_hi(d);
+            dzh[j] = h;
+            dzl[j] = d - h;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          *reinterpret_cast<float*>(dt_hi + dt_off + 16 * j) = dzh[j];
+          if (with_lo) *reinterpret_cast<float*>(dt_lo + dt_off + 16 * j) = dzl[j];
+        }
+        tmem_st8(lane_addr + T2_DZH + cpart * CW, dzh);
+        if (with_lo) tmem_st8(lane_addr + T2_DZL + cpart * CW, dzl);
+      }
+      // ---- operands of the next MMA batch: W'(i) transposed for G2(i), W'(i+1) for G1(i+1)
+      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);
+      if (i + 1 < n_my) {
+        if ((i + 1) & 1) store_wb_regs(wB, wc, wb1_hi, wb1_lo, with_lo);
+        else store_wb_regs(wB, wc, wb0_hi, wb0_lo, with_lo);
+      }
+      tmem_st_wait();
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_arrive(1, NT2);
+#pragma unroll
+      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
+      if (i + 2 < n_my) {
+        const int t2 = tile + 2 * G;
+        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
+      }
+      // ---- E2(i-1): overlaps the MMAs of iteration i
+      if (i > 0) e2_apply(i - 1);
+      // ---- W/m/v of tile i in the E2 layout (consumed one iteration later)
+      {
+        if (is_bias) {
+          eoff = (size_t)v0 + cpart * CW + jb;
+          ecnt = (cpart * CW + jb < nv) ? 1 : 0;
+        } else {
+          eoff = (size_t)(v0 + cpart * CW) * H + brow;
+          ecnt = (brow < H) ? max(0, min(CW, vm)) : 0;
+        }
+        const float* pW = eW + eoff;
+        const float* pM = eM + eoff;
+        const float* pV = eV + eoff;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          if (j < ecnt) {
+            pw[j] = pW[(size_t)j * H];
+            pm[j] = __ldcs(pM + (size_t)j * H);
+            pv[j] = __ldcs(pV + (size_t)j * H);
+          }
+        }
+      }
+    }
+    mbar_wait(&bar_mma, phase);                       // G2/G3 of the last tile
+    tc_fence_after();
+    e2_apply(n_my - 1);
+    // ---- flush dh2 (lane = batch row, columns = hidden unit)
+    for (int c = cpart; c < g.Np / CW; c += NT / 128) {
+      float d[CW];
+      tmem_ld8(lane_addr + T2_DH + c * CW, d);
+      if (brow < B) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          int kk = c * CW + j;
+          if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
+        }
+      }
+    }
+    float s = warp_sum(loss_local);
+    if (lane == 0) red[warp] = s;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+    atomicAdd(loss_sum, tot);
+  }
+  if (warp == NT / 32) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // scores kernel (predict): out[b, v] = logit or sigmoid(logit); loops over batch chunks per tile
 // ---------------------------------------------------------------------------------------------
 template <int SPLIT>
@@ -773,15 +1114,46 @@ static bool tc_supported(int B, int H, const char* what) {
   return true;
 }
 
+// smem of the pipelined kernel: Hb hi/lo + 2 x Wb hi/lo + Wtb hi/lo + Dtb hi/lo
+static size_t tc2_smem_bytes(const tc::Geom& g) {
+  return 2 * (size_t)g.hb_bytes + 4 * (size_t)g.wb_bytes + 2 * (size_t)g.wt_bytes + 2 * (size_t)g.dt_bytes + 128;
+}
+// Envelope of the pipelined kernel: TMEM budget, shared-memory budget, bias lanes inside one warp.
+static bool tc2_supported(int B, int H) {
+  tc::Geom g = tc::make_geom(H);
+  int BK = (B + 7) & ~7;
+  if (B > tc::BM || g.Np + 2 * BK > 320) return false;
+  if ((H & 31) + 1 + tc::CW > 32) return false;
+  return tc2_smem_bytes(g) <= 227 * 1024 - 256;
+}
+
 int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
                      int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
-                     const aae_step_state* st, float* dh2, double* loss_sum, int split, cudaStream_t s) {
+                     const aae_step_state* st, float* dh2, double* loss_sum, int split, bool pipelined,
+                     cudaStream_t s) {
   if (!tc_supported(B, H, "dec_out_train")) return AAE_E_UNSUPPORTED;
   if (B > tc::BM) {
     set_error("dec_out_train: tensor-core kernel handles batch <= %d (got %d); use impl=simt", tc::BM, B);
     return AAE_E_UNSUPPORTED;
   }
   tc::Geom g = tc::make_geom(H);
+  int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
+  int grid = std::min(n_tiles, sm_count());
+  if (pipelined && tc2_supported(B, H)) {
+    size_t smem = tc2_smem_bytes(g);
+    void (*kern)(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
+                 const int32_t*, float, const aae_step_state*, float*, double*);
+    if (H == 100) kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 100> : tc::dec_out_train_tc2_kernel<1, 100>;
+    else kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 0> : tc::dec_out_train_tc2_kernel<1, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
+      return AAE_E_CUDA;
+    }
+    kern<<<grid, tc::NT2, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+                                     (float)(1.0 / n_total), st, dh2, loss_sum);
+    return check_launch("dec_out_train(tc2)");
+  }
   size_t smem = tc::smem_bytes(g);
   auto kern = (split == 3) ? tc::dec_out_train_tc_kernel<3> : tc::dec_out_train_tc_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -789,8 +1161,6 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
     set_error("dec_out_train(tc): smem %zu: %s", smem, cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
-  int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
-  int grid = std::min(n_tiles, sm_count());
   kern<<<grid, tc::NT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
                                   (float)(1.0 / n_total), st, dh2, loss_sum);
   return check_launch("dec_out_train(tc)");

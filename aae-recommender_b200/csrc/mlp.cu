@@ -9,69 +9,184 @@
 
 namespace aae {
 
-constexpr int MLP_THREADS = 128;
+constexpr int MLP_THREADS = 256;
+constexpr int STAGE_FLOATS = 10240;   // one staging buffer (40 KB); two of them per CTA
 
-// y[r][o] = b[o] + sum_i x[r][i] * W[o*I + i]; one warp per output, lanes over i (coalesced rows).
-template <int R>
-__device__ __forceinline__ void row_linear(const float* xs, int ldx, int I, const float* __restrict__ W,
-                                           const float* __restrict__ b, int O, float* ys, int ldy) {
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o0 = warp * 2; o0 < O; o0 += nw * 2) {
-    int o1 = o0 + 1;
-    bool has1 = o1 < O;
-    float acc0[R], acc1[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc0[r] = acc1[r] = 0.f;
-    const float* w0 = W + (size_t)o0 * I;
-    const float* w1 = W + (size_t)(has1 ? o1 : o0) * I;
-    for (int i = lane; i < I; i += 32) {
-      float a = __ldg(w0 + i), c = __ldg(w1 + i);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float x = xs[r * ldx + i];
-        acc0[r] = fmaf(a, x, acc0[r]);
-        acc1[r] = fmaf(c, x, acc1[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float s0 = warp_sum(acc0[r]), s1 = warp_sum(acc1[r]);
-      if (lane == 0) {
-        ys[r * ldy + o0] = s0 + b[o0];
-        if (has1) ys[r * ldy + o1] = s1 + b[o1];
-      }
-    }
-  }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// dx[r][i] = sum_o dy[r][o] * W[o*I + i]; one thread per i (coalesced over i).
+// One weight matrix of a kernel's layer sequence, torch layout [O, I] row-major.
+struct LayerW {
+  const float* W;
+  int O, I;
+};
+// Rows [r0, r1) of layer `layer`, resident in shared memory at w (row pitch I).
+struct Chunk {
+  const float* w;
+  int layer, r0, r1;
+};
+
+// Streams the weight matrices of the kernel's whole layer sequence through two shared-memory buffers with
+// cp.async, one chunk of whole rows at a time, always one chunk ahead of the consumer (across layer
+// boundaries too: the weights do not depend on the activations).  All threads call every method.
+struct Stager {
+  float *buf0, *buf1;
+  const LayerW* L;
+  int n;
+  int pl, pr, pbuf;   // next chunk to prefetch
+  int cl, cr, cbuf;   // next chunk to consume
+  int inflight;
+
+  __device__ static int rows_per_chunk(int I) {
+    int a = (I & 3) == 0 ? 1 : ((I & 1) == 0 ? 2 : 4);   // chunk starts stay 16-byte aligned
+    int r = STAGE_FLOATS / I;
+    if (r >= a) r -= r % a;
+    return max(r, 1);
+  }
+  __device__ void init(float* b0, float* b1, const LayerW* layers, int nlayers) {
+    buf0 = b0; buf1 = b1; L = layers; n = nlayers;
+    pl = pr = pbuf = cl = cr = cbuf = inflight = 0;
+    issue();
+  }
+  __device__ void issue() {
+    if (pl >= n) return;
+    const LayerW l = L[pl];
+    const int rc = min(rows_per_chunk(l.I), l.O - pr);
+    const float* src = l.W + (size_t)pr * l.I;
+    float* dst = pbuf ? buf1 : buf0;
+    const int nf = rc * l.I;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int n4 = nf >> 2;
+      for (int q = threadIdx.x; q < n4; q += blockDim.x) cp_async16(dst + 4 * q, src + 4 * q);
+      for (int q = (n4 << 2) + threadIdx.x; q < nf; q += blockDim.x) cp_async4(dst + q, src + q);
+    } else {
+      for (int q = threadIdx.x; q < nf; q += blockDim.x) cp_async4(dst + q, src + q);
+    }
+    cp_async_commit();
+    pbuf ^= 1;
+    ++inflight;
+    pr += rc;
+    if (pr >= l.O) { ++pl; pr = 0; }
+  }
+  // Next chunk, ready in shared memory.  The caller must __syncthreads() after it has finished reading a
+  // chunk and before the next acquire (the chunk after next lands in the same buffer).
+  __device__ Chunk acquire() {
+    Chunk c;
+    const LayerW l = L[cl];
+    const int rc = min(rows_per_chunk(l.I), l.O - cr);
+    c.layer = cl; c.r0 = cr; c.r1 = cr + rc;
+    c.w = cbuf ? buf1 : buf0;
+    issue();
+    if (inflight == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+    --inflight;
+    __syncthreads();
+    cbuf ^= 1;
+    cr += rc;
+    if (cr >= l.O) { ++cl; cr = 0; }
+    return c;
+  }
+};
+
+// y[r][o] = b[o] + sum_i x[r][i] * W[o][i] for the rows o of one chunk; a warp owns four outputs at a
+// time, lanes over i (conflict-free shared-memory reads), shuffle reduction.
 template <int R>
-__device__ __forceinline__ void row_linear_bwd(const float* dys, int ldy, int O, const float* __restrict__ W, int I,
-                                               float* dxs, int ldx) {
-  for (int i = threadIdx.x; i < I; i += blockDim.x) {
-    float acc[R];
+__device__ __forceinline__ void linear_fwd_chunk(const Chunk& c, int I, const float* xs, int ldx,
+                                                 const float* __restrict__ b, float* ys, int ldy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int nrows = c.r1 - c.r0;
+  for (int o0 = warp * 4; o0 < nrows; o0 += nw * 4) {
+    const int no = min(4, nrows - o0);
+    const float* w = c.w + (size_t)o0 * I;
+    float acc[4][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
-    int o = 0;
-    for (; o + 4 <= O; o += 4) {
-      float w0 = __ldg(W + (size_t)o * I + i), w1 = __ldg(W + (size_t)(o + 1) * I + i);
-      float w2 = __ldg(W + (size_t)(o + 2) * I + i), w3 = __ldg(W + (size_t)(o + 3) * I + i);
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[q][r] = 0.f;
+    for (int i = lane; i < I; i += 32) {
+      const float w0 = w[i];
+      const float w1 = (no > 1) ? w[I + i] : 0.f;
+      const float w2 = (no > 2) ? w[2 * I + i] : 0.f;
+      const float w3 = (no > 3) ? w[3 * I + i] : 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float* d = dys + r * ldy + o;
-        acc[r] = fmaf(w0, d[0], acc[r]);
-        acc[r] = fmaf(w1, d[1], acc[r]);
-        acc[r] = fmaf(w2, d[2], acc[r]);
-        acc[r] = fmaf(w3, d[3], acc[r]);
+        const float x = xs[r * ldx + i];
+        acc[0][r] = fmaf(w0, x, acc[0][r]);
+        acc[1][r] = fmaf(w1, x, acc[1][r]);
+        acc[2][r] = fmaf(w2, x, acc[2][r]);
+        acc[3][r] = fmaf(w3, x, acc[3][r]);
       }
     }
-    for (; o < O; ++o) {
-      float w0 = __ldg(W + (size_t)o * I + i);
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmaf(w0, dys[r * ldy + o], acc[r]);
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float s = warp_sum(acc[q][r]);
+        if (lane == 0 && q < no) ys[r * ldy + c.r0 + o0 + q] = s + b[c.r0 + o0 + q];
+      }
+  }
+}
+// y = x . W^T + b for layer `layer` of the stager's sequence (all its chunks).  Ends with a barrier.
+template <int R>
+__device__ __forceinline__ void layer_fwd(Stager& sg, int layer, const float* xs, int ldx, const float* __restrict__ b,
+                                          float* ys, int ldy) {
+  const int I = sg.L[layer].I;
+  while (sg.cl == layer) {
+    const Chunk c = sg.acquire();
+    linear_fwd_chunk<R>(c, I, xs, ldx, b, ys, ldy);
+    __syncthreads();
+  }
+}
+// dx[r][i] = sum_o dy[r][o] * W[o][i] for layer `layer`: thread (i, part) walks the chunk's rows o == part
+// (mod parts), partial sums meet in shared memory (atomicAdd; dxs is zeroed first).  Ends with a barrier.
+template <int R>
+__device__ __forceinline__ void layer_bwd(Stager& sg, int layer, const float* dys, int ldy, float* dxs, int ldx) {
+  const int I = sg.L[layer].I;
+  for (int q = threadIdx.x; q < R * I; q += blockDim.x) dxs[(q / I) * ldx + (q % I)] = 0.f;
+  const int lanes = min((int)blockDim.x, (I + 31) & ~31);   // threads over i (whole warps)
+  const int parts = max(1, (int)blockDim.x / lanes);
+  const int part = threadIdx.x / lanes, il = threadIdx.x - part * lanes;
+  while (sg.cl == layer) {
+    const Chunk c = sg.acquire();          // barrier inside: the zeroing above is visible
+    const int nrows = c.r1 - c.r0;
+    if (part < parts) {
+      for (int i = il; i < I; i += lanes) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        int o = part;
+        for (; o + 3 * parts < nrows; o += 4 * parts) {
+          const float w0 = c.w[(size_t)o * I + i], w1 = c.w[(size_t)(o + parts) * I + i];
+          const float w2 = c.w[(size_t)(o + 2 * parts) * I + i], w3 = c.w[(size_t)(o + 3 * parts) * I + i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float* d = dys + r * ldy + c.r0 + o;
+            acc[r] = fmaf(w0, d[0], acc[r]);
+            acc[r] = fmaf(w1, d[parts], acc[r]);
+            acc[r] = fmaf(w2, d[2 * parts], acc[r]);
+            acc[r] = fmaf(w3, d[3 * parts], acc[r]);
+          }
+        }
+        for (; o < nrows; o += parts) {
+          const float w0 = c.w[(size_t)o * I + i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(w0, dys[r * ldy + c.r0 + o], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) atomicAdd(&dxs[r * ldx + i], acc[r]);
+      }
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) dxs[r * ldx + i] = acc[r];
+    __syncthreads();
   }
 }
 
@@ -140,7 +255,7 @@ struct DiscBlock {
 };
 
 // ---------------------------------------------------------------------------------------------
-// ae_step forward tail
+// ae_step forward tail.  Shared memory: [stage buffer 0 | stage buffer 1 | x (R*ld) | y (R*ld)]
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const float* __restrict__ h1pre,
@@ -150,24 +265,30 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const f
                                                              aae_drop d1, aae_drop d2, const aae_step_state* st,
                                                              float* a1, float* a2, float* zc, float* dd1, float* h2,
                                                              int train) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  __shared__ LayerW layers[4];
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   const int ld = max(H, Cp);
-  float* x = sm;
-  float* y = sm + R * ld;
+  float* x = sm + 2 * STAGE_FLOATS;
+  float* y = x + R * ld;
   int row0 = blockIdx.x * R;
   EncBlock E(enc, H, C);
   DecBlock D(dec, H, Cp);
   aae_drop none = {nullptr, 0.f, 0};
+  if (threadIdx.x == 0) {
+    layers[0] = {E.We2, H, H};
+    layers[1] = {E.We3, C, H};
+    layers[2] = {D.Wd1, H, Cp};
+    layers[3] = {D.Wd2, H, H};
+  }
+  __syncthreads();
+  Stager sg;
+  sg.init(sm, sm + STAGE_FLOATS, layers, 4);
   load_rows<R>(x, ld, h1pre, H, row0, B);
-  __syncthreads();
-  drop_relu<R>(x, ld, H, row0, B, train ? e1 : none, st, a1);
-  __syncthreads();
-  row_linear<R>(x, ld, H, E.We2, E.be2, H, y, ld);
-  __syncthreads();
+  drop_relu<R>(x, ld, H, row0, B, train ? e1 : none, st, a1);   // same thread -> element mapping as load_rows
+  layer_fwd<R>(sg, 0, x, ld, E.be2, y, ld);
   drop_relu<R>(y, ld, H, row0, B, train ? e2 : none, st, a2);
-  __syncthreads();
-  row_linear<R>(y, ld, H, E.We3, E.be3, C, x, ld);   // z -> x[0..C)
+  layer_fwd<R>(sg, 1, y, ld, E.be3, x, ld);   // z -> x[0..C)
   // concatenate the condition rows on the code (condition.py:312-316)
   for (int q = threadIdx.x; q < R * d.D; q += blockDim.x) {
     int r = q / d.D, i = q - r * d.D;
@@ -176,17 +297,14 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const f
   }
   __syncthreads();
   if (zc) store_rows<R>(x, ld, zc, Cp, row0, B);
-  row_linear<R>(x, ld, Cp, D.Wd1, D.bd1, H, y, ld);
-  __syncthreads();
+  layer_fwd<R>(sg, 2, x, ld, D.bd1, y, ld);
   drop_relu<R>(y, ld, H, row0, B, train ? d1 : none, st, dd1);
-  __syncthreads();
-  row_linear<R>(y, ld, H, D.Wd2, D.bd2, H, x, ld);
-  __syncthreads();
+  layer_fwd<R>(sg, 3, y, ld, D.bd2, x, ld);
   drop_relu<R>(x, ld, H, row0, B, train ? d2 : none, st, h2);
 }
 
 // ---------------------------------------------------------------------------------------------
-// ae_step backward tail
+// ae_step backward tail.  Shared memory: [stage 0 | stage 1 | g | t | act]
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const float* __restrict__ dh2,
@@ -198,75 +316,71 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const f
                                                              const float* __restrict__ dd1,
                                                              const float* __restrict__ h2, float* g_d2, float* g_d1,
                                                              float* g_z, float* g_e2, float* g_h1) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  __shared__ LayerW layers[4];
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   const int ld = max(H, Cp);
-  float* g = sm;
-  float* t = sm + R * ld;
-  float* act = sm + 2 * R * ld;
+  float* g = sm + 2 * STAGE_FLOATS;
+  float* t = g + R * ld;
+  float* act = t + R * ld;
   int row0 = blockIdx.x * R;
   EncBlock E(enc, H, C);
   DecBlock D(dec, H, Cp);
+  if (threadIdx.x == 0) {
+    layers[0] = {D.Wd2, H, H};
+    layers[1] = {D.Wd1, H, Cp};
+    layers[2] = {E.We3, C, H};
+    layers[3] = {E.We2, H, H};
+  }
+  __syncthreads();
+  Stager sg;
+  sg.init(sm, sm + STAGE_FLOATS, layers, 4);
+  // every elementwise pass below uses the same thread -> (row, unit) mapping, so load + mask need no barrier
   load_rows<R>(g, ld, dh2, H, row0, B);
   load_rows<R>(act, ld, h2, H, row0, B);
-  __syncthreads();
   drop_relu_bwd<R>(g, act, ld, H, row0, B, d2, st, g_d2);
-  __syncthreads();
-  row_linear_bwd<R>(g, ld, H, D.Wd2, H, t, ld);
+  layer_bwd<R>(sg, 0, g, ld, t, ld);
   load_rows<R>(act, ld, dd1, H, row0, B);
-  __syncthreads();
   drop_relu_bwd<R>(t, act, ld, H, row0, B, d1, st, g_d1);
-  __syncthreads();
-  row_linear_bwd<R>(t, ld, H, D.Wd1, Cp, g, ld);    // d(zc); only the first C entries go on
-  __syncthreads();
+  layer_bwd<R>(sg, 1, t, ld, g, ld);            // d(zc); only the first C entries go on
   store_rows<R>(g, ld, g_z, C, row0, B);
-  row_linear_bwd<R>(g, ld, C, E.We3, H, t, ld);
+  layer_bwd<R>(sg, 2, g, ld, t, ld);
   load_rows<R>(act, ld, a2, H, row0, B);
-  __syncthreads();
   drop_relu_bwd<R>(t, act, ld, H, row0, B, e2, st, g_e2);
-  __syncthreads();
-  row_linear_bwd<R>(t, ld, H, E.We2, H, g, ld);
+  layer_bwd<R>(sg, 3, t, ld, g, ld);
   load_rows<R>(act, ld, a1, H, row0, B);
-  __syncthreads();
   drop_relu_bwd<R>(g, act, ld, H, row0, B, e1, st, g_h1);
 }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// discriminator forward on one input held in zs[R][ld] (width C); leaves q1 in q1s, q2 in q2s,
-// returns sigmoid output per row in outs[r] (shared).
+// discriminator forward on one input held in zs[R][ld] (width C): layers lb (Wq1), lb+1 (Wq2), lb+2 (wq3) of
+// the stager's sequence; leaves q1 in q1s, q2 in q2s, the sigmoid output per row in outs[r] (shared).
 template <int R>
-__device__ __forceinline__ void disc_fwd(const float* zs, int ld, const DiscBlock& Q, int H, int C, int row0, int B,
-                                         const aae_drop& da, const aae_drop& db, const aae_step_state* st,
-                                         float* q1s, float* q2s, float* outs) {
-  row_linear<R>(zs, ld, C, Q.Wq1, Q.bq1, H, q1s, ld);
-  __syncthreads();
+__device__ __forceinline__ void disc_fwd(Stager& sg, int lb, const float* zs, int ld, const DiscBlock& Q, int H,
+                                         int row0, int B, const aae_drop& da, const aae_drop& db,
+                                         const aae_step_state* st, float* q1s, float* q2s, float* outs) {
+  layer_fwd<R>(sg, lb, zs, ld, Q.bq1, q1s, ld);
   drop_relu<R>(q1s, ld, H, row0, B, da, st, nullptr);
-  __syncthreads();
-  row_linear<R>(q1s, ld, H, Q.Wq2, Q.bq2, H, q2s, ld);
-  __syncthreads();
+  layer_fwd<R>(sg, lb + 1, q1s, ld, Q.bq2, q2s, ld);
   drop_relu<R>(q2s, ld, H, row0, B, db, st, nullptr);
-  __syncthreads();
-  row_linear<R>(q2s, ld, H, Q.wq3, Q.bq3, 1, outs, 1);
-  __syncthreads();
+  layer_fwd<R>(sg, lb + 2, q2s, ld, Q.bq3, outs, 1);
   if (threadIdx.x < R) outs[threadIdx.x] = sigmoid_acc(outs[threadIdx.x]);
   __syncthreads();
 }
 // backward of the discriminator given g_o[r] = dL/d(lin3 pre-activation): g2 <- grad at lin2 pre-act,
-// g1 <- grad at lin1 pre-act.
+// g1 <- grad at lin1 pre-act (layer lq2 of the stager's sequence is Wq2).
 template <int R>
-__device__ __forceinline__ void disc_bwd(const float* g_o, const DiscBlock& Q, int H, int ld, int row0, int B,
-                                         const aae_drop& da, const aae_drop& db, const aae_step_state* st,
-                                         const float* q1s, const float* q2s, float* g2, float* g1) {
+__device__ __forceinline__ void disc_bwd(Stager& sg, int lq2, const float* g_o, const DiscBlock& Q, int H, int ld,
+                                         int row0, int B, const aae_drop& da, const aae_drop& db,
+                                         const aae_step_state* st, const float* q1s, const float* q2s, float* g2,
+                                         float* g1) {
   for (int q = threadIdx.x; q < R * H; q += blockDim.x) {
     int r = q / H, i = q - r * H;
     g2[r * ld + i] = g_o[r] * __ldg(Q.wq3 + i);
   }
-  __syncthreads();
-  drop_relu_bwd<R>(g2, q2s, ld, H, row0, B, db, st, nullptr);
-  __syncthreads();
-  row_linear_bwd<R>(g2, ld, H, Q.Wq2, H, g1, ld);
-  __syncthreads();
+  drop_relu_bwd<R>(g2, q2s, ld, H, row0, B, db, st, nullptr);   // same mapping as the loop above
+  layer_bwd<R>(sg, lq2, g2, ld, g1, ld);
   drop_relu_bwd<R>(g1, q1s, ld, H, row0, B, da, st, nullptr);
   __syncthreads();
 }
@@ -283,10 +397,11 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
                                                                  aae_drop r2, aae_drop f1, aae_drop f2,
                                                                  const aae_step_state* st, float* acts, float* grads,
                                                                  double* loss_sum) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  __shared__ LayerW layers[10];
   const int H = d.H, C = d.C, B = d.B;
   const int ld = max(H, C);
-  float* x = sm;
+  float* x = sm + 2 * STAGE_FLOATS;
   float* y = x + R * ld;
   float* q1 = y + R * ld;
   float* q2 = q1 + R * ld;
@@ -298,6 +413,14 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
   DiscBlock Q(disc, H, C);
   aae_drop none = {nullptr, 0.f, 0};
   const int AW = 2 * (C + 2 * H), GW = 2 * (2 * H + 1);
+  if (threadIdx.x == 0) {
+    layers[0] = {Q.Wq1, H, C}; layers[1] = {Q.Wq2, H, H}; layers[2] = {Q.wq3, 1, H}; layers[3] = {Q.Wq2, H, H};
+    layers[4] = {E.We2, H, H}; layers[5] = {E.We3, C, H};
+    layers[6] = {Q.Wq1, H, C}; layers[7] = {Q.Wq2, H, H}; layers[8] = {Q.wq3, 1, H}; layers[9] = {Q.Wq2, H, H};
+  }
+  __syncthreads();
+  Stager sg;
+  sg.init(sm, sm + STAGE_FLOATS, layers, 10);
   float lsum = 0.f;
   for (int side = 0; side < 2; ++side) {
     if (side == 0) {
@@ -312,17 +435,13 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
     } else {
       // z_fake = enc(batch) in eval mode (aae.py:714, 722)
       load_rows<R>(x, ld, h1pre, H, row0, B);
-      __syncthreads();
       drop_relu<R>(x, ld, H, row0, B, none, st, nullptr);
-      __syncthreads();
-      row_linear<R>(x, ld, H, E.We2, E.be2, H, y, ld);
-      __syncthreads();
+      layer_fwd<R>(sg, 4, x, ld, E.be2, y, ld);
       drop_relu<R>(y, ld, H, row0, B, none, st, nullptr);
-      __syncthreads();
-      row_linear<R>(y, ld, H, E.We3, E.be3, C, zz, ld);
+      layer_fwd<R>(sg, 5, y, ld, E.be3, zz, ld);
     }
-    __syncthreads();
-    disc_fwd<R>(zz, ld, Q, H, C, row0, B, side ? f1 : r1, side ? f2 : r2, st, q1, q2, outs);
+    const int lb = side ? 6 : 0;
+    disc_fwd<R>(sg, lb, zz, ld, Q, H, row0, B, side ? f1 : r1, side ? f2 : r2, st, q1, q2, outs);
     if (threadIdx.x < R && row0 + threadIdx.x < B) {
       float o = outs[threadIdx.x];
       float g;
@@ -349,7 +468,7 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
         ar[C + H + i] = q2[r * ld + i];
       }
     }
-    disc_bwd<R>(go, Q, H, ld, row0, B, side ? f1 : r1, side ? f2 : r2, st, q1, q2, y, x);
+    disc_bwd<R>(sg, lb + 3, go, Q, H, ld, row0, B, side ? f1 : r1, side ? f2 : r2, st, q1, q2, y, x);
     for (int r = 0; r < R; ++r) {
       int row = row0 + r;
       if (row >= B) break;
@@ -376,10 +495,11 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
                                                                 const aae_step_state* st, float* a1, float* a2,
                                                                 float* g_z, float* g_e2, float* g_h1,
                                                                 double* loss_sum) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  __shared__ LayerW layers[9];
   const int H = d.H, C = d.C, B = d.B;
   const int ld = max(H, C);
-  float* xa1 = sm;               // a1
+  float* xa1 = sm + 2 * STAGE_FLOATS;   // a1
   float* xa2 = xa1 + R * ld;     // a2
   float* zz = xa2 + R * ld;      // z
   float* q1 = zz + R * ld;
@@ -391,17 +511,20 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
   int row0 = blockIdx.x * R;
   EncBlock E(enc, H, C);
   DiscBlock Q(disc, H, C);
+  if (threadIdx.x == 0) {
+    layers[0] = {E.We2, H, H}; layers[1] = {E.We3, C, H};
+    layers[2] = {Q.Wq1, H, C}; layers[3] = {Q.Wq2, H, H}; layers[4] = {Q.wq3, 1, H};
+    layers[5] = {Q.Wq2, H, H}; layers[6] = {Q.Wq1, H, C}; layers[7] = {E.We3, C, H}; layers[8] = {E.We2, H, H};
+  }
+  __syncthreads();
+  Stager sg;
+  sg.init(sm, sm + STAGE_FLOATS, layers, 9);
   load_rows<R>(xa1, ld, h1pre, H, row0, B);
-  __syncthreads();
   drop_relu<R>(xa1, ld, H, row0, B, e1, st, a1);
-  __syncthreads();
-  row_linear<R>(xa1, ld, H, E.We2, E.be2, H, xa2, ld);
-  __syncthreads();
+  layer_fwd<R>(sg, 0, xa1, ld, E.be2, xa2, ld);
   drop_relu<R>(xa2, ld, H, row0, B, e2, st, a2);
-  __syncthreads();
-  row_linear<R>(xa2, ld, H, E.We3, E.be3, C, zz, ld);
-  __syncthreads();
-  disc_fwd<R>(zz, ld, Q, H, C, row0, B, q1d, q2d, st, q1, q2, outs);
+  layer_fwd<R>(sg, 1, xa2, ld, E.be3, zz, ld);
+  disc_fwd<R>(sg, 2, zz, ld, Q, H, row0, B, q1d, q2d, st, q1, q2, outs);
   if (threadIdx.x < R && row0 + threadIdx.x < B) {
     float o = outs[threadIdx.x];
     float a = o + 1e-12f;                           // -mean(log(D(enc(x)) + TINY)), aae.py:738
@@ -409,16 +532,12 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
     go[threadIdx.x] = (-1.0f / (float)B) / a * (1.0f - o) * o;
   }
   __syncthreads();
-  disc_bwd<R>(go, Q, H, ld, row0, B, q1d, q2d, st, q1, q2, t0, t1);   // t1 = grad at disc.lin1 pre-act
-  row_linear_bwd<R>(t1, ld, H, Q.Wq1, C, t0, ld);                    // dz
-  __syncthreads();
+  disc_bwd<R>(sg, 5, go, Q, H, ld, row0, B, q1d, q2d, st, q1, q2, t0, t1);   // t1 = grad at disc.lin1 pre-act
+  layer_bwd<R>(sg, 6, t1, ld, t0, ld);                                      // dz
   store_rows<R>(t0, ld, g_z, C, row0, B);
-  row_linear_bwd<R>(t0, ld, C, E.We3, H, t1, ld);
-  __syncthreads();
+  layer_bwd<R>(sg, 7, t0, ld, t1, ld);
   drop_relu_bwd<R>(t1, xa2, ld, H, row0, B, e2, st, g_e2);
-  __syncthreads();
-  row_linear_bwd<R>(t1, ld, H, E.We2, H, t0, ld);
-  __syncthreads();
+  layer_bwd<R>(sg, 8, t1, ld, t0, ld);
   drop_relu_bwd<R>(t0, xa1, ld, H, row0, B, e1, st, g_h1);
 }
 
@@ -430,45 +549,85 @@ struct WJob {
   const float* dY; int ldy;   // row pitch
   const float* X;  int ldx;   // X == nullptr -> bias job (X == 1)
   int rows, O, I;
-  float* out;                 // [O, I]
+  float* out;                 // [O, I] gradient (may be nullptr when Adam is fused)
+  float *p, *m, *v;           // p != nullptr: Adam applied in place right after the reduction
+  int which;                  // 0: gen_lr step size (enc_optim / dec_optim), 1: reg_lr (gen_optim / disc_optim)
   int begin;                  // first linear output index of this job
 };
 struct WJobs {
   WJob j[10];
   int n, total;
+  const aae_step_state* st;
 };
-__global__ void __launch_bounds__(256) small_wgrad_kernel(WJobs jobs) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= jobs.total) return;
+constexpr int WG_OUT = 64;    // outputs per CTA
+constexpr int WG_PARTS = 4;   // threads per output (split of the batch rows)
+__global__ void __launch_bounds__(WG_OUT * WG_PARTS) small_wgrad_kernel(WJobs jobs) {
+  __shared__ float part_s[WG_PARTS][WG_OUT];
+  const int el = threadIdx.x % WG_OUT, part = threadIdx.x / WG_OUT;
+  const int idx = blockIdx.x * WG_OUT + el;
+  const bool live = idx < jobs.total;
   int k = 0;
 #pragma unroll
   for (int q = 1; q < 10; ++q)
     if (q < jobs.n && idx >= jobs.j[q].begin) k = q;
   const WJob& J = jobs.j[k];
-  int e = idx - J.begin;
-  int o = e / J.I, i = e - o * J.I;
-  float acc0 = 0.f, acc1 = 0.f;
-  int r = 0;
-  if (J.X) {
-    for (; r + 2 <= J.rows; r += 2) {
-      acc0 = fmaf(J.dY[(size_t)r * J.ldy + o], J.X[(size_t)r * J.ldx + i], acc0);
-      acc1 = fmaf(J.dY[(size_t)(r + 1) * J.ldy + o], J.X[(size_t)(r + 1) * J.ldx + i], acc1);
+  const int e = idx - J.begin;
+  const int o = e / J.I, i = e - o * J.I;
+  float acc = 0.f;
+  if (live) {
+    // rows part, part + 4, ...: 8 independent loads in flight per thread
+    const float* dy = J.dY + o;
+    int r = part;
+    if (J.X) {
+      const float* x = J.X + i;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (; r + 3 * WG_PARTS < J.rows; r += 4 * WG_PARTS) {
+        a0 = fmaf(dy[(size_t)r * J.ldy], x[(size_t)r * J.ldx], a0);
+        a1 = fmaf(dy[(size_t)(r + WG_PARTS) * J.ldy], x[(size_t)(r + WG_PARTS) * J.ldx], a1);
+        a2 = fmaf(dy[(size_t)(r + 2 * WG_PARTS) * J.ldy], x[(size_t)(r + 2 * WG_PARTS) * J.ldx], a2);
+        a3 = fmaf(dy[(size_t)(r + 3 * WG_PARTS) * J.ldy], x[(size_t)(r + 3 * WG_PARTS) * J.ldx], a3);
+      }
+      for (; r < J.rows; r += WG_PARTS) a0 = fmaf(dy[(size_t)r * J.ldy], x[(size_t)r * J.ldx], a0);
+      acc = (a0 + a1) + (a2 + a3);
+    } else {
+      for (; r < J.rows; r += WG_PARTS) acc += dy[(size_t)r * J.ldy];
     }
-    for (; r < J.rows; ++r) acc0 = fmaf(J.dY[(size_t)r * J.ldy + o], J.X[(size_t)r * J.ldx + i], acc0);
-  } else {
-    for (; r < J.rows; ++r) acc0 += J.dY[(size_t)r * J.ldy + o];
   }
-  J.out[e] = acc0 + acc1;
+  part_s[part][el] = acc;
+  __syncthreads();
+  if (part == 0 && live) {
+    float g = (part_s[0][el] + part_s[1][el]) + (part_s[2][el] + part_s[3][el]);
+    if (J.out) J.out[e] = g;
+    if (J.p) {
+      AdamK ak = adam_load(jobs.st, J.which);
+      float pp = J.p[e], mm = J.m[e], vv = J.v[e];
+      adam_update(ak, g, pp, mm, vv);
+      J.p[e] = pp; J.m[e] = mm; J.v[e] = vv;
+    }
+  }
 }
 
-static void add_job(WJobs& js, const float* dY, int ldy, const float* X, int ldx, int rows, int O, int I, float* out) {
+// Adam target of a packed parameter block (nullptr p: gradient only)
+struct OptBlock {
+  float *p, *m, *v;
+  int which;
+};
+static OptBlock opt_of(const aae_adam_block& a) { return OptBlock{a.p, a.m, a.v, a.which}; }
+
+static void add_job(WJobs& js, const float* dY, int ldy, const float* X, int ldx, int rows, int O, int I, float* out,
+                    const OptBlock& ob, size_t off) {
   WJob& j = js.j[js.n++];
-  j.dY = dY; j.ldy = ldy; j.X = X; j.ldx = ldx; j.rows = rows; j.O = O; j.I = I; j.out = out;
+  j.dY = dY; j.ldy = ldy; j.X = X; j.ldx = ldx; j.rows = rows; j.O = O; j.I = I;
+  j.out = out ? out + off : nullptr;
+  j.p = ob.p ? ob.p + off : nullptr;
+  j.m = ob.p ? ob.m + off : nullptr;
+  j.v = ob.p ? ob.v + off : nullptr;
+  j.which = ob.which;
   j.begin = js.total;
   js.total += O * I;
 }
 static int launch_jobs(const WJobs& js, cudaStream_t s) {
-  small_wgrad_kernel<<<cdiv(js.total, 256), 256, 0, s>>>(js);
+  small_wgrad_kernel<<<cdiv(js.total, WG_OUT), WG_OUT * WG_PARTS, 0, s>>>(js);
   return check_launch("small_wgrad");
 }
 
@@ -481,11 +640,14 @@ using namespace aae;
 #define LAUNCH_R(kernel, B, smem_floats_per_row, stream, ...)                                          \
   do {                                                                                                 \
     int R_ = rows_per_cta(B);                                                                          \
-    size_t smem_ = sizeof(float) * (size_t)(smem_floats_per_row) * R_ + 64;                            \
-    if (R_ == 1)                                                                                       \
+    size_t smem_ = sizeof(float) * ((size_t)(smem_floats_per_row) * R_ + 2 * STAGE_FLOATS) + 64;       \
+    if (R_ == 1) {                                                                                     \
+      cudaFuncSetAttribute(kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);        \
       kernel<1><<<cdiv(B, 1), MLP_THREADS, smem_, as_stream(stream)>>>(__VA_ARGS__);                   \
-    else                                                                                               \
+    } else {                                                                                           \
+      cudaFuncSetAttribute(kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);        \
       kernel<4><<<cdiv(B, 4), MLP_THREADS, smem_, as_stream(stream)>>>(__VA_ARGS__);                   \
+    }                                                                                                  \
   } while (0)
 
 extern "C" {
@@ -544,56 +706,64 @@ int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float*
 
 int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, const float* dd1, const float* g_d2,
                  const float* g_d1, const float* g_z, const float* g_e2, const float* g_h1, float* g_enc, float* g_dec,
-                 void* stream) {
-  AAE_REQUIRE(a1 && a2 && zc && dd1 && g_d2 && g_d1 && g_z && g_e2 && g_h1 && g_enc && g_dec, "null pointer");
+                 aae_adam_block enc_opt, aae_adam_block dec_opt, const aae_step_state* st, void* stream) {
+  AAE_REQUIRE(a1 && a2 && zc && dd1 && g_d2 && g_d1 && g_z && g_e2 && g_h1, "null pointer");
+  AAE_REQUIRE((g_enc || enc_opt.p) && (g_dec || dec_opt.p), "no output");
+  AAE_REQUIRE(st || (!enc_opt.p && !dec_opt.p), "fused Adam needs the step state");
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   WJobs js;
-  js.n = 0; js.total = 0;
+  js.n = 0; js.total = 0; js.st = st;
   // enc block [b1 | We2 | be2 | We3 | be3]
-  float* p = g_enc;
-  add_job(js, g_h1, H, nullptr, 0, B, H, 1, p); p += H;
-  add_job(js, g_e2, H, a1, H, B, H, H, p); p += (size_t)H * H;
-  add_job(js, g_e2, H, nullptr, 0, B, H, 1, p); p += H;
-  add_job(js, g_z, C, a2, H, B, C, H, p); p += (size_t)C * H;
-  add_job(js, g_z, C, nullptr, 0, B, C, 1, p);
+  OptBlock eo = opt_of(enc_opt), dop = opt_of(dec_opt);
+  size_t off = 0;
+  add_job(js, g_h1, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;
+  add_job(js, g_e2, H, a1, H, B, H, H, g_enc, eo, off); off += (size_t)H * H;
+  add_job(js, g_e2, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;
+  add_job(js, g_z, C, a2, H, B, C, H, g_enc, eo, off); off += (size_t)C * H;
+  add_job(js, g_z, C, nullptr, 0, B, C, 1, g_enc, eo, off);
   // dec block [Wd1 | bd1 | Wd2 | bd2]
-  p = g_dec;
-  add_job(js, g_d1, H, zc, Cp, B, H, Cp, p); p += (size_t)H * Cp;
-  add_job(js, g_d1, H, nullptr, 0, B, H, 1, p); p += H;
-  add_job(js, g_d2, H, dd1, H, B, H, H, p); p += (size_t)H * H;
-  add_job(js, g_d2, H, nullptr, 0, B, H, 1, p);
+  off = 0;
+  add_job(js, g_d1, H, zc, Cp, B, H, Cp, g_dec, dop, off); off += (size_t)H * Cp;
+  add_job(js, g_d1, H, nullptr, 0, B, H, 1, g_dec, dop, off); off += H;
+  add_job(js, g_d2, H, dd1, H, B, H, H, g_dec, dop, off); off += (size_t)H * H;
+  add_job(js, g_d2, H, nullptr, 0, B, H, 1, g_dec, dop, off);
   return launch_jobs(js, as_stream(stream));
 }
 
-int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, void* stream) {
-  AAE_REQUIRE(acts && grads && g_disc, "null pointer");
+int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, aae_adam_block disc_opt,
+                   const aae_step_state* st, void* stream) {
+  AAE_REQUIRE(acts && grads && (g_disc || disc_opt.p), "null pointer");
+  AAE_REQUIRE(st || !disc_opt.p, "fused Adam needs the step state");
   const int H = d.H, C = d.C, B = d.B;
   // two virtual rows (real, fake) per batch row
   const int AW = C + 2 * H, GW = 2 * H + 1;
   WJobs js;
-  js.n = 0; js.total = 0;
-  float* p = g_disc;  // [Wq1 | bq1 | Wq2 | bq2 | wq3 | bq3]
-  add_job(js, grads, GW, acts, AW, 2 * B, H, C, p); p += (size_t)H * C;
-  add_job(js, grads, GW, nullptr, 0, 2 * B, H, 1, p); p += H;
-  add_job(js, grads + H, GW, acts + C, AW, 2 * B, H, H, p); p += (size_t)H * H;
-  add_job(js, grads + H, GW, nullptr, 0, 2 * B, H, 1, p); p += H;
-  add_job(js, grads + 2 * H, GW, acts + C + H, AW, 2 * B, 1, H, p); p += H;
-  add_job(js, grads + 2 * H, GW, nullptr, 0, 2 * B, 1, 1, p);
+  js.n = 0; js.total = 0; js.st = st;
+  OptBlock qo = opt_of(disc_opt);
+  size_t off = 0;  // [Wq1 | bq1 | Wq2 | bq2 | wq3 | bq3]
+  add_job(js, grads, GW, acts, AW, 2 * B, H, C, g_disc, qo, off); off += (size_t)H * C;
+  add_job(js, grads, GW, nullptr, 0, 2 * B, H, 1, g_disc, qo, off); off += H;
+  add_job(js, grads + H, GW, acts + C, AW, 2 * B, H, H, g_disc, qo, off); off += (size_t)H * H;
+  add_job(js, grads + H, GW, nullptr, 0, 2 * B, H, 1, g_disc, qo, off); off += H;
+  add_job(js, grads + 2 * H, GW, acts + C + H, AW, 2 * B, 1, H, g_disc, qo, off); off += H;
+  add_job(js, grads + 2 * H, GW, nullptr, 0, 2 * B, 1, 1, g_disc, qo, off);
   return launch_jobs(js, as_stream(stream));
 }
 
 int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z, const float* g_e2, const float* g_h1,
-                  float* g_enc, void* stream) {
-  AAE_REQUIRE(a1 && a2 && g_z && g_e2 && g_h1 && g_enc, "null pointer");
+                  float* g_enc, aae_adam_block enc_opt, const aae_step_state* st, void* stream) {
+  AAE_REQUIRE(a1 && a2 && g_z && g_e2 && g_h1 && (g_enc || enc_opt.p), "null pointer");
+  AAE_REQUIRE(st || !enc_opt.p, "fused Adam needs the step state");
   const int H = d.H, C = d.C, B = d.B;
   WJobs js;
-  js.n = 0; js.total = 0;
-  float* p = g_enc;
-  add_job(js, g_h1, H, nullptr, 0, B, H, 1, p); p += H;
-  add_job(js, g_e2, H, a1, H, B, H, H, p); p += (size_t)H * H;
-  add_job(js, g_e2, H, nullptr, 0, B, H, 1, p); p += H;
-  add_job(js, g_z, C, a2, H, B, C, H, p); p += (size_t)C * H;
-  add_job(js, g_z, C, nullptr, 0, B, C, 1, p);
+  js.n = 0; js.total = 0; js.st = st;
+  OptBlock eo = opt_of(enc_opt);
+  size_t off = 0;
+  add_job(js, g_h1, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;
+  add_job(js, g_e2, H, a1, H, B, H, H, g_enc, eo, off); off += (size_t)H * H;
+  add_job(js, g_e2, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;
+  add_job(js, g_z, C, a2, H, B, C, H, g_enc, eo, off); off += (size_t)C * H;
+  add_job(js, g_z, C, nullptr, 0, B, C, 1, g_enc, eo, off);
   return launch_jobs(js, as_stream(stream));
 }
 

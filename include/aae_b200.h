@@ -69,6 +69,14 @@ int aae_device_check(int dev);
 /* ---- step bookkeeping ------------------------------------------------------------------- */
 int aae_step_state_init(aae_step_state* st, float gen_lr, float reg_lr, uint64_t seed, void* stream);
 int aae_step_tick(aae_step_state* st, void* stream);
+/* One launch for the start of a partial_fit: aae_step_tick + zero of loss_sums[0..n_sums), of the
+ * touched-row counter n_uniq (may be NULL), of dh2[0..n_dh2) and of the first indptr[B]*H floats of the
+ * compact first-layer gradient buffers G1 / G2 (each may be NULL). */
+int aae_step_begin(aae_step_state* st, double* loss_sums, int n_sums, int32_t* n_uniq, float* dh2, int64_t n_dh2,
+                   float* G1, float* G2, const int32_t* indptr, int B, int H, void* stream);
+/* One launch for its end: aae_batch_slots_reset + aae_finish_losses. */
+int aae_step_end(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, const double* sums,
+                 double n_total, int B, float* losses, void* stream);
 
 /* ---- K1: encoder first layer on the sparse multi-hot input ---------------------------------
  * Replaces F.normalize(inp, 1) + Encoder.lin1 (aae.py:132-135): out[b,:] = b1 + sum_{i in set_b}
@@ -79,9 +87,10 @@ int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const floa
 
 /* ---- touched-row bookkeeping for the sparse first layer -------------------------------------
  * slot_of[V] (all -1 between steps) maps an item of the current batch to a dense slot, uniq[]
- * lists the items, n_uniq[0] their count.  Only items in [v_begin, v_end) get slots. */
+ * lists the items, n_uniq[0] their count.  Only items in [v_begin, v_end) get slots.
+ * counter_is_zero != 0: n_uniq[0] was already cleared (aae_step_begin), skip the clearing launch. */
 int aae_batch_slots(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end,
-                    int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, void* stream);
+                    int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, int counter_is_zero, void* stream);
 int aae_batch_slots_reset(int32_t* slot_of, const int32_t* uniq, int32_t* n_uniq, int cap, void* stream);
 
 /* ---- K2: weight gradient of the sparse first layer ------------------------------------------
@@ -145,13 +154,24 @@ int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float*
                   aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
                   float* g_e2, float* g_h1, double* loss_sum, void* stream);
 
-/* Weight/bias gradients of the small layers: block-shaped outputs matching the parameter blocks. */
+/* Weight/bias gradients of the small layers (reductions over the batch): block-shaped outputs matching
+ * the parameter blocks.  With an aae_adam_block whose p is non-NULL the optimizer step of that block
+ * (enc_optim/dec_optim aae.py:706-707, disc_optim :731, gen_optim :741) is applied in the same kernel,
+ * in place, right after each element's reduction; the gradient pointer may then be NULL. */
+typedef struct {
+  float* p;      /* packed parameter block (NULL: gradient only) */
+  float* m;      /* Adam first moments, same shape */
+  float* v;      /* Adam second moments */
+  int which;     /* 0: step_size_gen (enc_optim, dec_optim), 1: step_size_reg (gen_optim, disc_optim) */
+} aae_adam_block;
 int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, const float* dd1,
                  const float* g_d2, const float* g_d1, const float* g_z, const float* g_e2, const float* g_h1,
-                 float* g_enc, float* g_dec, void* stream);
-int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, void* stream);
-int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z, const float* g_e2,
-                  const float* g_h1, float* g_enc, void* stream);
+                 float* g_enc, float* g_dec, aae_adam_block enc_opt, aae_adam_block dec_opt,
+                 const aae_step_state* st, void* stream);
+int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, aae_adam_block disc_opt,
+                   const aae_step_state* st, void* stream);
+int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z, const float* g_e2, const float* g_h1,
+                  float* g_enc, aae_adam_block enc_opt, const aae_step_state* st, void* stream);
 
 /* ---- K3: the n_items-wide decoder output layer, training ------------------------------------
  * Replaces Decoder.lin3 + torch.sigmoid (aae.py:176-177), F.binary_cross_entropy(x+1e-12, t+1e-12)
@@ -160,7 +180,9 @@ int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z
  * [v_begin, v_begin+Vloc): loss_sum[0] += sum of BCE terms, dh2[B,H] += dZ.Wd3 (old weights), then
  * Wd3/bd3 and their Adam moments are updated in place.  n_total = B * V_global (the BCE mean).
  * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 tensor-core kernel (3xTF32, fp32-accurate),
- * 2 = tcgen05 single-pass TF32. */
+ * 2 = tcgen05 single-pass TF32; 1 and 2 run the software-pipelined kernel when the shape fits its TMEM /
+ * shared-memory envelope (n_hidden 100: batch <= 104) and the one-tile-at-a-time kernel otherwise;
+ * 3 / 4 force the latter (3xTF32 / TF32). */
 int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
                       float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices,
                       double n_total, const aae_step_state* st, float* dh2, double* loss_sum, int impl,

@@ -80,6 +80,20 @@ def test_tc_train_matches_fp32_kernel(B, V):
     assert _rel(mg, mr) < 2e-5 and _rel(vg, vr) < 4e-5
 
 
+@pytest.mark.parametrize("B,V,H,impl", [(100, 3200, 100, 3), (100, 40000, 100, 1), (64, 5000, 64, 1), (50, 3000, 116, 1),
+                                        (104, 9000, 100, 1), (100, 4733, 100, 1)])
+def test_tc_train_variants_match_fp32_kernel(B, V, H, impl):
+    """impl 3 = the one-tile-at-a-time kernel; impl 1 = pipelined kernel (compile-time and run-time n_hidden,
+    many tiles per CTA, ragged last tile) or its fallback when the shape is outside the pipelined envelope."""
+    ref, Wr, br, mr, vr = _run_train(0, B, V, H=H, steps=3)
+    got, Wg, bg, mg, vg = _run_train(impl, B, V, H=H, steps=3)
+    for (lr, dr), (lg, dg) in zip(ref, got):
+        assert abs(lg - lr) / abs(lr) < 2e-6
+        assert _rel(dg, dr) < 2e-5
+    assert _rel(Wg, Wr) < 2e-6 and _rel(bg, br) < 2e-6
+    assert _rel(mg, mr) < 2e-5 and _rel(vg, vr) < 4e-5
+
+
 def test_tc_single_tf32_is_close_but_not_parity():
     ref, Wr, *_ = _run_train(0, 100, 3200)
     got, Wg, *_ = _run_train(2, 100, 3200)
