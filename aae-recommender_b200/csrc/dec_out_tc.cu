@@ -151,6 +151,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue only: the registers are valid after tmem_ld8_wait (which ties them to the wait)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t* r, float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -578,6 +591,31 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// Row cursor with one entry of lookahead: n0 = indices[pos] is compared every tile, n1 = indices[pos+1] was
+// requested when the cursor last moved, so the compare never waits on a load issued in the same tile.
+struct RowCursor2 {
+  int pos, end, n0, n1;
+};
+__device__ __forceinline__ void cursor_advance(RowCursor2& c, const int32_t* __restrict__ indices) {
+  c.n0 = c.n1;
+  ++c.pos;
+  c.n1 = (c.pos + 1 < c.end) ? __ldg(indices + c.pos + 1) : 0x7fffffff;
+}
+// bits of the items of [v0g, v0g + TN) in the row; first skips the row's items below v0g
+__device__ __forceinline__ uint32_t tile_targets2(RowCursor2& c, const int32_t* __restrict__ indices, int v0g) {
+  while (c.n0 < v0g) cursor_advance(c, indices);
+  uint32_t m = 0;
+  while (c.n0 < v0g + TN) {
+    m |= 1u << (c.n0 - v0g);
+    cursor_advance(c, indices);
+  }
+  return m;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  if (bytes >= 16u)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes & ~15u) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pipelined training kernel (the default for the reference's shapes).  Same three GEMMs and epilogues as
 // above, but the tile loop is software-pipelined around ONE dedicated MMA-issuing warp:
@@ -695,10 +733,31 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const SmemOp op_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
     const SmemOp op_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
     const int ksteps_b = BK / 8;
+    // L2 prefetch of a tile's W/m/v rows (contiguous: TN*H floats each) and bias triplet
+    auto prefetch_tile = [&](int j) {
+      if (j >= n_my) return;
+      const int tile = blockIdx.x + j * G;
+      const int v0 = tile * TN;
+      const int nv = min(TN, Vloc - v0);
+      const uint32_t wbytes = (uint32_t)nv * (uint32_t)H * 4u;
+      prefetch_l2_bulk(Wd3 + (size_t)v0 * H, wbytes);
+      prefetch_l2_bulk(mW + (size_t)v0 * H, wbytes);
+      prefetch_l2_bulk(vW + (size_t)v0 * H, wbytes);
+      prefetch_l2_bulk(bd3 + v0, (uint32_t)nv * 4u);
+      prefetch_l2_bulk(mb + v0, (uint32_t)nv * 4u);
+      prefetch_l2_bulk(vb + v0, (uint32_t)nv * 4u);
+    };
+    if (elect_one()) {
+      prefetch_tile(1);
+      prefetch_tile(2);
+      prefetch_tile(3);
+    }
+    __syncwarp();
     for (int it = 0; it <= n_my; ++it) {
       named_bar_sync(1, NT2);
       tc_fence_after();
       if (elect_one()) {
+        prefetch_tile(it + 4);
         if (it > 0) {
           const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
           issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g1, 0u);
@@ -736,15 +795,16 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const uint32_t dt_off = (uint32_t)cpart * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
     const float rvf = (brow < B) ? 1.0f : 0.f;
-    RowCursor cur;
+    RowCursor2 cur;
     cur.pos = cur.end = 0;
-    cur.nxt = 0x7fffffff;
+    cur.n0 = cur.n1 = 0x7fffffff;
     if (brow < B) {
       cur.pos = indptr[brow];
       cur.end = indptr[brow + 1];
       int first = v_begin + (int)blockIdx.x * TN;
       while (cur.pos < cur.end && indices[cur.pos] < first) ++cur.pos;
-      if (cur.pos < cur.end) cur.nxt = indices[cur.pos];
+      if (cur.pos < cur.end) cur.n0 = indices[cur.pos];
+      if (cur.pos + 1 < cur.end) cur.n1 = indices[cur.pos + 1];
     }
     WChunk wc[WCH];
     make_wchunks(wc, g);
@@ -768,15 +828,40 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     float* const eW = is_bias ? bd3 : Wd3;
     float* const eM = is_bias ? mb : mW;
     float* const eV = is_bias ? vb : vW;
-    float pw[CW], pm[CW], pv[CW];
-    size_t eoff = 0;
-    int ecnt = 0;
     uint32_t phase = 0;
     float loss_local = 0.f;
 
-    auto e2_apply = [&](int i_done) {
+    // E2 of tile index j (its dW'^T is complete): W/m/v come from L2 (bulk-prefetched by the issuer warp two
+    // iterations ahead), so the loads are issued here, next to their use, instead of living in registers.
+    auto e2_apply = [&](int j_done) {
+      const int tile = blockIdx.x + j_done * G;
+      const int v0 = tile * TN;
+      const int nv = min(TN, Vloc - v0);
+      uint32_t gr[CW];
+      tmem_ld8_issue(lane_addr + T2_DW + (uint32_t)(j_done & 1) * 32u + cpart * CW, gr);
+      size_t eoff;
+      int ecnt;
+      if (is_bias) {
+        eoff = (size_t)v0 + cpart * CW + jb;
+        ecnt = (cpart * CW + jb < nv) ? 1 : 0;
+      } else {
+        eoff = (size_t)(v0 + cpart * CW) * H + brow;
+        ecnt = (brow < H) ? max(0, min(CW, nv - cpart * CW)) : 0;
+      }
+      float* pW = eW + eoff;
+      float* pM = eM + eoff;
+      float* pV = eV + eoff;
+      float pw[CW], pm[CW], pv[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        if (j < ecnt) {
+          pw[j] = pW[(size_t)j * H];
+          pm[j] = __ldcs(pM + (size_t)j * H);
+          pv[j] = __ldcs(pV + (size_t)j * H);
+        }
+      }
       float gw[CW];
-      tmem_ld8(lane_addr + T2_DW + (uint32_t)(i_done & 1) * 32u + cpart * CW, gw);
+      tmem_ld8_wait(gr, gw);
       if (bias_warp) {
         float gb = 0.f;
 #pragma unroll
@@ -786,9 +871,6 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         }
         if (is_bias) gw[0] = gb;
       }
-      float* pW = eW + eoff;
-      float* pM = eM + eoff;
-      float* pV = eV + eoff;
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
         if (j < ecnt) {
@@ -806,20 +888,30 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       const int v0 = tile * TN;
       const int nv = min(TN, Vloc - v0);
       // positives of this tile for this thread's row (cursor over the row's sorted CSR columns)
-      while (cur.nxt < v_begin + v0) {
-        ++cur.pos;
-        cur.nxt = (cur.pos < cur.end) ? indices[cur.pos] : 0x7fffffff;
-      }
-      const uint32_t tb = (tile_targets(cur, indices, v_begin + v0) >> (cpart * CW)) & 0xffu;
+      const uint32_t tb = (tile_targets2(cur, indices, v_begin + v0) >> (cpart * CW)) & 0xffu;
       const int vm = nv - cpart * CW;                 // valid columns of this thread's 8 (>= 8: all)
 
       mbar_wait(&bar_mma, phase);                     // G1(i) and G2/G3(i-1) have completed
       phase ^= 1;
       tc_fence_after();
+      uint32_t zr[CW];
+      tmem_ld8_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, zr);
+      // ---- operands of the next MMA batch: W'(i) transposed for G2(i), W'(i+1) for G1(i+1)
+      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);
+      if (i + 1 < n_my) {
+        if ((i + 1) & 1) store_wb_regs(wB, wc, wb1_hi, wb1_lo, with_lo);
+        else store_wb_regs(wB, wc, wb0_hi, wb0_lo, with_lo);
+      }
+#pragma unroll
+      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
+      if (i + 2 < n_my) {
+        const int t2 = tile + 2 * G;
+        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
+      }
       // ---- E1(i)
       {
         float z[CW], dzh[CW], dzl[CW];
-        tmem_ld8(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, z);
+        tmem_ld8_wait(zr, z);
         float zmax = 0.f;
 #pragma unroll
         for (int j = 0; j < CW; ++j) zmax = fmaxf(zmax, fabsf(z[j]));
@@ -851,45 +943,12 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         tmem_st8(lane_addr + T2_DZH + cpart * CW, dzh);
         if (with_lo) tmem_st8(lane_addr + T2_DZL + cpart * CW, dzl);
       }
-      // ---- operands of the next MMA batch: W'(i) transposed for G2(i), W'(i+1) for G1(i+1)
-      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);
-      if (i + 1 < n_my) {
-        if ((i + 1) & 1) store_wb_regs(wB, wc, wb1_hi, wb1_lo, with_lo);
-        else store_wb_regs(wB, wc, wb0_hi, wb0_lo, with_lo);
-      }
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();
       named_bar_arrive(1, NT2);
-#pragma unroll
-      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
-      if (i + 2 < n_my) {
-        const int t2 = tile + 2 * G;
-        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
-      }
       // ---- E2(i-1): overlaps the MMAs of iteration i
       if (i > 0) e2_apply(i - 1);
-      // ---- W/m/v of tile i in the E2 layout (consumed one iteration later)
-      {
-        if (is_bias) {
-          eoff = (size_t)v0 + cpart * CW + jb;
-          ecnt = (cpart * CW + jb < nv) ? 1 : 0;
-        } else {
-          eoff = (size_t)(v0 + cpart * CW) * H + brow;
-          ecnt = (brow < H) ? max(0, min(CW, vm)) : 0;
-        }
-        const float* pW = eW + eoff;
-        const float* pM = eM + eoff;
-        const float* pV = eV + eoff;
-#pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          if (j < ecnt) {
-            pw[j] = pW[(size_t)j * H];
-            pm[j] = __ldcs(pM + (size_t)j * H);
-            pv[j] = __ldcs(pV + (size_t)j * H);
-          }
-        }
-      }
     }
     mbar_wait(&bar_mma, phase);                       // G2/G3 of the last tile
     tc_fence_after();
