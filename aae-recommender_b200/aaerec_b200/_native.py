@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaae_b200.so")
+LIB_PATH = os.environ.get("AAE_B200_LIB") or os.path.join(_HERE, "libaae_b200.so")   # override: kernel A/B experiments
 
 P = C.c_void_p
 I = C.c_int

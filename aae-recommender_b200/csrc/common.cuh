@@ -47,18 +47,23 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 // m/denom uses the 2-ulp fast division, sqrt the approximate instruction: both far inside the 1e-4
 // parity tolerance (the update is lr * O(1)), and they keep the fused epilogues off the slow paths.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // max relative error 2^-23; denom >= eps = 1e-8 here
+  return r;
+}
 __device__ __forceinline__ void adam_update(const AdamK& k, float g, float& p, float& m, float& v) {
   m = fmaf(k.w1, g - m, m);
   v = fmaf(k.w2 * g, g, v * k.beta2);
   float denom = fmaf(sqrt_approx(v), k.inv_bc2_sqrt, k.eps);
-  p = fmaf(-k.step_size, __fdividef(m, denom), p);
+  p = fmaf(-k.step_size, m * rcp_approx(denom), p);
 }
 // zero-gradient update (rows that are not in the batch)
 __device__ __forceinline__ void adam_update_zero(const AdamK& k, float& p, float& m, float& v) {
   m = fmaf(k.w1, -m, m);
   v = v * k.beta2;
   float denom = fmaf(sqrt_approx(v), k.inv_bc2_sqrt, k.eps);
-  p = fmaf(-k.step_size, __fdividef(m, denom), p);
+  p = fmaf(-k.step_size, m * rcp_approx(denom), p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,13 @@
 // Reference: aaerec/aae.py:176-177 (lin3 + sigmoid), :693-695 (BCE), :703 (backward), :707 (dec_optim).
 #include "common.cuh"
 
+#ifndef TC_WAIT_HINT
+#define TC_WAIT_HINT 0x989680u
+#endif
+#ifndef TC2_G1_FIRST
+#define TC2_G1_FIRST 1
+#endif
+
 namespace aae {
 namespace tc {
 
@@ -79,15 +86,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
   while (!done) {
-    if (++spins > (1u << 26)) __trap();   // a lost MMA completion must not hang the device
+    if (++spins > (1u << 22)) __trap();   // a lost MMA completion must not hang the device
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(TC_WAIT_HINT)   // suspend-time hint: sleep in hardware, do not spin
         : "memory");
   }
 }
@@ -591,15 +598,26 @@ __global__ void __launch_bounds__(NT, 1) dec_out_train_tc_kernel(
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// Row cursor with one entry of lookahead: n0 = indices[pos] is compared every tile, n1 = indices[pos+1] was
-// requested when the cursor last moved, so the compare never waits on a load issued in the same tile.
+// Row cursor with three entries of lookahead: n0 = indices[pos] is compared every tile; n1..n3 were requested
+// when the cursor last moved, so a compare only waits on a load when the row has four items within one
+// stretch of tiles (the stall would otherwise hit every warp: 32 rows advance independently).
 struct RowCursor2 {
-  int pos, end, n0, n1;
+  int pos, end, n0, n1, n2, n3;
 };
+__device__ __forceinline__ void cursor_init(RowCursor2& c, const int32_t* __restrict__ indices, int pos, int end) {
+  c.pos = pos;
+  c.end = end;
+  c.n0 = (pos < end) ? __ldg(indices + pos) : 0x7fffffff;
+  c.n1 = (pos + 1 < end) ? __ldg(indices + pos + 1) : 0x7fffffff;
+  c.n2 = (pos + 2 < end) ? __ldg(indices + pos + 2) : 0x7fffffff;
+  c.n3 = (pos + 3 < end) ? __ldg(indices + pos + 3) : 0x7fffffff;
+}
 __device__ __forceinline__ void cursor_advance(RowCursor2& c, const int32_t* __restrict__ indices) {
   c.n0 = c.n1;
+  c.n1 = c.n2;
+  c.n2 = c.n3;
   ++c.pos;
-  c.n1 = (c.pos + 1 < c.end) ? __ldg(indices + c.pos + 1) : 0x7fffffff;
+  c.n3 = (c.pos + 3 < c.end) ? __ldg(indices + c.pos + 3) : 0x7fffffff;
 }
 // bits of the items of [v0g, v0g + TN) in the row; first skips the row's items below v0g
 __device__ __forceinline__ uint32_t tile_targets2(RowCursor2& c, const int32_t* __restrict__ indices, int v0g) {
@@ -643,14 +661,26 @@ __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("
 
 // target 0 and |z| < 16: ATen's clamped formula (common.cuh bce_term) equals softplus(z) / sigmoid(z)/N to
 // far below 1e-6 relative; everything else goes through bce_term.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// ~15 instructions: u = e^-|z| (one ex2), 1/(1+u) (one rcp), log(1+u) (one lg2).  log(1+u) through lg2 has an
+// absolute error of one rounding of 1+u (6e-8, unbiased) per element: invisible in the mean over B*V terms;
+// the gradient sigmoid(z)/N is accurate to ~2 ulp.
 __device__ __forceinline__ float bce_neg_fast(float z, float inv_n, float& dz) {
-  float u = __expf(-fabsf(z));
-  float r = __fdividef(1.0f, 1.0f + u);
+  float u = ex2_approx(-1.4426950408889634f * fabsf(z));
+  float t = 1.0f + u;
+  float r = rcp_approx(t);
   float x = (z >= 0.f) ? r : u * r;
-  float poly = u * (1.0f - u * (0.5f - u * (0.33333334f - u * (0.25f - 0.2f * u))));
-  float l1p = (u < 0.0625f) ? poly : __logf(1.0f + u);
   dz = x * inv_n;
-  return fmaxf(z, 0.f) + l1p;
+  return fmaf(lg2_approx(t), 0.6931471805599453f, fmaxf(z, 0.f));
 }
 
 __device__ __forceinline__ void store_wb_regs(const float4* wr, const WChunk* wc, unsigned char* wb_hi,
@@ -680,43 +710,78 @@ __device__ __forceinline__ void store_wt_regs(const float4* wr, const WChunk* wc
   }
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk copy global -> shared (contiguous bytes, 16-byte aligned), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <int SPLIT, int HC>
 __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const float* __restrict__ h2, int B, int Hrt, float* __restrict__ Wd3, float* __restrict__ bd3,
     float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
     int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
-    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum) {
+    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum, int smem_total) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_g1, bar_g23;   // completion of G1(i) / of G3(i-1)+G2(i-1)
+  __shared__ uint64_t bar_stage;         // E2 stage (W/m/v rows of one tile) filled by TMA
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[NT / 32];
   const int H = HC ? HC : Hrt;
   const Geom g = make_geom(H);
   constexpr bool with_lo = (SPLIT == 3);
+  const int BK = (B + 7) & ~7;
+  // Hb keeps only round8(B) rows: the M = 128 MMA reads the rows beyond from whatever follows in shared
+  // memory (finite numbers: everything is zero-filled first), and those logit rows are never used.
+  const uint32_t hb_eff = (uint32_t)(BK / 8) * g.hb_sbo;
   unsigned char* hb_hi = smem;
-  unsigned char* hb_lo = hb_hi + g.hb_bytes;
-  unsigned char* wb0_hi = hb_lo + g.hb_bytes;
-  unsigned char* wb0_lo = wb0_hi + g.wb_bytes;
-  unsigned char* wb1_hi = wb0_lo + g.wb_bytes;
-  unsigned char* wb1_lo = wb1_hi + g.wb_bytes;
-  unsigned char* wt_hi = wb1_lo + g.wb_bytes;
+  unsigned char* hb_lo = hb_hi + hb_eff;
+  unsigned char* wb_hi = hb_lo + hb_eff;
+  unsigned char* wb_lo = wb_hi + g.wb_bytes;
+  unsigned char* wt_hi = wb_lo + g.wb_bytes;
   unsigned char* wt_lo = wt_hi + g.wt_bytes;
   unsigned char* dt_hi = wt_lo + g.wt_bytes;
   unsigned char* dt_lo = dt_hi + g.dt_bytes;
+  float* sW = reinterpret_cast<float*>(dt_lo + g.dt_bytes);
+  float* sM = sW + TN * H;
+  float* sV = sM + TN * H;
+  float* sB = sV + TN * H;               // [3][TN]: bd3, mb, vb of the tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (Vloc + TN - 1) / TN;
   const int G = gridDim.x;
   const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;     // tiles blockIdx.x, +G, ... (grid <= n_tiles)
-  const int BK = (B + 7) & ~7;
   const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
 
   if (warp == NT / 32) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
-    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_g1, 1);
+    mbar_init(&bar_g23, 1);
+    mbar_init(&bar_stage, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int q = tid; q < (int)(2 * g.wt_bytes) / 16; q += NT2) reinterpret_cast<float4*>(wt_hi)[q] = make_float4(0, 0, 0, 0);
-  fill_hb(hb_hi, hb_lo, g, h2, 0, B, with_lo, NT2);
+  for (int q = tid; q < smem_total / 16; q += NT2) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    const int ncg = g.Kp / 4;
+    for (int q = tid; q < BK * ncg; q += NT2) {
+      int r = q / ncg, cg = q - r * ncg;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < B) {
+        int c = cg * 4;
+        if (c + 3 < H) x = *reinterpret_cast<const float4*>(h2 + (size_t)r * H + c);
+        else if (c == H) x.x = 1.0f;
+      }
+      store_split4(hb_hi, hb_lo, r, cg, g.hb_sbo, x, with_lo);
+    }
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -726,50 +791,62 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
   const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
 
   if (warp == NT / 32) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer + TMA producer =================
     const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
-    const SmemOp op_wb0 = make_op(wb0_hi, wb0_lo, CORE, g.wb_sbo, 2 * CORE);
-    const SmemOp op_wb1 = make_op(wb1_hi, wb1_lo, CORE, g.wb_sbo, 2 * CORE);
+    const SmemOp op_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
     const SmemOp op_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
     const SmemOp op_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
     const int ksteps_b = BK / 8;
-    // L2 prefetch of a tile's W/m/v rows (contiguous: TN*H floats each) and bias triplet
-    auto prefetch_tile = [&](int j) {
+    // tile j of this CTA -> E2 stage (a ragged last tile is read from global memory by E2 instead)
+    auto stage_copy = [&](int j) {
+      const int v0 = ((int)blockIdx.x + j * G) * TN;
+      if (Vloc - v0 >= TN) {
+        const uint32_t wbytes = (uint32_t)(TN * H) * 4u, bbytes = TN * 4u;
+        mbar_arrive_expect_tx(&bar_stage, 3u * wbytes + 3u * bbytes);
+        bulk_g2s(sW, Wd3 + (size_t)v0 * H, wbytes, &bar_stage);
+        bulk_g2s(sM, mW + (size_t)v0 * H, wbytes, &bar_stage);
+        bulk_g2s(sV, vW + (size_t)v0 * H, wbytes, &bar_stage);
+        bulk_g2s(sB, bd3 + v0, bbytes, &bar_stage);
+        bulk_g2s(sB + TN, mb + v0, bbytes, &bar_stage);
+        bulk_g2s(sB + 2 * TN, vb + v0, bbytes, &bar_stage);
+      } else {
+        mbar_arrive(&bar_stage);
+      }
+    };
+    // L2 prefetch of the W rows that the loader warps read two tiles ahead
+    auto prefetch_w = [&](int j) {
       if (j >= n_my) return;
-      const int tile = blockIdx.x + j * G;
-      const int v0 = tile * TN;
+      const int v0 = ((int)blockIdx.x + j * G) * TN;
       const int nv = min(TN, Vloc - v0);
-      const uint32_t wbytes = (uint32_t)nv * (uint32_t)H * 4u;
-      prefetch_l2_bulk(Wd3 + (size_t)v0 * H, wbytes);
-      prefetch_l2_bulk(mW + (size_t)v0 * H, wbytes);
-      prefetch_l2_bulk(vW + (size_t)v0 * H, wbytes);
-      prefetch_l2_bulk(bd3 + v0, (uint32_t)nv * 4u);
-      prefetch_l2_bulk(mb + v0, (uint32_t)nv * 4u);
-      prefetch_l2_bulk(vb + v0, (uint32_t)nv * 4u);
+      prefetch_l2_bulk(Wd3 + (size_t)v0 * H, (uint32_t)nv * (uint32_t)H * 4u);
     };
     if (elect_one()) {
-      prefetch_tile(1);
-      prefetch_tile(2);
-      prefetch_tile(3);
+      stage_copy(0);
+      prefetch_w(2);
+      prefetch_w(3);
     }
     __syncwarp();
     for (int it = 0; it <= n_my; ++it) {
       named_bar_sync(1, NT2);
       tc_fence_after();
       if (elect_one()) {
-        prefetch_tile(it + 4);
+        // logits of the next tile first: its epilogue math then overlaps the backward GEMMs of this tile
+        if (it < n_my) issue_gemm<SPLIT>(tmem + T2_Z + (uint32_t)(it & 1) * 32u, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
+        mma_commit(&bar_g1);
         if (it > 0) {
           const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
           issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g1, 0u);
           issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2, it > 1 ? 1u : 0u);
         }
-        if (it < n_my) {
-          if (it & 1) issue_gemm<SPLIT>(tmem + T2_Z + 32u, op_hb, op_wb1, g.Kp / 8, idesc_g1, 0u);
-          else issue_gemm<SPLIT>(tmem + T2_Z, op_hb, op_wb0, g.Kp / 8, idesc_g1, 0u);
-        }
-        mma_commit(&bar_mma);
+        mma_commit(&bar_g23);
+        prefetch_w(it + 4);
       }
       __syncwarp();
+      if (it >= 2) {
+        named_bar_sync(2, NT2);          // every epilogue thread has read tile it-2 out of the stage
+        if (elect_one()) stage_copy(it - 1);
+        __syncwarp();
+      }
     }
   } else {
     // ================= epilogue / loader warps =================
@@ -796,15 +873,13 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
     const float rvf = (brow < B) ? 1.0f : 0.f;
     RowCursor2 cur;
-    cur.pos = cur.end = 0;
-    cur.n0 = cur.n1 = 0x7fffffff;
-    if (brow < B) {
-      cur.pos = indptr[brow];
-      cur.end = indptr[brow + 1];
-      int first = v_begin + (int)blockIdx.x * TN;
-      while (cur.pos < cur.end && indices[cur.pos] < first) ++cur.pos;
-      if (cur.pos < cur.end) cur.n0 = indices[cur.pos];
-      if (cur.pos + 1 < cur.end) cur.n1 = indices[cur.pos + 1];
+    {
+      int p0 = 0, p1 = 0;
+      if (brow < B) {
+        p0 = indptr[brow];
+        p1 = indptr[brow + 1];
+      }
+      cursor_init(cur, indices, p0, p1);
     }
     WChunk wc[WCH];
     make_wchunks(wc, g);
@@ -812,15 +887,15 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     {
       const int t0 = blockIdx.x;
       load_w_regs(wA, wc, Wd3, bd3, H, t0 * TN, min(TN, Vloc - t0 * TN));
-      store_wb_regs(wA, wc, wb0_hi, wb0_lo, with_lo);
+      store_wb_regs(wA, wc, wb_hi, wb_lo, with_lo);
       if (n_my > 1) load_w_regs(wB, wc, Wd3, bd3, H, (t0 + G) * TN, min(TN, Vloc - (t0 + G) * TN));
     }
     fence_async_smem();
     tc_fence_before();
     named_bar_arrive(1, NT2);
 
-    // E2 addressing: normal lanes (k < H) walk 8 item rows of Wd3/mW/vW at pitch H; lanes H+1..H+8 own one
-    // bias element each; all use the same immediate offsets j*H (bias lanes only ever touch j = 0).
+    // E2 addressing: normal lanes (k < H) walk 8 item rows at pitch H; lanes H+1..H+8 own one bias element
+    // each; all use the same immediate offsets j*H (bias lanes only ever touch j = 0).
     const int kb = H & 31;                           // lane of hidden unit H inside its warp
     const bool bias_warp = (q4 == (H >> 5));
     const int jb = brow - (H + 1);                   // bias lanes: 0..7
@@ -828,11 +903,14 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     float* const eW = is_bias ? bd3 : Wd3;
     float* const eM = is_bias ? mb : mW;
     float* const eV = is_bias ? vb : vW;
-    uint32_t phase = 0;
+    const float* const sWp = is_bias ? sB + cpart * CW + jb : sW + cpart * CW * H + brow;
+    const float* const sMp = is_bias ? sB + TN + cpart * CW + jb : sM + cpart * CW * H + brow;
+    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CW + jb : sV + cpart * CW * H + brow;
+    const int ecnt_full = is_bias ? 1 : (brow < H ? CW : 0);
+    uint32_t phase = 0, phase_e = 0;
     float loss_local = 0.f;
 
-    // E2 of tile index j (its dW'^T is complete): W/m/v come from L2 (bulk-prefetched by the issuer warp two
-    // iterations ahead), so the loads are issued here, next to their use, instead of living in registers.
+    // E2 of tile index j (its dW'^T is complete): old W/m/v come from the TMA-filled stage
     auto e2_apply = [&](int j_done) {
       const int tile = blockIdx.x + j_done * G;
       const int v0 = tile * TN;
@@ -852,14 +930,28 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       float* pM = eM + eoff;
       float* pV = eV + eoff;
       float pw[CW], pm[CW], pv[CW];
+      mbar_wait(&bar_stage, phase_e);
+      phase_e ^= 1;
+      if (nv == TN) {
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        if (j < ecnt) {
-          pw[j] = pW[(size_t)j * H];
-          pm[j] = __ldcs(pM + (size_t)j * H);
-          pv[j] = __ldcs(pV + (size_t)j * H);
+        for (int j = 0; j < CW; ++j) {
+          if (j < ecnt_full) {
+            pw[j] = sWp[j * H];
+            pm[j] = sMp[j * H];
+            pv[j] = sVp[j * H];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          if (j < ecnt) {
+            pw[j] = pW[(size_t)j * H];
+            pm[j] = pM[(size_t)j * H];
+            pv[j] = pV[(size_t)j * H];
+          }
         }
       }
+      if (j_done + 1 < n_my) named_bar_arrive(2, NT2);   // the stage may be refilled (tile j_done + 1)
       float gw[CW];
       tmem_ld8_wait(gr, gw);
       if (bias_warp) {
@@ -891,26 +983,16 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       const uint32_t tb = (tile_targets2(cur, indices, v_begin + v0) >> (cpart * CW)) & 0xffu;
       const int vm = nv - cpart * CW;                 // valid columns of this thread's 8 (>= 8: all)
 
-      mbar_wait(&bar_mma, phase);                     // G1(i) and G2/G3(i-1) have completed
-      phase ^= 1;
+      // ---- E1(i), math part: needs only G1(i)
+      mbar_wait(&bar_g1, phase);
       tc_fence_after();
-      uint32_t zr[CW];
-      tmem_ld8_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, zr);
-      // ---- operands of the next MMA batch: W'(i) transposed for G2(i), W'(i+1) for G1(i+1)
-      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);
-      if (i + 1 < n_my) {
-        if ((i + 1) & 1) store_wb_regs(wB, wc, wb1_hi, wb1_lo, with_lo);
-        else store_wb_regs(wB, wc, wb0_hi, wb0_lo, with_lo);
-      }
-#pragma unroll
-      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
-      if (i + 2 < n_my) {
-        const int t2 = tile + 2 * G;
-        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
-      }
-      // ---- E1(i)
+      float dzh[CW], dzl[CW];
       {
-        float z[CW], dzh[CW], dzl[CW];
+        float z[CW];
+        uint32_t zr[CW];
+        tmem_ld8_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, zr);
+        // W'(i+1) for G1(i+1): G1(i) has finished reading the buffer
+        if (i + 1 < n_my) store_wb_regs(wB, wc, wb_hi, wb_lo, with_lo);
         tmem_ld8_wait(zr, z);
         float zmax = 0.f;
 #pragma unroll
@@ -935,33 +1017,51 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
             dzl[j] = d - h;
           }
         }
-#pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          *reinterpret_cast<float*>(dt_hi + dt_off + 16 * j) = dzh[j];
-          if (with_lo) *reinterpret_cast<float*>(dt_lo + dt_off + 16 * j) = dzl[j];
-        }
-        tmem_st8(lane_addr + T2_DZH + cpart * CW, dzh);
-        if (with_lo) tmem_st8(lane_addr + T2_DZL + cpart * CW, dzl);
       }
+      // ---- operand stores: need G2/G3(i-1) to be done with dZ, Dtb and Wtb
+      mbar_wait(&bar_g23, phase);
+      phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        *reinterpret_cast<float*>(dt_hi + dt_off + 16 * j) = dzh[j];
+        if (with_lo) *reinterpret_cast<float*>(dt_lo + dt_off + 16 * j) = dzl[j];
+      }
+      tmem_st8(lane_addr + T2_DZH + cpart * CW, dzh);
+      if (with_lo) tmem_st8(lane_addr + T2_DZL + cpart * CW, dzl);
+      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);              // W'(i) transposed for G2(i)
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();
       named_bar_arrive(1, NT2);
+#pragma unroll
+      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
+      if (i + 2 < n_my) {
+        const int t2 = tile + 2 * G;
+        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
+      }
       // ---- E2(i-1): overlaps the MMAs of iteration i
       if (i > 0) e2_apply(i - 1);
     }
-    mbar_wait(&bar_mma, phase);                       // G2/G3 of the last tile
+    mbar_wait(&bar_g23, phase);                       // G2/G3 of the last tile
     tc_fence_after();
     e2_apply(n_my - 1);
-    // ---- flush dh2 (lane = batch row, columns = hidden unit)
-    for (int c = cpart; c < g.Np / CW; c += NT / 128) {
-      float d[CW];
-      tmem_ld8(lane_addr + T2_DH + c * CW, d);
-      if (brow < B) {
+    // ---- flush dh2 (lane = batch row, columns = hidden unit); the column order is rotated per CTA so that
+    // the 148 CTAs, which finish together, do not all hit the same addresses at the same time
+    {
+      const int nch = g.Np / CW;
+      const int rot = (int)(blockIdx.x % (unsigned)nch);
+      for (int c = cpart; c < nch; c += NT / 128) {
+        int cc = c + rot;
+        if (cc >= nch) cc -= nch;
+        float d[CW];
+        tmem_ld8(lane_addr + T2_DH + cc * CW, d);
+        if (brow < B) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          int kk = c * CW + j;
-          if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
+          for (int j = 0; j < CW; ++j) {
+            int kk = cc * CW + j;
+            if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
+          }
         }
       }
     }
@@ -1173,9 +1273,14 @@ static bool tc_supported(int B, int H, const char* what) {
   return true;
 }
 
-// smem of the pipelined kernel: Hb hi/lo + 2 x Wb hi/lo + Wtb hi/lo + Dtb hi/lo
-static size_t tc2_smem_bytes(const tc::Geom& g) {
-  return 2 * (size_t)g.hb_bytes + 4 * (size_t)g.wb_bytes + 2 * (size_t)g.wt_bytes + 2 * (size_t)g.dt_bytes + 128;
+// smem of the pipelined kernel: Hb hi/lo (round8(B) rows) + Wb hi/lo + Wtb hi/lo + Dtb hi/lo + E2 stage
+static size_t tc2_smem_bytes(const tc::Geom& g, int B) {
+  size_t hb_eff = (size_t)(((B + 7) & ~7) / 8) * g.hb_sbo;
+  size_t n = 2 * hb_eff + 2 * (size_t)g.wb_bytes + 2 * (size_t)g.wt_bytes + 2 * (size_t)g.dt_bytes +
+             3 * (size_t)tc::TN * g.H * 4 + 3 * tc::TN * 4;
+  // the M = 128 operand view of Hb reaches 16 row groups from the start of its lo half
+  size_t reach = hb_eff + 16 * (size_t)g.hb_sbo;
+  return std::max(n, reach);
 }
 // Envelope of the pipelined kernel: TMEM budget, shared-memory budget, bias lanes inside one warp.
 static bool tc2_supported(int B, int H) {
@@ -1183,7 +1288,7 @@ static bool tc2_supported(int B, int H) {
   int BK = (B + 7) & ~7;
   if (B > tc::BM || g.Np + 2 * BK > 320) return false;
   if ((H & 31) + 1 + tc::CW > 32) return false;
-  return tc2_smem_bytes(g) <= 227 * 1024 - 256;
+  return tc2_smem_bytes(g, B) <= 227 * 1024 - 256;
 }
 
 int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
@@ -1198,10 +1303,13 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
   tc::Geom g = tc::make_geom(H);
   int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
   int grid = std::min(n_tiles, sm_count());
-  if (pipelined && tc2_supported(B, H)) {
-    size_t smem = tc2_smem_bytes(g);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(Wd3) | reinterpret_cast<uintptr_t>(mW) |
+                           reinterpret_cast<uintptr_t>(vW) | reinterpret_cast<uintptr_t>(bd3) |
+                           reinterpret_cast<uintptr_t>(mb) | reinterpret_cast<uintptr_t>(vb)) & 15) == 0;   // TMA bulk copies
+  if (pipelined && aligned16 && tc2_supported(B, H)) {
+    size_t smem = tc2_smem_bytes(g, B);
     void (*kern)(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
-                 const int32_t*, float, const aae_step_state*, float*, double*);
+                 const int32_t*, float, const aae_step_state*, float*, double*, int);
     if (H == 100) kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 100> : tc::dec_out_train_tc2_kernel<1, 100>;
     else kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 0> : tc::dec_out_train_tc2_kernel<1, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1210,7 +1318,7 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
       return AAE_E_CUDA;
     }
     kern<<<grid, tc::NT2, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
-                                     (float)(1.0 / n_total), st, dh2, loss_sum);
+                                     (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem);
     return check_launch("dec_out_train(tc2)");
   }
   size_t smem = tc::smem_bytes(g);
