@@ -25,6 +25,9 @@
 #ifndef TC_WAIT_HINT
 #define TC_WAIT_HINT 0x989680u
 #endif
+#ifndef TC_WAIT_SLEEP_NS
+#define TC_WAIT_SLEEP_NS 40
+#endif
 #ifndef TC2_G1_FIRST
 #define TC2_G1_FIRST 1
 #endif
@@ -86,7 +89,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
   while (!done) {
-    if (++spins > (1u << 22)) __trap();   // a lost MMA completion must not hang the device
+    if (spins) __nanosleep(TC_WAIT_SLEEP_NS);   // back off: spinning warps steal issue slots from the MMA issuer
+    if (++spins > (1u << 22)) __trap();          // a lost MMA completion must not hang the device
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -872,14 +876,40 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const uint32_t dt_off = (uint32_t)cpart * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
     const float rvf = (brow < B) ? 1.0f : 0.f;
-    RowCursor2 cur;
-    {
-      int p0 = 0, p1 = 0;
-      if (brow < B) {
-        p0 = indptr[brow];
-        p1 = indptr[brow + 1];
+    // Positives of this thread's row inside THIS CTA's tiles, found once: a row has ~|set|/gridDim items per
+    // CTA, so up to four (tile iteration, 8-bit column mask) events live in registers and the tile loop only
+    // compares its counter with the next event.  More than four: per-tile bisection of the row (rare).
+    constexpr uint32_t EV_NONE = 0xffffffffu;
+    uint32_t ev0 = EV_NONE, ev1 = EV_NONE, ev2 = EV_NONE, ev3 = EV_NONE;   // (iteration << 8) | mask of my 8 columns
+    bool ev_over = false;
+    int row_p0 = 0, row_p1 = 0;
+    if (brow < B) {
+      row_p0 = indptr[brow];
+      row_p1 = indptr[brow + 1];
+      uint32_t last_it = EV_NONE >> 8;
+      for (int p = row_p0; p < row_p1; ++p) {
+        const int v = __ldg(indices + p) - v_begin;
+        if (v < 0 || v >= Vloc) continue;
+        const int t = v / TN;
+        if (t % G != (int)blockIdx.x) continue;
+        const int col = v - t * TN;
+        if ((col >> 3) != cpart) continue;             // another warp's columns
+        const uint32_t it_ = (uint32_t)(t / G), bit = 1u << (col & 7);
+        if (it_ == last_it) {                          // same tile as the previous event: merge
+          if (ev3 != EV_NONE) ev3 |= bit;
+          else if (ev2 != EV_NONE) ev2 |= bit;
+          else if (ev1 != EV_NONE) ev1 |= bit;
+          else ev0 |= bit;
+        } else {
+          const uint32_t e = (it_ << 8) | bit;
+          if (ev0 == EV_NONE) ev0 = e;
+          else if (ev1 == EV_NONE) ev1 = e;
+          else if (ev2 == EV_NONE) ev2 = e;
+          else if (ev3 == EV_NONE) ev3 = e;
+          else ev_over = true;
+          last_it = it_;
+        }
       }
-      cursor_init(cur, indices, p0, p1);
     }
     WChunk wc[WCH];
     make_wchunks(wc, g);
@@ -979,8 +1009,26 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       const int tile = blockIdx.x + i * G;
       const int v0 = tile * TN;
       const int nv = min(TN, Vloc - v0);
-      // positives of this tile for this thread's row (cursor over the row's sorted CSR columns)
-      const uint32_t tb = (tile_targets2(cur, indices, v_begin + v0) >> (cpart * CW)) & 0xffu;
+      // positives of this tile among this thread's 8 columns
+      uint32_t tb = 0u;
+      if ((ev0 >> 8) == (uint32_t)i) {
+        tb = ev0 & 0xffu;
+        ev0 = ev1; ev1 = ev2; ev2 = ev3; ev3 = EV_NONE;
+      }
+      if (ev_over) {                                   // overflowed event list: bisect the row for this tile
+        const int lo_item = v_begin + v0 + cpart * CW;
+        int lo = row_p0, hi = row_p1;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(indices + mid) < lo_item) lo = mid + 1; else hi = mid;
+        }
+        tb = 0u;
+        for (int p = lo; p < row_p1; ++p) {
+          int d = __ldg(indices + p) - lo_item;
+          if (d >= CW) break;
+          tb |= 1u << d;
+        }
+      }
       const int vm = nv - cpart * CW;                 // valid columns of this thread's 8 (>= 8: all)
 
       // ---- E1(i), math part: needs only G1(i)
@@ -1057,10 +1105,13 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         float d[CW];
         tmem_ld8(lane_addr + T2_DH + cc * CW, d);
         if (brow < B) {
+          float* dst = dh2 + (size_t)brow * H + cc * CW;       // H % 4 == 0: 16-byte aligned groups of 4
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            int kk = cc * CW + j;
-            if (kk < H) atomicAdd(dh2 + (size_t)brow * H + kk, d[j]);
+          for (int j = 0; j < CW; j += 4) {
+            if (cc * CW + j + 3 < H)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(d[j]), "f"(d[j + 1]),
+                           "f"(d[j + 2]), "f"(d[j + 3])
+                           : "memory");
           }
         }
       }
