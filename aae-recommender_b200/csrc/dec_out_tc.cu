@@ -28,6 +28,9 @@
 #ifndef TC_WAIT_SLEEP_NS
 #define TC_WAIT_SLEEP_NS 40
 #endif
+#ifndef TC2_CW
+#define TC2_CW 8    // accumulator columns per epilogue thread of the pipelined kernel (8 or 16; measured: 8 -> 163 us, 16 -> 222 us)
+#endif
 #ifndef TC2_G1_FIRST
 #define TC2_G1_FIRST 1
 #endif
@@ -182,6 +185,37 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+// N-column variants used by the pipelined kernel (N = 8 or 16)
+template <int N> struct TmemIO;
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void ld_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  }
+  static __device__ __forceinline__ void ld_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) { tmem_st8(taddr, v); }
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+  static __device__ __forceinline__ void ld_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const float* v) { tmem_st16(taddr, v); }
+};
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // byte offset of element (r, c) in a core-matrix-tiled buffer whose row groups are `s_r` bytes apart
@@ -657,7 +691,6 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // Bias: lane k == H of dW'^T holds the bias gradients; they are handed to lanes H+1..H+8 of the same warp,
 // which run the same Adam code on bd3/mb/vb (one element each) -- no divergent bias path.
 // ---------------------------------------------------------------------------------------------
-constexpr int NT2 = NT + 32;
 constexpr uint32_t T2_Z = 0, T2_DW = 64, T2_DZH = 128, T2_DZL = 160, T2_DH = 192;
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -687,10 +720,43 @@ __device__ __forceinline__ float bce_neg_fast(float z, float inv_n, float& dz) {
   return fmaf(lg2_approx(t), 0.6931471805599453f, fmaxf(z, 0.f));
 }
 
+// this thread's share of the W' tile when NW warps split the Kp/4 (<= 32) 16-byte column groups
+template <int NCH, int NW>
+__device__ __forceinline__ void make_wchunks_t(WChunk* wc, const Geom& g) {
+  const int ncg = g.Kp / 4;
+  const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    int cg = w + NW * j;
+    wc[j].goff = -2;
+    if (cg < ncg) {
+      int c = cg * 4;
+      wc[j].goff = (c + 3 < g.H) ? r * g.H + c : (c == g.H ? -1 : -3);
+    }
+    wc[j].wb_off = (uint32_t)(r >> 3) * g.wb_sbo + (uint32_t)cg * CORE + (uint32_t)(r & 7) * 16u;
+    wc[j].wt_off = (uint32_t)(cg >> 1) * g.wt_sbo + (uint32_t)(r >> 2) * g.wt_lbo + (uint32_t)(cg & 1) * 64u +
+                   (uint32_t)(r & 3) * 4u;
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void load_w_regs_t(float4* wr, const WChunk* wc, const float* __restrict__ Wd3,
+                                              const float* __restrict__ bd3, int H, int v0, int nv) {
+  const int r = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nv) {
+      if (wc[j].goff >= 0) x = __ldcs(reinterpret_cast<const float4*>(Wd3 + (size_t)v0 * H + wc[j].goff));
+      else if (wc[j].goff == -1) x.x = __ldg(bd3 + v0 + r);
+    }
+    wr[j] = x;
+  }
+}
+template <int NCH>
 __device__ __forceinline__ void store_wb_regs(const float4* wr, const WChunk* wc, unsigned char* wb_hi,
                                               unsigned char* wb_lo, bool with_lo) {
 #pragma unroll
-  for (int j = 0; j < WCH; ++j) {
+  for (int j = 0; j < NCH; ++j) {
     if (wc[j].goff == -2) continue;
     float4 x = wr[j];
     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
@@ -698,10 +764,11 @@ __device__ __forceinline__ void store_wb_regs(const float4* wr, const WChunk* wc
     if (with_lo) *reinterpret_cast<float4*>(wb_lo + wc[j].wb_off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
   }
 }
+template <int NCH>
 __device__ __forceinline__ void store_wt_regs(const float4* wr, const WChunk* wc, unsigned char* wt_hi,
                                               unsigned char* wt_lo, bool with_lo) {
 #pragma unroll
-  for (int j = 0; j < WCH; ++j) {
+  for (int j = 0; j < NCH; ++j) {
     if (wc[j].goff == -2) continue;
     float4 x = wr[j];
     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
@@ -728,8 +795,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
-template <int SPLIT, int HC>
-__global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
+// CWT = accumulator columns per epilogue thread (8: 16 epilogue warps, 16: 8 fatter warps with twice the
+// instruction-level parallelism and half the per-warp fixed work)
+template <int CWT> struct Tc2Cfg {
+  static constexpr int NPART = TN / CWT;          // column parts per TMEM lane quarter
+  static constexpr int NWE = 4 * NPART;           // epilogue warps
+  static constexpr int NTT = 32 * NWE + 32;       // + the MMA / TMA warp
+  static constexpr int WCHT = 32 / NWE;           // W' chunks per thread
+};
+template <int SPLIT, int HC, int CWT>
+__global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     const float* __restrict__ h2, int B, int Hrt, float* __restrict__ Wd3, float* __restrict__ bd3,
     float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
     int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
@@ -738,7 +813,8 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
   __shared__ uint64_t bar_g1, bar_g23;   // completion of G1(i) / of G3(i-1)+G2(i-1)
   __shared__ uint64_t bar_stage;         // E2 stage (W/m/v rows of one tile) filled by TMA
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[NT / 32];
+  constexpr int NPART = Tc2Cfg<CWT>::NPART, NWE = Tc2Cfg<CWT>::NWE, NTT = Tc2Cfg<CWT>::NTT, WCHT = Tc2Cfg<CWT>::WCHT;
+  __shared__ float red[NWE];
   const int H = HC ? HC : Hrt;
   const Geom g = make_geom(H);
   constexpr bool with_lo = (SPLIT == 3);
@@ -764,18 +840,18 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
   const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;     // tiles blockIdx.x, +G, ... (grid <= n_tiles)
   const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
 
-  if (warp == NT / 32) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (warp == NWE) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_g1, 1);
     mbar_init(&bar_g23, 1);
     mbar_init(&bar_stage, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int q = tid; q < smem_total / 16; q += NT2) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
+  for (int q = tid; q < smem_total / 16; q += NTT) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
   __syncthreads();
   {
     const int ncg = g.Kp / 4;
-    for (int q = tid; q < BK * ncg; q += NT2) {
+    for (int q = tid; q < BK * ncg; q += NTT) {
       int r = q / ncg, cg = q - r * ncg;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < B) {
@@ -794,7 +870,7 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
   const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
   const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
 
-  if (warp == NT / 32) {
+  if (warp == NWE) {
     // ================= MMA issuer + TMA producer =================
     const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
     const SmemOp op_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
@@ -831,7 +907,7 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     }
     __syncwarp();
     for (int it = 0; it <= n_my; ++it) {
-      named_bar_sync(1, NT2);
+      named_bar_sync(1, NTT);
       tc_fence_after();
       if (elect_one()) {
         // logits of the next tile first: its epilogue math then overlaps the backward GEMMs of this tile
@@ -847,7 +923,7 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       }
       __syncwarp();
       if (it >= 2) {
-        named_bar_sync(2, NT2);          // every epilogue thread has read tile it-2 out of the stage
+        named_bar_sync(2, NTT);          // every epilogue thread has read tile it-2 out of the stage
         if (elect_one()) stage_copy(it - 1);
         __syncwarp();
       }
@@ -859,49 +935,49 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     const int brow = q4 * 32 + lane;                 // E1: batch row of this thread; E2: hidden unit
     const AdamK ak = adam_load(st, 0);
     // H2'^T -> TMEM (lane = hidden unit, column = batch row), BK columns
-    for (int c = cpart; c < BK / CW; c += NT / 128) {
-      float hi[CW], lo[CW];
+    for (int c = cpart; c < BK / 8; c += NPART) {
+      float hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        int b = c * CW + j;
+      for (int j = 0; j < 8; ++j) {
+        int b = c * 8 + j;
         float x = 0.f;
         if (b < B) x = (brow < H) ? h2[(size_t)b * H + brow] : (brow == H ? 1.0f : 0.f);
         hi[j] = tf32_hi(x);
         lo[j] = x - hi[j];
       }
-      tmem_st8(lane_addr + T2_HTH + c * CW, hi);
-      if (with_lo) tmem_st8(lane_addr + T2_HTL + c * CW, lo);
+      tmem_st8(lane_addr + T2_HTH + c * 8, hi);
+      if (with_lo) tmem_st8(lane_addr + T2_HTL + c * 8, lo);
     }
     tmem_st_wait();
-    const uint32_t dt_off = (uint32_t)cpart * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
+    const uint32_t dt_off = (uint32_t)(cpart * (CWT / 8)) * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
     const float rvf = (brow < B) ? 1.0f : 0.f;
     // Positives of this thread's row inside THIS CTA's tiles, found once: a row has ~|set|/gridDim items per
     // CTA, so up to four (tile iteration, 8-bit column mask) events live in registers and the tile loop only
     // compares its counter with the next event.  More than four: per-tile bisection of the row (rare).
     constexpr uint32_t EV_NONE = 0xffffffffu;
-    uint32_t ev0 = EV_NONE, ev1 = EV_NONE, ev2 = EV_NONE, ev3 = EV_NONE;   // (iteration << 8) | mask of my 8 columns
+    uint32_t ev0 = EV_NONE, ev1 = EV_NONE, ev2 = EV_NONE, ev3 = EV_NONE;   // (iteration << 16) | mask of my CWT columns
     bool ev_over = false;
     int row_p0 = 0, row_p1 = 0;
     if (brow < B) {
       row_p0 = indptr[brow];
       row_p1 = indptr[brow + 1];
-      uint32_t last_it = EV_NONE >> 8;
+      uint32_t last_it = EV_NONE >> 16;
       for (int p = row_p0; p < row_p1; ++p) {
         const int v = __ldg(indices + p) - v_begin;
         if (v < 0 || v >= Vloc) continue;
         const int t = v / TN;
         if (t % G != (int)blockIdx.x) continue;
         const int col = v - t * TN;
-        if ((col >> 3) != cpart) continue;             // another warp's columns
-        const uint32_t it_ = (uint32_t)(t / G), bit = 1u << (col & 7);
+        if (col / CWT != cpart) continue;             // another warp's columns
+        const uint32_t it_ = (uint32_t)(t / G), bit = 1u << (col % CWT);
         if (it_ == last_it) {                          // same tile as the previous event: merge
           if (ev3 != EV_NONE) ev3 |= bit;
           else if (ev2 != EV_NONE) ev2 |= bit;
           else if (ev1 != EV_NONE) ev1 |= bit;
           else ev0 |= bit;
         } else {
-          const uint32_t e = (it_ << 8) | bit;
+          const uint32_t e = (it_ << 16) | bit;
           if (ev0 == EV_NONE) ev0 = e;
           else if (ev1 == EV_NONE) ev1 = e;
           else if (ev2 == EV_NONE) ev2 = e;
@@ -911,32 +987,32 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         }
       }
     }
-    WChunk wc[WCH];
-    make_wchunks(wc, g);
-    float4 wA[WCH], wB[WCH];
+    WChunk wc[WCHT];
+    make_wchunks_t<WCHT, NWE>(wc, g);
+    float4 wA[WCHT], wB[WCHT];
     {
       const int t0 = blockIdx.x;
-      load_w_regs(wA, wc, Wd3, bd3, H, t0 * TN, min(TN, Vloc - t0 * TN));
-      store_wb_regs(wA, wc, wb_hi, wb_lo, with_lo);
-      if (n_my > 1) load_w_regs(wB, wc, Wd3, bd3, H, (t0 + G) * TN, min(TN, Vloc - (t0 + G) * TN));
+      load_w_regs_t<WCHT>(wA, wc, Wd3, bd3, H, t0 * TN, min(TN, Vloc - t0 * TN));
+      store_wb_regs<WCHT>(wA, wc, wb_hi, wb_lo, with_lo);
+      if (n_my > 1) load_w_regs_t<WCHT>(wB, wc, Wd3, bd3, H, (t0 + G) * TN, min(TN, Vloc - (t0 + G) * TN));
     }
     fence_async_smem();
     tc_fence_before();
-    named_bar_arrive(1, NT2);
+    named_bar_arrive(1, NTT);
 
     // E2 addressing: normal lanes (k < H) walk 8 item rows at pitch H; lanes H+1..H+8 own one bias element
     // each; all use the same immediate offsets j*H (bias lanes only ever touch j = 0).
     const int kb = H & 31;                           // lane of hidden unit H inside its warp
     const bool bias_warp = (q4 == (H >> 5));
     const int jb = brow - (H + 1);                   // bias lanes: 0..7
-    const bool is_bias = (jb >= 0 && jb < CW);
+    const bool is_bias = (jb >= 0 && jb < CWT);
     float* const eW = is_bias ? bd3 : Wd3;
     float* const eM = is_bias ? mb : mW;
     float* const eV = is_bias ? vb : vW;
-    const float* const sWp = is_bias ? sB + cpart * CW + jb : sW + cpart * CW * H + brow;
-    const float* const sMp = is_bias ? sB + TN + cpart * CW + jb : sM + cpart * CW * H + brow;
-    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CW + jb : sV + cpart * CW * H + brow;
-    const int ecnt_full = is_bias ? 1 : (brow < H ? CW : 0);
+    const float* const sWp = is_bias ? sB + cpart * CWT + jb : sW + cpart * CWT * H + brow;
+    const float* const sMp = is_bias ? sB + TN + cpart * CWT + jb : sM + cpart * CWT * H + brow;
+    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CWT + jb : sV + cpart * CWT * H + brow;
+    const int ecnt_full = is_bias ? 1 : (brow < H ? CWT : 0);
     uint32_t phase = 0, phase_e = 0;
     float loss_local = 0.f;
 
@@ -945,26 +1021,26 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       const int tile = blockIdx.x + j_done * G;
       const int v0 = tile * TN;
       const int nv = min(TN, Vloc - v0);
-      uint32_t gr[CW];
-      tmem_ld8_issue(lane_addr + T2_DW + (uint32_t)(j_done & 1) * 32u + cpart * CW, gr);
+      uint32_t gr[CWT];
+      TmemIO<CWT>::ld_issue(lane_addr + T2_DW + (uint32_t)(j_done & 1) * 32u + cpart * CWT, gr);
       size_t eoff;
       int ecnt;
       if (is_bias) {
-        eoff = (size_t)v0 + cpart * CW + jb;
-        ecnt = (cpart * CW + jb < nv) ? 1 : 0;
+        eoff = (size_t)v0 + cpart * CWT + jb;
+        ecnt = (cpart * CWT + jb < nv) ? 1 : 0;
       } else {
-        eoff = (size_t)(v0 + cpart * CW) * H + brow;
-        ecnt = (brow < H) ? max(0, min(CW, nv - cpart * CW)) : 0;
+        eoff = (size_t)(v0 + cpart * CWT) * H + brow;
+        ecnt = (brow < H) ? max(0, min(CWT, nv - cpart * CWT)) : 0;
       }
       float* pW = eW + eoff;
       float* pM = eM + eoff;
       float* pV = eV + eoff;
-      float pw[CW], pm[CW], pv[CW];
+      float pw[CWT], pm[CWT], pv[CWT];
       mbar_wait(&bar_stage, phase_e);
       phase_e ^= 1;
       if (nv == TN) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
+        for (int j = 0; j < CWT; ++j) {
           if (j < ecnt_full) {
             pw[j] = sWp[j * H];
             pm[j] = sMp[j * H];
@@ -973,7 +1049,7 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
+        for (int j = 0; j < CWT; ++j) {
           if (j < ecnt) {
             pw[j] = pW[(size_t)j * H];
             pm[j] = pM[(size_t)j * H];
@@ -981,20 +1057,22 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
           }
         }
       }
-      if (j_done + 1 < n_my) named_bar_arrive(2, NT2);   // the stage may be refilled (tile j_done + 1)
-      float gw[CW];
-      tmem_ld8_wait(gr, gw);
+      if (j_done + 1 < n_my) named_bar_arrive(2, NTT);   // the stage may be refilled (tile j_done + 1)
+      float gw[CWT];
+      TmemIO<CWT>::ld_wait(gr);
+#pragma unroll
+      for (int j = 0; j < CWT; ++j) gw[j] = __uint_as_float(gr[j]);
       if (bias_warp) {
         float gb = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
+        for (int j = 0; j < CWT; ++j) {
           float t = __shfl_sync(0xffffffffu, gw[j], kb);
           if (jb == j) gb = t;
         }
         if (is_bias) gw[0] = gb;
       }
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
+      for (int j = 0; j < CWT; ++j) {
         if (j < ecnt) {
           float p = pw[j], m = pm[j], vv = pv[j];
           adam_update(ak, gw[j], p, m, vv);
@@ -1011,12 +1089,12 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       const int nv = min(TN, Vloc - v0);
       // positives of this tile among this thread's 8 columns
       uint32_t tb = 0u;
-      if ((ev0 >> 8) == (uint32_t)i) {
-        tb = ev0 & 0xffu;
+      if ((ev0 >> 16) == (uint32_t)i) {
+        tb = ev0 & 0xffffu;
         ev0 = ev1; ev1 = ev2; ev2 = ev3; ev3 = EV_NONE;
       }
       if (ev_over) {                                   // overflowed event list: bisect the row for this tile
-        const int lo_item = v_begin + v0 + cpart * CW;
+        const int lo_item = v_begin + v0 + cpart * CWT;
         int lo = row_p0, hi = row_p1;
         while (lo < hi) {
           int mid = (lo + hi) >> 1;
@@ -1025,29 +1103,31 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
         tb = 0u;
         for (int p = lo; p < row_p1; ++p) {
           int d = __ldg(indices + p) - lo_item;
-          if (d >= CW) break;
+          if (d >= CWT) break;
           tb |= 1u << d;
         }
       }
-      const int vm = nv - cpart * CW;                 // valid columns of this thread's 8 (>= 8: all)
+      const int vm = nv - cpart * CWT;                 // valid columns of this thread's 8 (>= 8: all)
 
       // ---- E1(i), math part: needs only G1(i)
       mbar_wait(&bar_g1, phase);
       tc_fence_after();
-      float dzh[CW], dzl[CW];
+      float dzh[CWT], dzl[CWT];
       {
-        float z[CW];
-        uint32_t zr[CW];
-        tmem_ld8_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CW, zr);
+        float z[CWT];
+        uint32_t zr[CWT];
+        TmemIO<CWT>::ld_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CWT, zr);
         // W'(i+1) for G1(i+1): G1(i) has finished reading the buffer
-        if (i + 1 < n_my) store_wb_regs(wB, wc, wb_hi, wb_lo, with_lo);
-        tmem_ld8_wait(zr, z);
+        if (i + 1 < n_my) store_wb_regs<WCHT>(wB, wc, wb_hi, wb_lo, with_lo);
+        TmemIO<CWT>::ld_wait(zr);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) z[j] = __uint_as_float(zr[j]);
         float zmax = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) zmax = fmaxf(zmax, fabsf(z[j]));
-        if (tb == 0u && vm >= CW && zmax < 16.0f) {
+        for (int j = 0; j < CWT; ++j) zmax = fmaxf(zmax, fabsf(z[j]));
+        if (tb == 0u && vm >= CWT && zmax < 16.0f) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
+          for (int j = 0; j < CWT; ++j) {
             float d;
             float l = bce_neg_fast(z[j], inv_n_row, d);
             loss_local = fmaf(l, rvf, loss_local);
@@ -1057,7 +1137,7 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
+          for (int j = 0; j < CWT; ++j) {
             float d = 0.f;
             if (brow < B && j < vm) loss_local += bce_term(z[j], (tb >> j) & 1u, inv_n, d);
             float h = tf32_hi(d);
@@ -1071,22 +1151,23 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
       phase ^= 1;
       tc_fence_after();
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        *reinterpret_cast<float*>(dt_hi + dt_off + 16 * j) = dzh[j];
-        if (with_lo) *reinterpret_cast<float*>(dt_lo + dt_off + 16 * j) = dzl[j];
+      for (int j = 0; j < CWT; ++j) {
+        const uint32_t o = dt_off + (uint32_t)(j >> 3) * g.dt_sbo + (uint32_t)(j & 7) * 16u;
+        *reinterpret_cast<float*>(dt_hi + o) = dzh[j];
+        if (with_lo) *reinterpret_cast<float*>(dt_lo + o) = dzl[j];
       }
-      tmem_st8(lane_addr + T2_DZH + cpart * CW, dzh);
-      if (with_lo) tmem_st8(lane_addr + T2_DZL + cpart * CW, dzl);
-      store_wt_regs(wA, wc, wt_hi, wt_lo, with_lo);              // W'(i) transposed for G2(i)
+      TmemIO<CWT>::st(lane_addr + T2_DZH + cpart * CWT, dzh);
+      if (with_lo) TmemIO<CWT>::st(lane_addr + T2_DZL + cpart * CWT, dzl);
+      store_wt_regs<WCHT>(wA, wc, wt_hi, wt_lo, with_lo);              // W'(i) transposed for G2(i)
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();
-      named_bar_arrive(1, NT2);
+      named_bar_arrive(1, NTT);
 #pragma unroll
-      for (int j = 0; j < WCH; ++j) wA[j] = wB[j];
+      for (int j = 0; j < WCHT; ++j) wA[j] = wB[j];
       if (i + 2 < n_my) {
         const int t2 = tile + 2 * G;
-        load_w_regs(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
+        load_w_regs_t<WCHT>(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
       }
       // ---- E2(i-1): overlaps the MMAs of iteration i
       if (i > 0) e2_apply(i - 1);
@@ -1097,18 +1178,24 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
     // ---- flush dh2 (lane = batch row, columns = hidden unit); the column order is rotated per CTA so that
     // the 148 CTAs, which finish together, do not all hit the same addresses at the same time
     {
-      const int nch = g.Np / CW;
+      const int nch = g.Np / CWT;
       const int rot = (int)(blockIdx.x % (unsigned)nch);
-      for (int c = cpart; c < nch; c += NT / 128) {
+      for (int c = cpart; c < nch; c += NPART) {
         int cc = c + rot;
         if (cc >= nch) cc -= nch;
-        float d[CW];
-        tmem_ld8(lane_addr + T2_DH + cc * CW, d);
-        if (brow < B) {
-          float* dst = dh2 + (size_t)brow * H + cc * CW;       // H % 4 == 0: 16-byte aligned groups of 4
+        float d[CWT];
+        {
+          uint32_t dr[CWT];
+          TmemIO<CWT>::ld_issue(lane_addr + T2_DH + cc * CWT, dr);
+          TmemIO<CWT>::ld_wait(dr);
 #pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            if (cc * CW + j + 3 < H)
+          for (int j = 0; j < CWT; ++j) d[j] = __uint_as_float(dr[j]);
+        }
+        if (brow < B) {
+          float* dst = dh2 + (size_t)brow * H + cc * CWT;       // H % 4 == 0: 16-byte aligned groups of 4
+#pragma unroll
+          for (int j = 0; j < CWT; j += 4) {
+            if (cc * CWT + j + 3 < H)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(d[j]), "f"(d[j + 1]),
                            "f"(d[j + 2]), "f"(d[j + 3])
                            : "memory");
@@ -1123,10 +1210,10 @@ __global__ void __launch_bounds__(NT2, 1) dec_out_train_tc2_kernel(
   __syncthreads();
   if (tid == 0) {
     double tot = 0.0;
-    for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+    for (int w = 0; w < NWE; ++w) tot += (double)red[w];
     atomicAdd(loss_sum, tot);
   }
-  if (warp == NT / 32) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == NWE) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1338,7 +1425,7 @@ static bool tc2_supported(int B, int H) {
   tc::Geom g = tc::make_geom(H);
   int BK = (B + 7) & ~7;
   if (B > tc::BM || g.Np + 2 * BK > 320) return false;
-  if ((H & 31) + 1 + tc::CW > 32) return false;
+  if ((H & 31) + 1 + TC2_CW > 32) return false;   // bias lanes H+1..H+CW live in the warp of lane H
   return tc2_smem_bytes(g, B) <= 227 * 1024 - 256;
 }
 
@@ -1361,14 +1448,16 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
     size_t smem = tc2_smem_bytes(g, B);
     void (*kern)(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
                  const int32_t*, float, const aae_step_state*, float*, double*, int);
-    if (H == 100) kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 100> : tc::dec_out_train_tc2_kernel<1, 100>;
-    else kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 0> : tc::dec_out_train_tc2_kernel<1, 0>;
+    if (H == 100)
+      kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 100, TC2_CW> : tc::dec_out_train_tc2_kernel<1, 100, TC2_CW>;
+    else
+      kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 0, TC2_CW> : tc::dec_out_train_tc2_kernel<1, 0, TC2_CW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
       return AAE_E_CUDA;
     }
-    kern<<<grid, tc::NT2, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+    kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
                                      (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem);
     return check_launch("dec_out_train(tc2)");
   }

@@ -30,6 +30,7 @@ __device__ __forceinline__ void cp_async_wait() {
 struct LayerW {
   const float* W;
   int O, I;
+  int rpc;   // rows per staged chunk (filled by make_layer)
 };
 // Rows [r0, r1) of layer `layer`, resident in shared memory at w (row pitch I).
 struct Chunk {
@@ -54,6 +55,11 @@ struct Stager {
     if (r >= a) r -= r % a;
     return max(r, 1);
   }
+  __device__ static LayerW make_layer(const float* W, int O, int I) {
+    LayerW l;
+    l.W = W; l.O = O; l.I = I; l.rpc = rows_per_chunk(I);
+    return l;
+  }
   __device__ void init(float* b0, float* b1, const LayerW* layers, int nlayers) {
     buf0 = b0; buf1 = b1; L = layers; n = nlayers;
     pl = pr = pbuf = cl = cr = cbuf = inflight = 0;
@@ -62,7 +68,7 @@ struct Stager {
   __device__ void issue() {
     if (pl >= n) return;
     const LayerW l = L[pl];
-    const int rc = min(rows_per_chunk(l.I), l.O - pr);
+    const int rc = min(l.rpc, l.O - pr);
     const float* src = l.W + (size_t)pr * l.I;
     float* dst = pbuf ? buf1 : buf0;
     const int nf = rc * l.I;
@@ -84,7 +90,7 @@ struct Stager {
   __device__ Chunk acquire() {
     Chunk c;
     const LayerW l = L[cl];
-    const int rc = min(rows_per_chunk(l.I), l.O - cr);
+    const int rc = min(l.rpc, l.O - cr);
     c.layer = cl; c.r0 = cr; c.r1 = cr + rc;
     c.w = cbuf ? buf1 : buf0;
     issue();
@@ -113,6 +119,11 @@ __device__ __forceinline__ void linear_fwd_chunk(const Chunk& c, int I, const fl
     for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[q][r] = 0.f;
+    // bias of the output this lane will write (lanes 0, 8, 16, 24 <-> outputs 0..3), requested before the dot
+    // products so that its L2 latency is hidden
+    const int qw = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const bool writer = (lane & 7) == 0 && qw < no;
+    const float bias = writer ? __ldg(b + c.r0 + o0 + qw) : 0.f;
     for (int i = lane; i < I; i += 32) {
       const float w0 = w[i];
       const float w1 = (no > 1) ? w[I + i] : 0.f;
@@ -127,13 +138,21 @@ __device__ __forceinline__ void linear_fwd_chunk(const Chunk& c, int I, const fl
         acc[3][r] = fmaf(w3, x, acc[3][r]);
       }
     }
+    // transposing butterfly: 6 shuffles reduce the four sums at once (instead of 4 x 5)
+    const bool hi16 = lane & 16, hi8 = lane & 8;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float s = warp_sum(acc[q][r]);
-        if (lane == 0 && q < no) ys[r * ldy + c.r0 + o0 + q] = s + b[c.r0 + o0 + q];
-      }
+    for (int r = 0; r < R; ++r) {
+      float k0 = hi16 ? acc[2][r] : acc[0][r], k1 = hi16 ? acc[3][r] : acc[1][r];
+      float t0 = hi16 ? acc[0][r] : acc[2][r], t1 = hi16 ? acc[1][r] : acc[3][r];
+      k0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+      k1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+      float u = hi8 ? k1 : k0, v = hi8 ? k0 : k1;
+      u += __shfl_xor_sync(0xffffffffu, v, 8);
+      u += __shfl_xor_sync(0xffffffffu, u, 4);
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
+      if (writer) ys[r * ldy + c.r0 + o0 + qw] = u + bias;
+    }
   }
 }
 // y = x . W^T + b for layer `layer` of the stager's sequence (all its chunks).  Ends with a barrier.
@@ -276,10 +295,10 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const f
   DecBlock D(dec, H, Cp);
   aae_drop none = {nullptr, 0.f, 0};
   if (threadIdx.x == 0) {
-    layers[0] = {E.We2, H, H};
-    layers[1] = {E.We3, C, H};
-    layers[2] = {D.Wd1, H, Cp};
-    layers[3] = {D.Wd2, H, H};
+    layers[0] = Stager::make_layer(E.We2, H, H);
+    layers[1] = Stager::make_layer(E.We3, C, H);
+    layers[2] = Stager::make_layer(D.Wd1, H, Cp);
+    layers[3] = Stager::make_layer(D.Wd2, H, H);
   }
   __syncthreads();
   Stager sg;
@@ -327,10 +346,10 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const f
   EncBlock E(enc, H, C);
   DecBlock D(dec, H, Cp);
   if (threadIdx.x == 0) {
-    layers[0] = {D.Wd2, H, H};
-    layers[1] = {D.Wd1, H, Cp};
-    layers[2] = {E.We3, C, H};
-    layers[3] = {E.We2, H, H};
+    layers[0] = Stager::make_layer(D.Wd2, H, H);
+    layers[1] = Stager::make_layer(D.Wd1, H, Cp);
+    layers[2] = Stager::make_layer(E.We3, C, H);
+    layers[3] = Stager::make_layer(E.We2, H, H);
   }
   __syncthreads();
   Stager sg;
@@ -414,9 +433,9 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
   aae_drop none = {nullptr, 0.f, 0};
   const int AW = 2 * (C + 2 * H), GW = 2 * (2 * H + 1);
   if (threadIdx.x == 0) {
-    layers[0] = {Q.Wq1, H, C}; layers[1] = {Q.Wq2, H, H}; layers[2] = {Q.wq3, 1, H}; layers[3] = {Q.Wq2, H, H};
-    layers[4] = {E.We2, H, H}; layers[5] = {E.We3, C, H};
-    layers[6] = {Q.Wq1, H, C}; layers[7] = {Q.Wq2, H, H}; layers[8] = {Q.wq3, 1, H}; layers[9] = {Q.Wq2, H, H};
+    layers[0] = Stager::make_layer(Q.Wq1, H, C); layers[1] = Stager::make_layer(Q.Wq2, H, H); layers[2] = Stager::make_layer(Q.wq3, 1, H); layers[3] = Stager::make_layer(Q.Wq2, H, H);
+    layers[4] = Stager::make_layer(E.We2, H, H); layers[5] = Stager::make_layer(E.We3, C, H);
+    layers[6] = Stager::make_layer(Q.Wq1, H, C); layers[7] = Stager::make_layer(Q.Wq2, H, H); layers[8] = Stager::make_layer(Q.wq3, 1, H); layers[9] = Stager::make_layer(Q.Wq2, H, H);
   }
   __syncthreads();
   Stager sg;
@@ -512,9 +531,9 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
   EncBlock E(enc, H, C);
   DiscBlock Q(disc, H, C);
   if (threadIdx.x == 0) {
-    layers[0] = {E.We2, H, H}; layers[1] = {E.We3, C, H};
-    layers[2] = {Q.Wq1, H, C}; layers[3] = {Q.Wq2, H, H}; layers[4] = {Q.wq3, 1, H};
-    layers[5] = {Q.Wq2, H, H}; layers[6] = {Q.Wq1, H, C}; layers[7] = {E.We3, C, H}; layers[8] = {E.We2, H, H};
+    layers[0] = Stager::make_layer(E.We2, H, H); layers[1] = Stager::make_layer(E.We3, C, H);
+    layers[2] = Stager::make_layer(Q.Wq1, H, C); layers[3] = Stager::make_layer(Q.Wq2, H, H); layers[4] = Stager::make_layer(Q.wq3, 1, H);
+    layers[5] = Stager::make_layer(Q.Wq2, H, H); layers[6] = Stager::make_layer(Q.Wq1, H, C); layers[7] = Stager::make_layer(E.We3, C, H); layers[8] = Stager::make_layer(E.We2, H, H);
   }
   __syncthreads();
   Stager sg;
