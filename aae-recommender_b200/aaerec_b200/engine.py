@@ -15,6 +15,8 @@ computed redundantly (identical inputs and RNG on every rank), so the only excha
 all-reduce of h1pre partial sums and of (dh2, loss) -- SURVEY.md 8(e).
 """
 import ctypes as C
+import gc
+import os
 
 import numpy as np
 import torch
@@ -44,6 +46,33 @@ def disc_block_sizes(H, C_):
             ("disc.lin2.bias", H), ("disc.lin3.weight", H), ("disc.lin3.bias", 1)]
 
 
+class _Branch(object):
+    """Fork of the current stream onto ``engine.side2`` (see AAEEngine._branch)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        self.ctx = None
+
+    def __enter__(self):
+        eng = self.eng
+        if not eng.branches:
+            return self
+        cur = torch.cuda.current_stream(eng.dev)
+        eng._ev_fork2.record(cur)
+        eng.side2.wait_event(eng._ev_fork2)
+        self.ctx = torch.cuda.stream(eng.side2)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is None:
+            return False
+        self.eng._ev_join2.record(self.eng.side2)
+        self.ctx.__exit__(*a)
+        self.ctx = None
+        return False
+
+
 class AAEEngine(object):
     def __init__(self, n_items, n_hidden=100, n_code=50, cond_dim=0, gen_lr=1e-3, reg_lr=1e-3,
                  dropout=(.2, .2), prior_scale=None, normalize_inputs=True, device=None,
@@ -63,6 +92,7 @@ class AAEEngine(object):
         self.seed = int(seed)
         self.use_graph = bool(use_graph) and self.world == 1
         self.overlap_sweep = bool(overlap_sweep)
+        self.branches = os.environ.get("AAE_B200_NO_BRANCH", "") == ""   # parallel graph branches (debug switch)
         self.impl = self._pick_impl(impl)
         self.steps_done = 0
         self._launches_per_step = 0
@@ -85,13 +115,29 @@ class AAEEngine(object):
         self._ws_B = 0
         self._ws_nnz = 0
         self._graphs = {}
-        self.side = torch.cuda.Stream(device=self.dev)
+        # torch hands out streams from a small round-robin pool: make sure the three we use together (capture
+        # stream + two side streams) are different CUDA streams, or a fork would alias the capturing stream
+        self._cap_stream, self.side, self.side2 = self._distinct_streams(3)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
+        self._ev_fork2 = torch.cuda.Event()
+        self._ev_join2 = torch.cuda.Event()
         call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
         self._ensure_ws(max_batch, max_nnz or max_batch * 64)
 
     # ------------------------------------------------------------------ plumbing
+    def _distinct_streams(self, n):
+        seen = {torch.cuda.current_stream(self.dev).cuda_stream, torch.cuda.default_stream(self.dev).cuda_stream}
+        out = []
+        for _ in range(256):
+            st = torch.cuda.Stream(device=self.dev)
+            if st.cuda_stream not in seen:
+                seen.add(st.cuda_stream)
+                out.append(st)
+                if len(out) == n:
+                    return out
+        raise RuntimeError("could not obtain %d distinct CUDA streams" % n)
+
     def _pick_impl(self, impl):
         names = {"simt": 0, "fp32": 0, "tc": 1, "tc3": 1, "parity": 1, "tf32": 2, "fast": 2}
         if impl == "auto":
@@ -267,6 +313,15 @@ class AAEEngine(object):
                 out[name] = N.drop(None, p, i + 1)
         return out
 
+    def _branch(self):
+        """Context manager: work enqueued inside runs on a second side stream that forks from the current
+        stream here and is joined by the next ``_join()`` (a parallel branch of the captured graph)."""
+        return _Branch(self)
+
+    def _join(self):
+        if self.branches:
+            torch.cuda.current_stream(self.dev).wait_event(self._ev_join2)
+
     def _allreduce(self, t):
         if self.world > 1:
             import torch.distributed as dist
@@ -319,14 +374,18 @@ class AAEEngine(object):
         call("aae_ae_bwd", dims, ptr(self.dh2), ptr(self.enc), ptr(self.dec), dr["ae_e1"], dr["ae_e2"], dr["ae_d1"],
              dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.dd1), ptr(self.h2), ptr(self.g_d2), ptr(self.g_d1),
              ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), s())
-        call("aae_ae_wgrad", dims, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1), ptr(self.g_d2),
-             ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), None, None,
-             N.adam_block(self.enc, self.enc_m1, self.enc_v1, 0), N.adam_block(self.dec, self.dec_m, self.dec_v, 0),
-             st, s())       # enc_optim.step() / dec_optim.step() fused into the reduction
+        # the small-layer weight gradients (+ enc_optim / dec_optim, fused into the reduction) and the sparse
+        # first-layer gradient are independent: two branches of the step's graph
+        with self._branch():
+            call("aae_ae_wgrad", dims, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1), ptr(self.g_d2),
+                 ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), None, None,
+                 N.adam_block(self.enc, self.enc_m1, self.enc_v1, 0),
+                 N.adam_block(self.dec, self.dec_m, self.dec_v, 0), st, s())
         call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.g_h1), H, self.normalize,
              ptr(self.slot_of), lo, hi, ptr(self.G1), s())
         call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G1), ptr(self.W1t), ptr(self.W1_m1),
              ptr(self.W1_v1), H, st, 0, s())
+        self._join()
         # ---- disc_step (aae.py:713-732) and gen_step (734-743) share X.W1^T + b1 (same weights, same input)
         call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
              lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
@@ -339,12 +398,14 @@ class AAEEngine(object):
         call("aae_gen_phase", dims, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"], dr["gen_e2"],
              dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
              ptr(self.gg_h1), ptr(self.loss_sums[2:]), s())
-        call("aae_gen_wgrad", dims, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2), ptr(self.gg_h1),
-             None, N.adam_block(self.enc, self.enc_m2, self.enc_v2, 1), st, s())
+        with self._branch():
+            call("aae_gen_wgrad", dims, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
+                 ptr(self.gg_h1), None, N.adam_block(self.enc, self.enc_m2, self.enc_v2, 1), st, s())
         call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.gg_h1), H, self.normalize,
              ptr(self.slot_of), lo, hi, ptr(self.G2), s())
         call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G2), ptr(self.W1t), ptr(self.W1_m2),
              ptr(self.W1_v2), H, st, 1, s())
+        self._join()
         if self.overlap_sweep:
             cur.wait_event(self._ev_join)
         else:
@@ -370,8 +431,16 @@ class AAEEngine(object):
                 torch.cuda.synchronize(self.dev)
                 self._restore(snap)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.dev)):
-                    self._enqueue_step(B, injected)
+                # no cyclic garbage collection while capturing: collecting an old engine's CUDA graph in the
+                # middle of a capture invalidates it (torch collects once on entering the capture)
+                gc_was_on = gc.isenabled()
+                gc.disable()
+                try:
+                    with torch.cuda.graph(g, stream=self._cap_stream):
+                        self._enqueue_step(B, injected)
+                finally:
+                    if gc_was_on:
+                        gc.enable()
                 self._restore(snap)
                 self._graphs[key] = g
             g.replay()

@@ -432,16 +432,25 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
   DiscBlock Q(disc, H, C);
   aae_drop none = {nullptr, 0.f, 0};
   const int AW = 2 * (C + 2 * H), GW = 2 * (2 * H + 1);
+  // the two sides (real prior sample / encoder output) are independent until the weight gradients: they run in
+  // different CTAs (blockIdx.y), which halves the dependent chain of the phase
+  const int side = blockIdx.y;
   if (threadIdx.x == 0) {
-    layers[0] = Stager::make_layer(Q.Wq1, H, C); layers[1] = Stager::make_layer(Q.Wq2, H, H); layers[2] = Stager::make_layer(Q.wq3, 1, H); layers[3] = Stager::make_layer(Q.Wq2, H, H);
-    layers[4] = Stager::make_layer(E.We2, H, H); layers[5] = Stager::make_layer(E.We3, C, H);
-    layers[6] = Stager::make_layer(Q.Wq1, H, C); layers[7] = Stager::make_layer(Q.Wq2, H, H); layers[8] = Stager::make_layer(Q.wq3, 1, H); layers[9] = Stager::make_layer(Q.Wq2, H, H);
+    int n = 0;
+    if (side) {
+      layers[n++] = Stager::make_layer(E.We2, H, H);
+      layers[n++] = Stager::make_layer(E.We3, C, H);
+    }
+    layers[n++] = Stager::make_layer(Q.Wq1, H, C);
+    layers[n++] = Stager::make_layer(Q.Wq2, H, H);
+    layers[n++] = Stager::make_layer(Q.wq3, 1, H);
+    layers[n++] = Stager::make_layer(Q.Wq2, H, H);
   }
   __syncthreads();
   Stager sg;
-  sg.init(sm, sm + STAGE_FLOATS, layers, 10);
+  sg.init(sm, sm + STAGE_FLOATS, layers, side ? 6 : 4);
   float lsum = 0.f;
-  for (int side = 0; side < 2; ++side) {
+  {
     if (side == 0) {
       // z_real ~ N(0,1) * prior_scale (aae.py:716-718)
       for (int q = threadIdx.x; q < R * C; q += blockDim.x) {
@@ -455,11 +464,11 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
       // z_fake = enc(batch) in eval mode (aae.py:714, 722)
       load_rows<R>(x, ld, h1pre, H, row0, B);
       drop_relu<R>(x, ld, H, row0, B, none, st, nullptr);
-      layer_fwd<R>(sg, 4, x, ld, E.be2, y, ld);
+      layer_fwd<R>(sg, 0, x, ld, E.be2, y, ld);
       drop_relu<R>(y, ld, H, row0, B, none, st, nullptr);
-      layer_fwd<R>(sg, 5, y, ld, E.be3, zz, ld);
+      layer_fwd<R>(sg, 1, y, ld, E.be3, zz, ld);
     }
-    const int lb = side ? 6 : 0;
+    const int lb = side ? 2 : 0;
     disc_fwd<R>(sg, lb, zz, ld, Q, H, row0, B, side ? f1 : r1, side ? f2 : r2, st, q1, q2, outs);
     if (threadIdx.x < R && row0 + threadIdx.x < B) {
       float o = outs[threadIdx.x];
@@ -498,7 +507,6 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
       }
       if (threadIdx.x == 0) gr[2 * H] = go[r];
     }
-    __syncthreads();
   }
   if (threadIdx.x < R && lsum != 0.f) atomicAdd(loss_sum, (double)lsum);
 }
@@ -708,8 +716,19 @@ int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float pr
                    float* acts, float* grads, double* loss_sum, void* stream) {
   AAE_REQUIRE(h1pre && enc && disc && st && acts && grads && loss_sum, "null pointer");
   int ld = std::max(d.H, d.C);
-  LAUNCH_R(disc_phase_kernel, d.B, 5 * ld + 2, stream, d, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st,
-           acts, grads, loss_sum);
+  {
+    int R_ = rows_per_cta(d.B);
+    size_t smem_ = sizeof(float) * ((size_t)(5 * ld + 2) * R_ + 2 * STAGE_FLOATS) + 64;
+    if (R_ == 1) {
+      cudaFuncSetAttribute(disc_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+      disc_phase_kernel<1><<<dim3(cdiv(d.B, 1), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
+          d, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+    } else {
+      cudaFuncSetAttribute(disc_phase_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+      disc_phase_kernel<4><<<dim3(cdiv(d.B, 4), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
+          d, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+    }
+  }
   return check_launch("disc_phase");
 }
 
