@@ -25,6 +25,11 @@ class AaeDrop(C.Structure):
     _fields_ = [("mask", P), ("p", F), ("stream_id", C.c_uint32)]
 
 
+class AaeBag(C.Structure):
+    """Mirror of ``aae_bag``: the batch's CSR rows + W1t for the in-kernel gather (indptr NULL: read h1pre)."""
+    _fields_ = [("indptr", P), ("indices", P), ("W1t", P), ("normalize", I), ("v_begin", I), ("v_end", I)]
+
+
 class AdamBlock(C.Structure):
     """Mirror of ``aae_adam_block``: a packed parameter block with its Adam moments (p NULL: gradient only)."""
     _fields_ = [("p", P), ("m", P), ("v", P), ("which", I)]
@@ -52,11 +57,22 @@ _SIGS = {
     "aae_zero_rows": (I, [P, P, I, I, P]),
     "aae_rows_adam": (I, [P, P, I, P, P, P, P, I, P, I, P]),
     "aae_w1_sweep_untouched": (I, [P, I, I, I, P, P, P, P, P, P, P]),
+    "aae_w1_sweep_untouched_slim": (I, [P, I, I, I, P, P, P, P, P, P, I, P]),
     "aae_adam_dense": (I, [P, P, P, P, I64, P, I, P]),
     "aae_ae_fwd": (I, [AaeDims, P, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P]),
     "aae_ae_bwd": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P, P, P, P]),
     "aae_disc_phase": (I, [AaeDims, P, P, F, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P]),
     "aae_gen_phase": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
+    "aae_ae_fwd_bag": (I, [AaeDims, AaeBag, P, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
+    "aae_disc_phase_bag": (I, [AaeDims, AaeBag, P, P, F, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P]),
+    "aae_gen_phase_bag": (I, [AaeDims, AaeBag, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
+    "aae_predict_tail_bag": (I, [AaeDims, AaeBag, P, P, P, P, P, P]),
+    "aae_batch_prepare": (I, [P, P, I, I, I, P, P, P, P, P, P, P, I, P]),
+    "aae_w1_rows_update": (I, [P, P, I, P, P, P, I, P, P, P, P, I, P, I, P, P]),
+    "aae_step_finish": (I, [P, P, P, I, P, I, D, I, P, P, P, P]),
+    "aae_ktab_write": (I, [P, P, P]),
+    "aae_w1_catchup": (I, [P, P, I, I, I, P, P, P, P, P, P, P, I, P, P, P]),
+    "aae_w1_sweep_blocked": (I, [P, I, I, P, P, P, P, P, P, P, P, I, I, I, P]),
     "aae_ae_wgrad": (I, [AaeDims, P, P, P, P, P, P, P, P, P, P, P, AdamBlock, AdamBlock, P, P]),
     "aae_disc_wgrad": (I, [AaeDims, P, P, P, AdamBlock, P, P]),
     "aae_gen_wgrad": (I, [AaeDims, P, P, P, P, P, P, AdamBlock, P, P]),
@@ -69,6 +85,8 @@ _SIGS = {
     "aae_tc_selftest": (I, [I, P, P, P, I, P]),
     "aae_upload_batch": (I, [P, P, I, I, P, P, P]),
     "aae_finish_losses": (I, [P, D, I, P, P]),
+    "aae_trace_set": (I, [P]),
+    "aae_trace_slots": (I, []),
 }
 
 EXPORTS = tuple(sorted(_SIGS))
@@ -103,7 +121,9 @@ def last_error():
 
 
 # kernels launched per entry point (for the bench's gpu_launches claim); memcpy-only calls count 0
-KERNELS = {"aae_upload_batch": 0, "aae_masked_topk": 2}
+KERNELS = {"aae_upload_batch": 0, "aae_masked_topk": 2, "aae_trace_set": 0, "aae_trace_slots": 0}
+TRACE_NAMES = ("batch_prepare", "w1_sweep_untouched", "ae_fwd", "dec_out_train", "ae_bwd", "ae_wgrad", "w1_rows_update_1",
+               "disc_phase", "disc_wgrad", "gen_phase", "gen_wgrad", "w1_rows_update_2", "step_finish", "bag_fwd", "w1_catchup")
 _launches = 0
 
 
@@ -163,6 +183,13 @@ def require_device(dev=0):
 
 def drop(mask=None, p=0.0, stream_id=0):
     return AaeDrop(P(mask.data_ptr()) if mask is not None else None, float(p), int(stream_id))
+
+
+def bag(indptr=None, indices=None, W1t=None, normalize=1, v_begin=0, v_end=0):
+    if indptr is None:
+        return AaeBag(None, None, None, 0, 0, 0)
+    return AaeBag(P(indptr.data_ptr()), P(indices.data_ptr()), P(W1t.data_ptr()), int(normalize), int(v_begin),
+                  int(v_end))
 
 
 def adam_block(p=None, m=None, v=None, which=0):

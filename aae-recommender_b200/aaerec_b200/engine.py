@@ -93,6 +93,10 @@ class AAEEngine(object):
         self.use_graph = bool(use_graph) and self.world == 1
         self.overlap_sweep = bool(overlap_sweep)
         self.branches = os.environ.get("AAE_B200_NO_BRANCH", "") == ""   # parallel graph branches (debug switch)
+        # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
+        self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "2"))
+        # W1t Adam policy: rows outside the batch are swept in G time-blocked groups (1 = dense sweep every step)
+        self.w1_groups = max(1, min(32, int(os.environ.get("AAE_B200_W1_GROUPS", "4"))))
         self.impl = self._pick_impl(impl)
         self.steps_done = 0
         self._launches_per_step = 0
@@ -110,6 +114,12 @@ class AAEEngine(object):
         self.disc, self.disc_m, self.disc_v, self.g_disc = (z(self.n_disc) for _ in range(4))
         self.state = torch.zeros(C.sizeof(N.StepState), dtype=torch.uint8, device=self.dev)
         self.slot_of = torch.full((Vl,), -1, dtype=torch.int32, device=self.dev)
+        # time-blocked dense Adam of W1t (w1_blocked.cu): last applied step per row, per-step claim marks, and the
+        # ring of per-step Adam constants
+        self.w1_last = torch.zeros(Vl, dtype=torch.int32, device=self.dev)
+        self.w1_claim = torch.zeros(Vl, dtype=torch.int32, device=self.dev)
+        self.ktab = torch.zeros(64 * 4, **f32)
+        self._w1_dirty = False
         self.loss_sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
         self.losses = torch.zeros(3, **f32)
         self._ws_B = 0
@@ -120,12 +130,24 @@ class AAEEngine(object):
         self._cap_stream, self.side, self.side2 = self._distinct_streams(3)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
+        self._ev_prep = torch.cuda.Event()
+        self._ev_k3 = torch.cuda.Event()
         self._ev_fork2 = torch.cuda.Event()
         self._ev_join2 = torch.cuda.Event()
-        call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
+        self._init_state()
         self._ensure_ws(max_batch, max_nnz or max_batch * 64)
 
     # ------------------------------------------------------------------ plumbing
+    def _init_state(self):
+        """Step state for step 1 (aae_step_finish advances it at the end of every step), loss sums cleared."""
+        call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
+        call("aae_step_tick", ptr(self.state), self._stream())
+        call("aae_ktab_write", ptr(self.state), ptr(self.ktab), self._stream())
+        self.loss_sums.zero_()
+        self.w1_last.zero_()
+        self.w1_claim.zero_()
+        self._w1_dirty = False
+
     def _distinct_streams(self, n):
         seen = {torch.cuda.current_stream(self.dev).cuda_stream, torch.cuda.default_stream(self.dev).cuda_stream}
         out = []
@@ -180,7 +202,7 @@ class AAEEngine(object):
         self.z_real = z(B, Cc)
         self.uniq = torch.zeros(nnz, **i32)
         self.n_uniq = torch.zeros(1, **i32)
-        self.G1, self.G2 = z(nnz, H), z(nnz, H)
+        self.csc_cnt, self.csc_pos, self.csc_off, self.csc_row = (torch.zeros(nnz + 1, **i32) for _ in range(4))
         self.h1pre, self.a1, self.a2, self.dd1, self.h2, self.dh2 = (z(B, H) for _ in range(6))
         self.zc = z(B, Cp)
         self.g_d2, self.g_d1, self.g_e2, self.g_h1 = (z(B, H) for _ in range(4))
@@ -225,7 +247,7 @@ class AAEEngine(object):
         for m in (self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2, self.Wd3_m, self.Wd3_v, self.bd3_m, self.bd3_v,
                   self.enc_m1, self.enc_v1, self.enc_m2, self.enc_v2, self.dec_m, self.dec_v, self.disc_m, self.disc_v):
             m.zero_()
-        call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
+        self._init_state()
         self.steps_done = 0
 
     def _gather_items(self, local):
@@ -234,6 +256,7 @@ class AAEEngine(object):
 
     def state_dict(self):
         """Weights in the reference's torch layout (full, gathered over shards), on the host."""
+        self.flush_w1()
         torch.cuda.synchronize(self.dev)
         out = {}
         out["enc.lin1.weight"] = self._gather_items(self.W1t[: self.Vloc]).t().contiguous().cpu()
@@ -338,6 +361,10 @@ class AAEEngine(object):
         self._launches_per_step = N.launch_count() - n0
 
     def _enqueue_step_impl(self, B, injected):
+        """One partial_fit as 11 launches, 9 of them on the dependent chain:
+        [ae_fwd+gather] -> K3 -> ae_bwd -> w1_rows_update || ae_wgrad -> [disc_phase+gather] -> disc_wgrad ->
+        [gen_phase+gather] -> w1_rows_update || gen_wgrad -> step_finish, with batch_prepare -> W1 sweep on a side
+        branch under the decoder kernel.  Item-sharded runs gather separately (the partial sums are all-reduced)."""
         s = self._stream
         H, dims = self.H, AaeDims(B, self.H, self.C, self.D)
         dr = self._drops(B, injected)
@@ -346,28 +373,43 @@ class AAEEngine(object):
         n_total = float(B) * float(self.V)
         cap = self.uniq.numel()
         cur = torch.cuda.current_stream(self.dev)
-        call("aae_step_begin", st, ptr(self.loss_sums), 3, ptr(self.n_uniq), ptr(self.dh2), B * H, ptr(self.G1),
-             ptr(self.G2), ptr(self.indptr), B, H, s())
-        call("aae_batch_slots", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.slot_of), ptr(self.uniq),
-             ptr(self.n_uniq), 1, s())
-        # rows that are not in the batch: both Adam states decay, on a side stream under the step
-        if self.overlap_sweep:
-            self._ev_fork.record(cur)
-            self.side.wait_event(self._ev_fork)
-            with torch.cuda.stream(self.side):
-                call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
-                     ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
-                self._ev_join.record(self.side)
+        fused = self.world == 1
+        bag = N.bag(self.indptr, self.indices, self.W1t, self.normalize, lo, hi) if fused else N.bag()
+        # ---- side branch: slots + transposed batch view, then the zero-gradient Adam decay of every row that is
+        # not in the batch (both optimizer states, one pass)
+        self._ev_fork.record(cur)
+        self.side.wait_event(self._ev_fork)
+        with torch.cuda.stream(self.side):
+            call("aae_batch_prepare", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.slot_of), ptr(self.uniq),
+                 ptr(self.n_uniq), ptr(self.csc_cnt), ptr(self.csc_pos), ptr(self.csc_off), ptr(self.csc_row), cap, s())
+            self._ev_prep.record(self.side)
+
+        def sweep():
+            call("aae_w1_sweep_blocked", ptr(self.slot_of), self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
+                 ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), st, ptr(self.ktab),
+                 self.w1_groups, 0, self.sweep_ctas if self.overlap_sweep else 0, s())
+        # rows of this batch: pending zero-gradient steps applied before the encoder reads them
+        call("aae_w1_catchup", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.w1_claim), ptr(self.W1t),
+             ptr(self.W1_m1), ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), H, st,
+             ptr(self.ktab), s())
         # ---- ae_step (aae.py:676-711)
-        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
-             lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
-        self._allreduce(self.h1pre[:B])
-        call("aae_ae_fwd", dims, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
+        if not fused:
+            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
+                 lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
+            self._allreduce(self.h1pre[:B])
+        call("aae_ae_fwd_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
              dr["ae_e2"], dr["ae_d1"], dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1),
-             ptr(self.h2), s())
+             ptr(self.h2), ptr(self.dh2), s())
         call("aae_dec_out_train", ptr(self.h2), B, H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m), ptr(self.Wd3_v),
              ptr(self.bd3_m), ptr(self.bd3_v), lo, self.Vloc, ptr(self.indptr), ptr(self.indices), n_total, st,
              ptr(self.dh2), ptr(self.loss_sums), self.impl_for(B), s())
+        if self.overlap_sweep:
+            # the decoder kernel owns the SMs and starves beside a bandwidth-bound neighbour (measured: 190 -> 375 us),
+            # so the sweep runs under the latency-bound tail of the step instead, sized to leave the SMs open
+            self._ev_k3.record(cur)
+            self.side.wait_event(self._ev_k3)
+            with torch.cuda.stream(self.side):
+                sweep()
         if self.world > 1:
             self._allreduce(self.dh2[:B])
             self._allreduce(self.loss_sums[:1])
@@ -375,44 +417,45 @@ class AAEEngine(object):
              dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.dd1), ptr(self.h2), ptr(self.g_d2), ptr(self.g_d1),
              ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), s())
         # the small-layer weight gradients (+ enc_optim / dec_optim, fused into the reduction) and the sparse
-        # first-layer gradient are independent: two branches of the step's graph
+        # first-layer update are independent: two branches of the step's graph
         with self._branch():
             call("aae_ae_wgrad", dims, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1), ptr(self.g_d2),
                  ptr(self.g_d1), ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), None, None,
                  N.adam_block(self.enc, self.enc_m1, self.enc_v1, 0),
                  N.adam_block(self.dec, self.dec_m, self.dec_v, 0), st, s())
-        call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.g_h1), H, self.normalize,
-             ptr(self.slot_of), lo, hi, ptr(self.G1), s())
-        call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G1), ptr(self.W1t), ptr(self.W1_m1),
-             ptr(self.W1_v1), H, st, 0, s())
+        cur.wait_event(self._ev_prep)
+        call("aae_w1_rows_update", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.csc_off), ptr(self.csc_row),
+             ptr(self.indptr), self.normalize, ptr(self.g_h1), ptr(self.W1t), ptr(self.W1_m1), ptr(self.W1_v1), H, st,
+             0, None, s())
         self._join()
-        # ---- disc_step (aae.py:713-732) and gen_step (734-743) share X.W1^T + b1 (same weights, same input)
-        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
-             lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
-        self._allreduce(self.h1pre2[:B])
-        call("aae_disc_phase", dims, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
+        # ---- disc_step (aae.py:713-732) and gen_step (734-743)
+        if not fused:
+            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
+                 lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
+            self._allreduce(self.h1pre2[:B])
+        call("aae_disc_phase_bag", dims, bag, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
              C.c_float(self.prior_scale), ptr(self.enc), ptr(self.disc), dr["disc_r1"], dr["disc_r2"], dr["disc_f1"],
              dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
         call("aae_disc_wgrad", dims, ptr(self.disc_acts), ptr(self.disc_grads), None,
              N.adam_block(self.disc, self.disc_m, self.disc_v, 1), st, s())
-        call("aae_gen_phase", dims, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"], dr["gen_e2"],
-             dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
+        call("aae_gen_phase_bag", dims, bag, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"],
+             dr["gen_e2"], dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
              ptr(self.gg_h1), ptr(self.loss_sums[2:]), s())
         with self._branch():
             call("aae_gen_wgrad", dims, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
                  ptr(self.gg_h1), None, N.adam_block(self.enc, self.enc_m2, self.enc_v2, 1), st, s())
-        call("aae_bag_bwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.gg_h1), H, self.normalize,
-             ptr(self.slot_of), lo, hi, ptr(self.G2), s())
-        call("aae_rows_adam", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.G2), ptr(self.W1t), ptr(self.W1_m2),
-             ptr(self.W1_v2), H, st, 1, s())
+        call("aae_w1_rows_update", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.csc_off), ptr(self.csc_row),
+             ptr(self.indptr), self.normalize, ptr(self.gg_h1), ptr(self.W1t), ptr(self.W1_m2), ptr(self.W1_v2), H, st,
+             1, ptr(self.w1_last), s())
         self._join()
         if self.overlap_sweep:
+            self._ev_join.record(self.side)
             cur.wait_event(self._ev_join)
         else:
-            call("aae_w1_sweep_untouched", ptr(self.slot_of), 0, self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
-                 ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), st, s())
-        call("aae_step_end", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), n_total, B,
-             ptr(self.losses), s())
+            cur.wait_event(self._ev_prep)
+            sweep()
+        call("aae_step_finish", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), 3,
+             n_total, B, ptr(self.losses), st, ptr(self.ktab), s())
 
     def train_step(self, B, injected=False):
         """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses
@@ -445,11 +488,22 @@ class AAEEngine(object):
                 self._graphs[key] = g
             g.replay()
         self.steps_done += 1
+        self._w1_dirty = True
+
+    def flush_w1(self):
+        """Apply every pending zero-gradient Adam step to W1t (time-blocked policy): after this the weights are
+        exactly those of dense Adam after ``steps_done`` steps.  Needed before reading rows outside a training
+        step (predict, weight export)."""
+        if self._w1_dirty:
+            call("aae_w1_sweep_blocked", None, self.Vloc, self.H, ptr(self.W1t), ptr(self.W1_m1), ptr(self.W1_v1),
+                 ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), ptr(self.state), ptr(self.ktab), self.w1_groups,
+                 1, 0, self._stream())
+            self._w1_dirty = False
 
     def _snapshot(self):
         names = ("W1t", "W1_m1", "W1_v1", "W1_m2", "W1_v2", "Wd3", "Wd3_m", "Wd3_v", "bd3", "bd3_m", "bd3_v",
                  "enc", "enc_m1", "enc_v1", "enc_m2", "enc_v2", "dec", "dec_m", "dec_v", "disc", "disc_m", "disc_v",
-                 "state")
+                 "state", "w1_last", "w1_claim", "ktab", "loss_sums")
         torch.cuda.synchronize(self.dev)
         return {n: getattr(self, n).clone() for n in names}
 
@@ -462,12 +516,17 @@ class AAEEngine(object):
     # ------------------------------------------------------------------ predict
     def predict_h2(self, B):
         """eval-mode encoder + condition + decoder head for the batch in the device buffers."""
+        self.flush_w1()
         dims = AaeDims(B, self.H, self.C, self.D)
-        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H,
-             self.normalize, self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(self.h1pre), self._stream())
-        self._allreduce(self.h1pre[:B])
-        call("aae_predict_tail", dims, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), ptr(self.h2),
-             self._stream())
+        if self.world == 1:
+            bag = N.bag(self.indptr, self.indices, self.W1t, self.normalize, self.v_begin, self.v_end)
+        else:
+            bag = N.bag()
+            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H,
+                 self.normalize, self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(self.h1pre), self._stream())
+            self._allreduce(self.h1pre[:B])
+        call("aae_predict_tail_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec),
+             ptr(self.h2), self._stream())
         return self.h2[:B]
 
     def scores(self, B, out, apply_sigmoid=True):

@@ -45,6 +45,11 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
 int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
                       float* out, int64_t ldo, int split, cudaStream_t s);
 
+void trace_set_bag(unsigned long long* p);
+void trace_set_mlp(unsigned long long* p);
+void trace_set_tc(unsigned long long* p);
+void trace_set_w1b(unsigned long long* p);
+
 }  // namespace aae
 
 using namespace aae;
@@ -68,6 +73,20 @@ int aae_device_check(int dev) {
   }
   return AAE_OK;
 }
+
+int aae_trace_set(uint64_t* buf) {
+  trace_set_bag(reinterpret_cast<unsigned long long*>(buf));
+  trace_set_mlp(reinterpret_cast<unsigned long long*>(buf));
+  trace_set_tc(reinterpret_cast<unsigned long long*>(buf));
+  trace_set_w1b(reinterpret_cast<unsigned long long*>(buf));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("trace_set: %s", cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  return AAE_OK;
+}
+int aae_trace_slots(void) { return 2 * (int)TR_N; }
 
 int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
                       float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,

@@ -2,9 +2,11 @@
 // weight gradient, and the Adam updates of W1t (touched rows sparse, untouched rows swept).
 // Reference: aaerec/aae.py:132-135 (F.normalize(p=1) + lin1), :703/:741 (backward), :706/:741
 // (enc_optim / gen_optim steps over the same parameters).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace aae {
+AAE_DEFINE_TRACE_SETTER(trace_set_bag)
 
 // ---------------------------------------------------------------------------------------------
 // step state
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(256) bag_fwd_kernel(const int32_t* __restrict_
                                                       float* __restrict__ out) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
+  trace_mark(TR_BAG_FWD, 0);
   if (warp >= B) return;
   int s = indptr[warp], e = indptr[warp + 1];
   float scale = 1.0f;
@@ -226,6 +229,249 @@ __global__ void __launch_bounds__(256) rows_adam_kernel(const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused-step bookkeeping: ONE single-CTA launch builds the touched-row slots and the transposed (item ->
+// batch rows) view of the batch.  It runs on a side branch of the step's graph, under the decoder kernel.
+// Phases (separated by block barriers): (1) slots: first occurrence of an item claims a slot; (2) per entry:
+// position among the item's occurrences; (3) exclusive scan of the counts; (4) fill csc_row.
+// ---------------------------------------------------------------------------------------------
+constexpr int PREP_THREADS = 1024;
+__device__ __forceinline__ int row_of_entry(const int32_t* __restrict__ indptr, int B, int e) {
+  int lo = 0, hi = B;                       // largest b with indptr[b] <= e
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(indptr + mid) <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(PREP_THREADS) batch_prepare_kernel(
+    const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int B, int v_begin, int v_end,
+    int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, int32_t* cnt, int32_t* pos, int32_t* csc_off, int32_t* csc_row,
+    int cap) {
+  __shared__ int s_n;
+  __shared__ int s_warp[PREP_THREADS / 32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nnz = __ldg(indptr + B);
+  trace_mark(TR_PREP, 0);
+  if (tid == 0) { s_n = 0; s_carry = 0; }
+  __syncthreads();
+  for (int e = tid; e < nnz; e += PREP_THREADS) {
+    int i = __ldg(indices + e);
+    if (i < v_begin || i >= v_end) continue;
+    i -= v_begin;
+    if (atomicCAS(&slot_of[i], -1, -2) == -1) {
+      int s = atomicAdd(&s_n, 1);
+      if (s < cap) { uniq[s] = i; cnt[s] = 0; }
+      __stcg(&slot_of[i], s);
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, cap);
+  for (int e = tid; e < nnz; e += PREP_THREADS) {
+    int i = __ldg(indices + e);
+    if (i < v_begin || i >= v_end) continue;
+    int s = __ldcg(&slot_of[i - v_begin]);
+    pos[e] = (s >= 0 && s < cap) ? atomicAdd(&cnt[s], 1) : -1;
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..n) in chunks of PREP_THREADS
+  for (int base = 0; base < n; base += PREP_THREADS) {
+    const int s = base + tid;
+    const int c = (s < n) ? __ldcg(&cnt[s]) : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int incl = x + (warp ? s_warp[warp - 1] : 0) + carry;
+    if (s < n) csc_off[s] = incl - c;
+    __syncthreads();
+    if (tid == PREP_THREADS - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) { csc_off[n] = s_carry; *n_uniq = n; }
+  __syncthreads();
+  for (int e = tid; e < nnz; e += PREP_THREADS) {
+    int i = __ldg(indices + e);
+    if (i < v_begin || i >= v_end) continue;
+    const int p = pos[e];
+    if (p < 0) continue;
+    const int s = __ldcg(&slot_of[i - v_begin]);
+    csc_row[__ldcg(&csc_off[s]) + p] = row_of_entry(indptr, B, e);
+  }
+  trace_mark(TR_PREP, 1);
+}
+
+// K2 fused: one warp per touched item: gradient row summed over the item's batch rows (ascending row order
+// when the item occurs in at most 32 rows, so the result does not depend on the atomics' arrival order in
+// batch_prepare), then Adam on W/m/v in registers.  No gradient buffer, no floating-point atomics.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) w1_rows_update_kernel(const int32_t* __restrict__ uniq,
+                                                             const int32_t* __restrict__ n_uniq, int cap,
+                                                             const int32_t* __restrict__ csc_off,
+                                                             const int32_t* __restrict__ csc_row,
+                                                             const int32_t* __restrict__ indptr, int normalize,
+                                                             const float* __restrict__ dh1, float* __restrict__ W,
+                                                             float* __restrict__ m, float* __restrict__ v, int H,
+                                                             const aae_step_state* __restrict__ st, int which,
+                                                             int32_t* last) {
+  const AdamK k = adam_load(st, which);
+  const int n = min(*n_uniq, cap);
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  trace_mark(which ? TR_ROWS2 : TR_ROWS1, 0);
+  constexpr int CPL = VEC4 ? 1 : 4;          // VEC4: one float4 per lane (H <= 128); else up to 4 strided floats
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const size_t row = (size_t)uniq[s] * H;
+    const int o0 = csc_off[s], cn = csc_off[s + 1] - o0;
+    // old parameter / moments: requested first, consumed after the gradient is summed
+    float4 p4 = make_float4(0, 0, 0, 0), m4 = p4, v4 = p4;
+    float ps[CPL], ms[CPL], vs[CPL];
+    if (VEC4) {
+      if (lane * 4 < H) {
+        p4 = *reinterpret_cast<const float4*>(W + row + lane * 4);
+        m4 = *reinterpret_cast<const float4*>(m + row + lane * 4);
+        v4 = *reinterpret_cast<const float4*>(v + row + lane * 4);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        int c = lane + 32 * q;
+        ps[q] = ms[q] = vs[q] = 0.f;
+        if (c < H) { ps[q] = W[row + c]; ms[q] = m[row + c]; vs[q] = v[row + c]; }
+      }
+    }
+    float4 g4 = make_float4(0, 0, 0, 0);
+    float gs[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) gs[q] = 0.f;
+    for (int c0 = 0; c0 < cn; c0 += 32) {
+      const int nn = min(32, cn - c0);
+      int r = (lane < nn) ? __ldg(csc_row + o0 + c0 + lane) : 0x7fffffff;
+      float sc = 1.0f;
+      if (normalize && lane < nn) sc = 1.0f / fmaxf((float)(__ldg(indptr + r + 1) - __ldg(indptr + r)), 1e-12f);
+      // rank of this lane's row among the chunk's rows (rows are distinct)
+      int rank = 0;
+      for (int j = 0; j < nn; ++j) rank += (__shfl_sync(0xffffffffu, r, j) < r) ? 1 : 0;
+#pragma unroll 4
+      for (int kx = 0; kx < nn; ++kx) {
+        const int src = __ffs(__ballot_sync(0xffffffffu, lane < nn && rank == kx)) - 1;
+        const int b = __shfl_sync(0xffffffffu, r, src);
+        const float w = __shfl_sync(0xffffffffu, sc, src);
+        if (VEC4) {
+          if (lane * 4 < H) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)b * H + lane * 4));
+            g4.x = fmaf(d.x, w, g4.x); g4.y = fmaf(d.y, w, g4.y); g4.z = fmaf(d.z, w, g4.z); g4.w = fmaf(d.w, w, g4.w);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            int c = lane + 32 * q;
+            if (c < H) gs[q] = fmaf(__ldg(dh1 + (size_t)b * H + c), w, gs[q]);
+          }
+        }
+      }
+    }
+    if (VEC4) {
+      if (lane * 4 < H) {
+        adam_update(k, g4.x, p4.x, m4.x, v4.x);
+        adam_update(k, g4.y, p4.y, m4.y, v4.y);
+        adam_update(k, g4.z, p4.z, m4.z, v4.z);
+        adam_update(k, g4.w, p4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(W + row + lane * 4) = p4;
+        *reinterpret_cast<float4*>(m + row + lane * 4) = m4;
+        *reinterpret_cast<float4*>(v + row + lane * 4) = v4;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        int c = lane + 32 * q;
+        if (c < H) {
+          adam_update(k, gs[q], ps[q], ms[q], vs[q]);
+          W[row + c] = ps[q]; m[row + c] = ms[q]; v[row + c] = vs[q];
+        }
+      }
+    }
+    if (last && lane == 0) last[uniq[s]] = st->t;
+  }
+  trace_mark(which ? TR_ROWS2 : TR_ROWS1, 1);
+}
+// any H: lanes stride over the hidden units, one pass per 32 columns (rows re-walked per pass)
+__global__ void __launch_bounds__(256) w1_rows_update_wide_kernel(const int32_t* __restrict__ uniq,
+                                                                  const int32_t* __restrict__ n_uniq, int cap,
+                                                                  const int32_t* __restrict__ csc_off,
+                                                                  const int32_t* __restrict__ csc_row,
+                                                                  const int32_t* __restrict__ indptr, int normalize,
+                                                                  const float* __restrict__ dh1, float* __restrict__ W,
+                                                                  float* __restrict__ m, float* __restrict__ v, int H,
+                                                                  const aae_step_state* __restrict__ st, int which,
+                                                             int32_t* last) {
+  const AdamK k = adam_load(st, which);
+  const int n = min(*n_uniq, cap);
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const size_t row = (size_t)uniq[s] * H;
+    const int o0 = csc_off[s], cn = csc_off[s + 1] - o0;
+    for (int c = lane; c < H; c += 32) {
+      float g = 0.f;
+      for (int j = 0; j < cn; ++j) {
+        const int b = __ldg(csc_row + o0 + j);
+        const float sc = normalize ? 1.0f / fmaxf((float)(__ldg(indptr + b + 1) - __ldg(indptr + b)), 1e-12f) : 1.0f;
+        g = fmaf(__ldg(dh1 + (size_t)b * H + c), sc, g);
+      }
+      float pp = W[row + c], mm = m[row + c], vv = v[row + c];
+      adam_update(k, g, pp, mm, vv);
+      W[row + c] = pp; m[row + c] = mm; v[row + c] = vv;
+    }
+    if (last && lane == 0) last[uniq[s]] = st->t;
+  }
+}
+
+// End of a fused step: slots released, losses finalised, accumulators cleared, step state advanced for the
+// next step.
+__global__ void __launch_bounds__(256) step_finish_kernel(int32_t* slot_of, const int32_t* __restrict__ uniq,
+                                                          const int32_t* __restrict__ n_uniq, int cap, double* sums,
+                                                          int n_sums, double n_total, int B, float* out,
+                                                          aae_step_state* st, float* ktab) {
+  trace_mark(TR_FINISH, 0);
+  int n = min(*n_uniq, cap);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) slot_of[uniq[s]] = -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = (float)(sums[0] / n_total);
+    out[1] = (float)(sums[1] / (double)B);
+    out[2] = (float)(sums[2] / (double)B);
+    for (int i = 0; i < n_sums; ++i) sums[i] = 0.0;
+    int t = st->t + 1;
+    st->t = t;
+    st->rng_step += 1;
+    double bc1 = 1.0 - pow(0.9, (double)t);
+    double bc2 = 1.0 - pow(0.999, (double)t);
+    st->step_size_gen = (float)((double)st->gen_lr / bc1);
+    st->step_size_reg = (float)((double)st->reg_lr / bc1);
+    st->bc2_sqrt = (float)sqrt(bc2);
+    if (ktab)
+      reinterpret_cast<float4*>(ktab)[t & (AAE_KTAB_SLOTS - 1)] =
+          make_float4(st->step_size_gen, st->step_size_reg, 1.0f / st->bc2_sqrt, 0.f);
+  }
+  trace_mark(TR_FINISH, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dense-Adam-equivalent sweep of the rows that are not in the batch: both optimizer states in one
 // pass (5 reads + 5 writes per parameter = 40 B), streaming float4, evict-first loads.
 // A warp owns 32 consecutive float4; the row (and so the touched test) is per float4.
@@ -236,6 +482,7 @@ __global__ void __launch_bounds__(256) w1_sweep_untouched_kernel(const int32_t* 
                                                                  float* __restrict__ m2, float* __restrict__ v2,
                                                                  const aae_step_state* __restrict__ st) {
   AdamK k1 = adam_load(st, 0), k2 = adam_load(st, 1);
+  trace_mark(TR_SWEEP, 0);
   int H4 = H >> 2;
   size_t begin = (size_t)r_begin * H4, end = (size_t)r_end * H4;
   for (size_t q = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < end;
@@ -257,6 +504,60 @@ __global__ void __launch_bounds__(256) w1_sweep_untouched_kernel(const int32_t* 
     __stcs(reinterpret_cast<float4*>(m2) + q, c);
     __stcs(reinterpret_cast<float4*>(v2) + q, d);
   }
+  trace_mark(TR_SWEEP, 1);
+}
+// Co-resident variant: the decoder-output kernel owns every SM (one 544-thread CTA, 221 KB of shared memory,
+// 52k registers), so a sweep launched as 8x256-thread CTAs per SM would simply keep it off the machine until
+// the sweep is done.  This variant is sized to fit BESIDE it: 64-thread CTAs of <= 96 registers (two of them
+// fit into the 13k registers the decoder kernel leaves free), each thread keeping U float4 positions of all five
+// tensors in flight (U*80 bytes) so that few threads still cover the HBM latency.
+template <int T, int U>
+__global__ void __launch_bounds__(T) w1_sweep_untouched_slim_kernel(const int32_t* __restrict__ slot_of, int r_begin,
+                                                                     int r_end, int H, float* __restrict__ W,
+                                                                     float* __restrict__ m1, float* __restrict__ v1,
+                                                                     float* __restrict__ m2, float* __restrict__ v2,
+                                                                     const aae_step_state* __restrict__ st) {
+  const AdamK k1 = adam_load(st, 0), k2 = adam_load(st, 1);
+  trace_mark(TR_SWEEP, 0);
+  const int H4 = H >> 2;
+  const size_t begin = (size_t)r_begin * H4, end = (size_t)r_end * H4;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t q0 = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q0 < end; q0 += nth * U) {
+    float4 p[U], a[U], b[U], c[U], d[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t q = q0 + (size_t)u * nth;
+      live[u] = q < end && __ldg(slot_of + (int)(q / H4)) < 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t q = q0 + (size_t)u * nth;
+      if (live[u]) {
+        p[u] = __ldcs(reinterpret_cast<const float4*>(W) + q);
+        a[u] = __ldcs(reinterpret_cast<const float4*>(m1) + q);
+        b[u] = __ldcs(reinterpret_cast<const float4*>(v1) + q);
+        c[u] = __ldcs(reinterpret_cast<const float4*>(m2) + q);
+        d[u] = __ldcs(reinterpret_cast<const float4*>(v2) + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t q = q0 + (size_t)u * nth;
+      if (live[u]) {
+        adam_update_zero(k1, p[u].x, a[u].x, b[u].x); adam_update_zero(k2, p[u].x, c[u].x, d[u].x);
+        adam_update_zero(k1, p[u].y, a[u].y, b[u].y); adam_update_zero(k2, p[u].y, c[u].y, d[u].y);
+        adam_update_zero(k1, p[u].z, a[u].z, b[u].z); adam_update_zero(k2, p[u].z, c[u].z, d[u].z);
+        adam_update_zero(k1, p[u].w, a[u].w, b[u].w); adam_update_zero(k2, p[u].w, c[u].w, d[u].w);
+        __stcs(reinterpret_cast<float4*>(W) + q, p[u]);
+        __stcs(reinterpret_cast<float4*>(m1) + q, a[u]);
+        __stcs(reinterpret_cast<float4*>(v1) + q, b[u]);
+        __stcs(reinterpret_cast<float4*>(m2) + q, c[u]);
+        __stcs(reinterpret_cast<float4*>(v2) + q, d[u]);
+      }
+    }
+  }
+  trace_mark(TR_SWEEP, 1);
 }
 __global__ void __launch_bounds__(256) w1_sweep_untouched_scalar_kernel(const int32_t* __restrict__ slot_of,
                                                                         int r_begin, int r_end, int H, float* W,
@@ -371,6 +672,62 @@ int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const flo
   int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)cap * 32, 256)));
   rows_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, G, W, m, v, H, st, which);
   return check_launch("rows_adam");
+}
+int aae_batch_prepare(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end, int32_t* slot_of,
+                      int32_t* uniq, int32_t* n_uniq, int32_t* cnt, int32_t* pos, int32_t* csc_off, int32_t* csc_row,
+                      int cap, void* stream) {
+  AAE_REQUIRE(indptr && indices && slot_of && uniq && n_uniq && cnt && pos && csc_off && csc_row, "null pointer");
+  AAE_REQUIRE(B > 0 && cap > 0, "bad size");
+  batch_prepare_kernel<<<1, PREP_THREADS, 0, as_stream(stream)>>>(indptr, indices, B, v_begin, v_end, slot_of, uniq,
+                                                                  n_uniq, cnt, pos, csc_off, csc_row, cap);
+  return check_launch("batch_prepare");
+}
+int aae_w1_rows_update(const int32_t* uniq, const int32_t* n_uniq, int cap, const int32_t* csc_off,
+                       const int32_t* csc_row, const int32_t* indptr, int normalize, const float* dh1, float* W,
+                       float* m, float* v, int H, const aae_step_state* st, int which, int32_t* last, void* stream) {
+  AAE_REQUIRE(uniq && n_uniq && csc_off && csc_row && indptr && dh1 && W && m && v && st, "null pointer");
+  int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)cap * 32, 256)));
+  if ((H & 3) == 0 && H <= 128)
+    w1_rows_update_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                      normalize, dh1, W, m, v, H, st, which, last);
+  else if (H <= 128)
+    w1_rows_update_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                       normalize, dh1, W, m, v, H, st, which, last);
+  else
+    w1_rows_update_wide_kernel<<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                     normalize, dh1, W, m, v, H, st, which, last);
+  return check_launch("w1_rows_update");
+}
+int aae_step_finish(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, double* sums, int n_sums,
+                    double n_total, int B, float* losses, aae_step_state* st, float* ktab, void* stream) {
+  AAE_REQUIRE(slot_of && uniq && n_uniq && sums && losses && st && n_sums >= 3, "null pointer");
+  step_finish_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(cap, 256))), 256, 0, as_stream(stream)>>>(
+      slot_of, uniq, n_uniq, cap, sums, n_sums, n_total, B, losses, st, ktab);
+  return check_launch("step_finish");
+}
+int aae_w1_sweep_untouched_slim(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
+                                float* m2, float* v2, const aae_step_state* st, int ctas_per_sm, void* stream) {
+  AAE_REQUIRE(slot_of && W && m1 && v1 && m2 && v2 && st, "null pointer");
+  AAE_REQUIRE((H & 3) == 0 && ctas_per_sm >= 1 && ctas_per_sm <= 8, "n_hidden must be a multiple of 4; 1..8 CTAs per SM");
+  if (r_end <= r_begin) return AAE_OK;
+  static int cfg = -1;   // experiment switch: AAE_B200_SWEEP_CFG = threads*10 + unroll
+  if (cfg < 0) {
+    const char* e = getenv("AAE_B200_SWEEP_CFG");
+    cfg = e ? atoi(e) : 644;
+  }
+  const int grid = ctas_per_sm * sm_count();
+  cudaStream_t s = as_stream(stream);
+#define SLIM(T, U) w1_sweep_untouched_slim_kernel<T, U><<<grid, T, 0, s>>>(slot_of, r_begin, r_end, H, W, m1, v1, m2, v2, st)
+  switch (cfg) {
+    case 642: SLIM(64, 2); break;
+    case 1282: SLIM(128, 2); break;
+    case 1284: SLIM(128, 4); break;
+    case 2562: SLIM(256, 2); break;
+    case 2561: SLIM(256, 1); break;
+    default: SLIM(64, 4); break;
+  }
+#undef SLIM
+  return check_launch("w1_sweep_untouched_slim");
 }
 int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
                            float* m2, float* v2, const aae_step_state* st, void* stream) {

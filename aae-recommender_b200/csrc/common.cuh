@@ -98,6 +98,29 @@ __device__ __forceinline__ float randn_elem(const aae_step_state* st, uint32_t i
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step timeline (debug/profiling): when a trace buffer is installed (aae_trace_set), block 0 of every kernel
+// of the step writes %globaltimer at its start (slot 2*id) and end (slot 2*id+1).  One pointer copy per
+// translation unit (no relocatable device code); NULL = off (one uniform load per kernel).
+// ---------------------------------------------------------------------------------------------
+enum TraceId { TR_PREP = 0, TR_SWEEP, TR_AE_FWD, TR_K3, TR_AE_BWD, TR_AE_WGRAD, TR_ROWS1, TR_DISC, TR_DISC_WGRAD,
+               TR_GEN, TR_GEN_WGRAD, TR_ROWS2, TR_FINISH, TR_BAG_FWD, TR_CATCHUP, TR_N };
+static __device__ unsigned long long* g_trace_buf = nullptr;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(int id, int end) {
+  // start = earliest block start, end = latest block end (the host presets the slots to ~0 / 0)
+  if (g_trace_buf && threadIdx.x == 0) {
+    if (end) atomicMax(g_trace_buf + 2 * id + 1, globaltimer_ns());
+    else atomicMin(g_trace_buf + 2 * id, globaltimer_ns());
+  }
+}
+#define AAE_DEFINE_TRACE_SETTER(name)                                                    \
+  void name(unsigned long long* p) { cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,6 +36,7 @@
 #endif
 
 namespace aae {
+AAE_DEFINE_TRACE_SETTER(trace_set_tc)
 namespace tc {
 
 constexpr int TN = 32;          // items per tile
@@ -840,6 +841,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
   const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;     // tiles blockIdx.x, +G, ... (grid <= n_tiles)
   const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
 
+  trace_mark(TR_K3, 0);
   if (warp == NWE) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_g1, 1);
@@ -1214,6 +1216,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     atomicAdd(loss_sum, tot);
   }
   if (warp == NWE) tmem_dealloc(tmem, TMEM_COLS);
+  trace_mark(TR_K3, 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 namespace aae {
+AAE_DEFINE_TRACE_SETTER(trace_set_mlp)
 
 constexpr int MLP_THREADS = 256;
 constexpr int STAGE_FLOATS = 10240;   // one staging buffer (40 KB); two of them per CTA
@@ -254,6 +255,66 @@ __device__ __forceinline__ void store_rows(const float* xs, int ld, float* g, in
   }
 }
 
+__device__ __forceinline__ float* align16f(float* p) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+}
+// Row r of h1pre computed in place of a load: b1 + (1/len) * sum of the W1t rows of the set's items (the sparse
+// first encoder layer, aae.py:132-135).  Warp w takes the items w, w + nw, ...; lanes over the hidden units;
+// the per-warp partial sums meet in `scratch` ([nw][H] floats).  Ends with a barrier.
+template <int R>
+__device__ __forceinline__ void gather_rows(float* xs, int ld, const aae_bag& bag, const float* __restrict__ b1, int H,
+                                            int row0, int B, float* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    int s = 0, e = 0;
+    if (row < B) { s = __ldg(bag.indptr + row); e = __ldg(bag.indptr + row + 1); }
+    float* part = scratch + warp * H;
+    if ((H & 3) == 0) {
+      const int H4 = H >> 2;
+      for (int c = lane; c < H4; c += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = s + warp; j < e; j += nw) {
+          const int i = __ldg(bag.indices + j);
+          if (i >= bag.v_begin && i < bag.v_end) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(bag.W1t + (size_t)(i - bag.v_begin) * H) + c);
+            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+          }
+        }
+        reinterpret_cast<float4*>(part)[c] = acc;
+      }
+    } else {
+      for (int c = lane; c < H; c += 32) {
+        float acc = 0.f;
+        for (int j = s + warp; j < e; j += nw) {
+          const int i = __ldg(bag.indices + j);
+          if (i >= bag.v_begin && i < bag.v_end) acc += __ldg(bag.W1t + (size_t)(i - bag.v_begin) * H + c);
+        }
+        part[c] = acc;
+      }
+    }
+    __syncthreads();
+    const float scale = bag.normalize ? 1.0f / fmaxf((float)(e - s), 1e-12f) : 1.0f;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+      float a = 0.f;
+      for (int w = 0; w < nw; ++w) a += scratch[w * H + c];
+      xs[r * ld + c] = (row < B) ? fmaf(a, scale, __ldg(b1 + c)) : 0.f;
+    }
+    __syncthreads();
+  }
+}
+// h1pre rows of this CTA: gathered from the bag, or loaded
+template <int R>
+__device__ __forceinline__ void input_rows(float* xs, int ld, const aae_bag& bag, const float* __restrict__ h1pre,
+                                           const float* __restrict__ b1, int H, int row0, int B, float* scratch) {
+  if (bag.indptr) {
+    gather_rows<R>(xs, ld, bag, b1, H, row0, B, scratch);
+  } else {
+    load_rows<R>(xs, ld, h1pre, H, row0, B);
+    __syncthreads();
+  }
+}
+
 struct EncBlock {
   const float *b1, *We2, *be2, *We3, *be3;
   __device__ EncBlock(const float* p, int H, int C) {
@@ -277,20 +338,26 @@ struct DiscBlock {
 // ae_step forward tail.  Shared memory: [stage buffer 0 | stage buffer 1 | x (R*ld) | y (R*ld)]
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const float* __restrict__ h1pre,
+__global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, aae_bag bag,
+                                                             const float* __restrict__ h1pre,
                                                              const float* __restrict__ cond,
                                                              const float* __restrict__ enc,
                                                              const float* __restrict__ dec, aae_drop e1, aae_drop e2,
                                                              aae_drop d1, aae_drop d2, const aae_step_state* st,
                                                              float* a1, float* a2, float* zc, float* dd1, float* h2,
-                                                             int train) {
+                                                             float* dh2_zero, int train) {
   extern __shared__ __align__(16) float sm[];
   __shared__ LayerW layers[4];
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   const int ld = max(H, Cp);
   float* x = sm + 2 * STAGE_FLOATS;
   float* y = x + R * ld;
+  float* scratch = align16f(y + R * ld);   // [MLP_THREADS/32][H]
   int row0 = blockIdx.x * R;
+  if (train) trace_mark(TR_AE_FWD, 0);
+  if (dh2_zero)
+    for (int q = threadIdx.x; q < R * H; q += blockDim.x)
+      if (row0 + q / H < B) dh2_zero[(size_t)row0 * H + q] = 0.f;
   EncBlock E(enc, H, C);
   DecBlock D(dec, H, Cp);
   aae_drop none = {nullptr, 0.f, 0};
@@ -303,8 +370,8 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const f
   __syncthreads();
   Stager sg;
   sg.init(sm, sm + STAGE_FLOATS, layers, 4);
-  load_rows<R>(x, ld, h1pre, H, row0, B);
-  drop_relu<R>(x, ld, H, row0, B, train ? e1 : none, st, a1);   // same thread -> element mapping as load_rows
+  input_rows<R>(x, ld, bag, h1pre, E.b1, H, row0, B, scratch);
+  drop_relu<R>(x, ld, H, row0, B, train ? e1 : none, st, a1);
   layer_fwd<R>(sg, 0, x, ld, E.be2, y, ld);
   drop_relu<R>(y, ld, H, row0, B, train ? e2 : none, st, a2);
   layer_fwd<R>(sg, 1, y, ld, E.be3, x, ld);   // z -> x[0..C)
@@ -320,6 +387,7 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, const f
   drop_relu<R>(y, ld, H, row0, B, train ? d1 : none, st, dd1);
   layer_fwd<R>(sg, 3, y, ld, D.bd2, x, ld);
   drop_relu<R>(x, ld, H, row0, B, train ? d2 : none, st, h2);
+  if (train) trace_mark(TR_AE_FWD, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,6 +411,7 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const f
   float* t = g + R * ld;
   float* act = t + R * ld;
   int row0 = blockIdx.x * R;
+  trace_mark(TR_AE_BWD, 0);
   EncBlock E(enc, H, C);
   DecBlock D(dec, H, Cp);
   if (threadIdx.x == 0) {
@@ -369,6 +438,7 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const f
   layer_bwd<R>(sg, 3, t, ld, g, ld);
   load_rows<R>(act, ld, a1, H, row0, B);
   drop_relu_bwd<R>(g, act, ld, H, row0, B, e1, st, g_h1);
+  trace_mark(TR_AE_BWD, 1);
 }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -409,7 +479,8 @@ __device__ __forceinline__ void disc_bwd(Stager& sg, int lq2, const float* g_o, 
 //            grads row layout [g1r (H) | g2r (H) | gor (1) | g1f (H) | g2f (H) | gof (1)]
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, const float* __restrict__ h1pre,
+__global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, aae_bag bag,
+                                                                 const float* __restrict__ h1pre,
                                                                  const float* __restrict__ z_real, float prior_scale,
                                                                  const float* __restrict__ enc,
                                                                  const float* __restrict__ disc, aae_drop r1,
@@ -427,7 +498,9 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
   float* zz = q2 + R * ld;
   float* outs = zz + R * ld;   // [R]
   float* go = outs + R;        // [R]
+  float* scratch = align16f(go + R);     // [MLP_THREADS/32][H]
   int row0 = blockIdx.x * R;
+  trace_mark(TR_DISC, 0);
   EncBlock E(enc, H, C);
   DiscBlock Q(disc, H, C);
   aae_drop none = {nullptr, 0.f, 0};
@@ -462,7 +535,7 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
       }
     } else {
       // z_fake = enc(batch) in eval mode (aae.py:714, 722)
-      load_rows<R>(x, ld, h1pre, H, row0, B);
+      input_rows<R>(x, ld, bag, h1pre, E.b1, H, row0, B, scratch);
       drop_relu<R>(x, ld, H, row0, B, none, st, nullptr);
       layer_fwd<R>(sg, 0, x, ld, E.be2, y, ld);
       drop_relu<R>(y, ld, H, row0, B, none, st, nullptr);
@@ -509,13 +582,15 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, con
     }
   }
   if (threadIdx.x < R && lsum != 0.f) atomicAdd(loss_sum, (double)lsum);
+  trace_mark(TR_DISC, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
 // gen_step
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, const float* __restrict__ h1pre,
+__global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, aae_bag bag,
+                                                                const float* __restrict__ h1pre,
                                                                 const float* __restrict__ enc,
                                                                 const float* __restrict__ disc, aae_drop e1,
                                                                 aae_drop e2, aae_drop q1d, aae_drop q2d,
@@ -535,7 +610,9 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
   float* t1 = t0 + R * ld;
   float* outs = t1 + R * ld;
   float* go = outs + R;
+  float* scratch = align16f(go + R);       // [MLP_THREADS/32][H]
   int row0 = blockIdx.x * R;
+  trace_mark(TR_GEN, 0);
   EncBlock E(enc, H, C);
   DiscBlock Q(disc, H, C);
   if (threadIdx.x == 0) {
@@ -546,7 +623,7 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
   __syncthreads();
   Stager sg;
   sg.init(sm, sm + STAGE_FLOATS, layers, 9);
-  load_rows<R>(xa1, ld, h1pre, H, row0, B);
+  input_rows<R>(xa1, ld, bag, h1pre, E.b1, H, row0, B, scratch);
   drop_relu<R>(xa1, ld, H, row0, B, e1, st, a1);
   layer_fwd<R>(sg, 0, xa1, ld, E.be2, xa2, ld);
   drop_relu<R>(xa2, ld, H, row0, B, e2, st, a2);
@@ -566,6 +643,7 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, cons
   drop_relu_bwd<R>(t1, xa2, ld, H, row0, B, e2, st, g_e2);
   layer_bwd<R>(sg, 8, t1, ld, t0, ld);
   drop_relu_bwd<R>(t0, xa1, ld, H, row0, B, e1, st, g_h1);
+  trace_mark(TR_GEN, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -585,6 +663,7 @@ struct WJobs {
   WJob j[10];
   int n, total;
   const aae_step_state* st;
+  int trace_id;
 };
 constexpr int WG_OUT = 64;    // outputs per CTA
 constexpr int WG_PARTS = 4;   // threads per output (split of the batch rows)
@@ -592,6 +671,7 @@ __global__ void __launch_bounds__(WG_OUT * WG_PARTS) small_wgrad_kernel(WJobs jo
   __shared__ float part_s[WG_PARTS][WG_OUT];
   const int el = threadIdx.x % WG_OUT, part = threadIdx.x / WG_OUT;
   const int idx = blockIdx.x * WG_OUT + el;
+  trace_mark(jobs.trace_id, 0);
   const bool live = idx < jobs.total;
   int k = 0;
 #pragma unroll
@@ -632,6 +712,7 @@ __global__ void __launch_bounds__(WG_OUT * WG_PARTS) small_wgrad_kernel(WJobs jo
       J.p[e] = pp; J.m[e] = mm; J.v[e] = vv;
     }
   }
+  trace_mark(jobs.trace_id, 1);
 }
 
 // Adam target of a packed parameter block (nullptr p: gradient only)
@@ -659,6 +740,7 @@ static int launch_jobs(const WJobs& js, cudaStream_t s) {
 }
 
 static inline int rows_per_cta(int B) { return B > 2048 ? 4 : 1; }
+#define SCRATCH_FLOATS(d) ((MLP_THREADS / 32) * (d).H + 8)
 
 }  // namespace aae
 
@@ -667,7 +749,7 @@ using namespace aae;
 #define LAUNCH_R(kernel, B, smem_floats_per_row, stream, ...)                                          \
   do {                                                                                                 \
     int R_ = rows_per_cta(B);                                                                          \
-    size_t smem_ = sizeof(float) * ((size_t)(smem_floats_per_row) * R_ + 2 * STAGE_FLOATS) + 64;       \
+    size_t smem_ = sizeof(float) * ((size_t)(smem_floats_per_row) * R_ + 2 * STAGE_FLOATS + SCRATCH_FLOATS(d)) + 64; \
     if (R_ == 1) {                                                                                     \
       cudaFuncSetAttribute(kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);        \
       kernel<1><<<cdiv(B, 1), MLP_THREADS, smem_, as_stream(stream)>>>(__VA_ARGS__);                   \
@@ -679,26 +761,45 @@ using namespace aae;
 
 extern "C" {
 
-int aae_ae_fwd(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, aae_drop e1,
-               aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st, float* a1, float* a2, float* zc,
-               float* dd1, float* h2, void* stream) {
-  AAE_REQUIRE(h1pre && enc && dec && st && a1 && a2 && zc && dd1 && h2, "null pointer");
+static const aae_bag NO_BAG = {nullptr, nullptr, nullptr, 0, 0, 0};
+static int check_bag(const aae_bag& bag, const float* h1pre) {
+  if (bag.indptr) return (bag.indices && bag.W1t && bag.v_end >= bag.v_begin) ? 1 : 0;
+  return h1pre ? 1 : 0;
+}
+
+int aae_ae_fwd_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* enc, const float* dec,
+                   aae_drop e1, aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st, float* a1, float* a2,
+                   float* zc, float* dd1, float* h2, float* dh2_zero, void* stream) {
+  AAE_REQUIRE(enc && dec && st && a1 && a2 && zc && dd1 && h2, "null pointer");
+  AAE_REQUIRE(check_bag(bag, h1pre), "neither a complete bag nor h1pre given");
   AAE_REQUIRE(d.D == 0 || cond, "condition rows missing");
   AAE_REQUIRE(d.B > 0 && d.H > 0 && d.C > 0 && d.H <= 2048 && d.C + d.D <= 4096, "size outside envelope");
   int ld = std::max(d.H, d.C + d.D);
-  LAUNCH_R(ae_fwd_kernel, d.B, 2 * ld, stream, d, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2, 1);
+  LAUNCH_R(ae_fwd_kernel, d.B, 2 * ld, stream, d, bag, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2,
+           dh2_zero, 1);
   return check_launch("ae_fwd");
 }
+int aae_ae_fwd(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, aae_drop e1,
+               aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st, float* a1, float* a2, float* zc,
+               float* dd1, float* h2, void* stream) {
+  return aae_ae_fwd_bag(d, NO_BAG, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2, nullptr, stream);
+}
 
-int aae_predict_tail(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, float* h2,
-                     void* stream) {
-  AAE_REQUIRE(h1pre && enc && dec && h2, "null pointer");
+int aae_predict_tail_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* enc,
+                         const float* dec, float* h2, void* stream) {
+  AAE_REQUIRE(enc && dec && h2, "null pointer");
+  AAE_REQUIRE(check_bag(bag, h1pre), "neither a complete bag nor h1pre given");
   AAE_REQUIRE(d.D == 0 || cond, "condition rows missing");
   int ld = std::max(d.H, d.C + d.D);
   aae_drop none = {nullptr, 0.f, 0};
-  LAUNCH_R(ae_fwd_kernel, d.B, 2 * ld, stream, d, h1pre, cond, enc, dec, none, none, none, none,
-           (const aae_step_state*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, h2, 0);
+  LAUNCH_R(ae_fwd_kernel, d.B, 2 * ld, stream, d, bag, h1pre, cond, enc, dec, none, none, none, none,
+           (const aae_step_state*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, h2,
+           (float*)nullptr, 0);
   return check_launch("predict_tail");
+}
+int aae_predict_tail(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, float* h2,
+                     void* stream) {
+  return aae_predict_tail_bag(d, NO_BAG, h1pre, cond, enc, dec, h2, stream);
 }
 
 int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec, aae_drop e1, aae_drop e2, aae_drop d1,
@@ -711,35 +812,48 @@ int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec,
   return check_launch("ae_bwd");
 }
 
-int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float prior_scale, const float* enc,
-                   const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2, const aae_step_state* st,
-                   float* acts, float* grads, double* loss_sum, void* stream) {
-  AAE_REQUIRE(h1pre && enc && disc && st && acts && grads && loss_sum, "null pointer");
+int aae_disc_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* z_real, float prior_scale,
+                       const float* enc, const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2,
+                       const aae_step_state* st, float* acts, float* grads, double* loss_sum, void* stream) {
+  AAE_REQUIRE(enc && disc && st && acts && grads && loss_sum, "null pointer");
+  AAE_REQUIRE(check_bag(bag, h1pre), "neither a complete bag nor h1pre given");
   int ld = std::max(d.H, d.C);
   {
     int R_ = rows_per_cta(d.B);
-    size_t smem_ = sizeof(float) * ((size_t)(5 * ld + 2) * R_ + 2 * STAGE_FLOATS) + 64;
+    size_t smem_ = sizeof(float) * ((size_t)(5 * ld + 2) * R_ + 2 * STAGE_FLOATS + SCRATCH_FLOATS(d)) + 64;
     if (R_ == 1) {
       cudaFuncSetAttribute(disc_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
       disc_phase_kernel<1><<<dim3(cdiv(d.B, 1), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
-          d, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+          d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
     } else {
       cudaFuncSetAttribute(disc_phase_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
       disc_phase_kernel<4><<<dim3(cdiv(d.B, 4), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
-          d, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+          d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
     }
   }
   return check_launch("disc_phase");
 }
+int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float prior_scale, const float* enc,
+                   const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2, const aae_step_state* st,
+                   float* acts, float* grads, double* loss_sum, void* stream) {
+  return aae_disc_phase_bag(d, NO_BAG, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum,
+                            stream);
+}
 
+int aae_gen_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* enc, const float* disc, aae_drop e1,
+                      aae_drop e2, aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
+                      float* g_e2, float* g_h1, double* loss_sum, void* stream) {
+  AAE_REQUIRE(enc && disc && st && a1 && a2 && g_z && g_e2 && g_h1 && loss_sum, "null pointer");
+  AAE_REQUIRE(check_bag(bag, h1pre), "neither a complete bag nor h1pre given");
+  int ld = std::max(d.H, d.C);
+  LAUNCH_R(gen_phase_kernel, d.B, 7 * ld + 2, stream, d, bag, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2,
+           g_h1, loss_sum);
+  return check_launch("gen_phase");
+}
 int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float* disc, aae_drop e1, aae_drop e2,
                   aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z, float* g_e2,
                   float* g_h1, double* loss_sum, void* stream) {
-  AAE_REQUIRE(h1pre && enc && disc && st && a1 && a2 && g_z && g_e2 && g_h1 && loss_sum, "null pointer");
-  int ld = std::max(d.H, d.C);
-  LAUNCH_R(gen_phase_kernel, d.B, 7 * ld + 2, stream, d, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2, g_h1,
-           loss_sum);
-  return check_launch("gen_phase");
+  return aae_gen_phase_bag(d, NO_BAG, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2, g_h1, loss_sum, stream);
 }
 
 int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, const float* dd1, const float* g_d2,
@@ -750,7 +864,7 @@ int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, 
   AAE_REQUIRE(st || (!enc_opt.p && !dec_opt.p), "fused Adam needs the step state");
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   WJobs js;
-  js.n = 0; js.total = 0; js.st = st;
+  js.n = 0; js.total = 0; js.st = st; js.trace_id = TR_AE_WGRAD;
   // enc block [b1 | We2 | be2 | We3 | be3]
   OptBlock eo = opt_of(enc_opt), dop = opt_of(dec_opt);
   size_t off = 0;
@@ -776,7 +890,7 @@ int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_d
   // two virtual rows (real, fake) per batch row
   const int AW = C + 2 * H, GW = 2 * H + 1;
   WJobs js;
-  js.n = 0; js.total = 0; js.st = st;
+  js.n = 0; js.total = 0; js.st = st; js.trace_id = TR_DISC_WGRAD;
   OptBlock qo = opt_of(disc_opt);
   size_t off = 0;  // [Wq1 | bq1 | Wq2 | bq2 | wq3 | bq3]
   add_job(js, grads, GW, acts, AW, 2 * B, H, C, g_disc, qo, off); off += (size_t)H * C;
@@ -794,7 +908,7 @@ int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z
   AAE_REQUIRE(st || !enc_opt.p, "fused Adam needs the step state");
   const int H = d.H, C = d.C, B = d.B;
   WJobs js;
-  js.n = 0; js.total = 0; js.st = st;
+  js.n = 0; js.total = 0; js.st = st; js.trace_id = TR_GEN_WGRAD;
   OptBlock eo = opt_of(enc_opt);
   size_t off = 0;
   add_job(js, g_h1, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;

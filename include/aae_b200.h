@@ -113,6 +113,37 @@ int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const flo
 int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
                            float* m2, float* v2, const aae_step_state* st, void* stream);
 
+/* Same update, sized to run BESIDE aae_dec_out_train (whose one CTA per SM leaves 13k registers and no shared
+ * memory free): ctas_per_sm x 64-thread CTAs of <= 96 registers, four float4 positions of all five tensors in
+ * flight per thread.  n_hidden % 4 == 0. */
+int aae_w1_sweep_untouched_slim(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1,
+                                float* v1, float* m2, float* v2, const aae_step_state* st, int ctas_per_sm,
+                                void* stream);
+
+/* ---- time-blocked dense Adam for W1t (the engine's default policy) ----------------------------------
+ * The zero-gradient Adam update of a row that is not in the batch depends only on the row and on the step's
+ * bias corrections, so it may be applied late -- bit-identically -- as long as that happens before the row is
+ * read again.  last[Vloc] (int32, zero-initialised) holds the last step applied to each row, ktab
+ * [AAE_KTAB_SLOTS][4] floats the constants of recent steps (slot t % AAE_KTAB_SLOTS: step_size_gen,
+ * step_size_reg, 1/sqrt(1-b2^t), 0).  Each step only the rows of group t % G of G contiguous groups are swept
+ * (their <= G pending steps replayed in registers, the same fp32 operations in the same order as the dense
+ * sweep): 40/G bytes of HBM traffic per parameter per step instead of 40.  G = 1 is the dense sweep.
+ *   aae_ktab_write      : store the constants of step st->t (after aae_step_state_init + aae_step_tick).
+ *   aae_w1_catchup      : rows of the batch -> up to date through step t-1 (before the encoder gathers them);
+ *                         claim[Vloc] (int32, zero-initialised) de-duplicates items shared by several sets.
+ *   aae_w1_sweep_blocked: flush == 0: group t % G, rows with slot_of < 0, up to step t;  flush != 0: every row up
+ *                         to step t-1 (call between steps, before predict / weight export).
+ *                         ctas_per_sm > 0: slim 128-thread CTAs that run beside the step's small kernels.
+ *   aae_w1_rows_update with last != NULL stamps the updated rows with step t. */
+#define AAE_KTAB_SLOTS 64
+int aae_ktab_write(const aae_step_state* st, float* ktab, void* stream);
+int aae_w1_catchup(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end, int32_t* claim,
+                   float* W, float* m1, float* v1, float* m2, float* v2, int32_t* last, int H,
+                   const aae_step_state* st, const float* ktab, void* stream);
+int aae_w1_sweep_blocked(const int32_t* slot_of, int Vloc, int H, float* W, float* m1, float* v1, float* m2,
+                         float* v2, int32_t* last, const aae_step_state* st, const float* ktab, int G, int flush,
+                         int ctas_per_sm, void* stream);
+
 /* Elementwise Adam over a contiguous block of n parameters (the small replicated layers). */
 int aae_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, const aae_step_state* st,
                    int which, void* stream);
@@ -153,6 +184,53 @@ int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float pr
 int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float* disc, aae_drop e1, aae_drop e2,
                   aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
                   float* g_e2, float* g_h1, double* loss_sum, void* stream);
+
+/* ---- fused step (the engine's default flow): the sparse first layer inside the row-local kernels ----
+ * aae_bag describes the batch's CSR rows and W1t; a kernel given a bag with indptr != NULL computes its row
+ * of h1pre = b1 + sum_{i in set_b} W1t[i,:] (/|set_b|) itself (aae.py:132-135) instead of reading it from
+ * memory, which removes the separate gather launch from the step's dependent chain.  indptr == NULL: the
+ * kernel reads `h1pre` (item-sharded runs, where the partial sums are all-reduced first). */
+typedef struct {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const float* W1t;        /* [v_end - v_begin, H] */
+  int normalize;
+  int v_begin, v_end;
+} aae_bag;
+/* aae_ae_fwd with the optional in-kernel gather; dh2_zero (may be NULL): the [B,H] accumulator of
+ * aae_dec_out_train, cleared row by row here so that the step needs no separate zeroing launch. */
+int aae_ae_fwd_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* enc,
+                   const float* dec, aae_drop e1, aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st,
+                   float* a1, float* a2, float* zc, float* dd1, float* h2, float* dh2_zero, void* stream);
+int aae_disc_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* z_real, float prior_scale,
+                       const float* enc, const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2,
+                       const aae_step_state* st, float* acts, float* grads, double* loss_sum, void* stream);
+int aae_gen_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* enc, const float* disc, aae_drop e1,
+                      aae_drop e2, aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2,
+                      float* g_z, float* g_e2, float* g_h1, double* loss_sum, void* stream);
+int aae_predict_tail_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* enc,
+                         const float* dec, float* h2, void* stream);
+
+/* Batch bookkeeping in ONE launch (off the step's dependent chain): touched-row slots as aae_batch_slots
+ * (slot_of / uniq / n_uniq; n_uniq is cleared here) plus the transposed view of the batch: for slot s the
+ * batch rows that contain item uniq[s] are csc_row[csc_off[s] .. csc_off[s+1]).  cnt [cap] and pos [nnz] are
+ * int32 scratch, csc_off has cap+1 entries, csc_row nnz entries; cap >= number of distinct local items. */
+int aae_batch_prepare(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end,
+                      int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, int32_t* cnt, int32_t* pos,
+                      int32_t* csc_off, int32_t* csc_row, int cap, void* stream);
+/* K2 fused: gradient of the sparse first layer AND Adam on the touched rows, no intermediate buffer and no
+ * atomics: for every touched item i, g = sum_{b : i in set_b} dh1[b,:] (/|set_b|) over the rows listed by
+ * aae_batch_prepare, then the Adam update of W[i,:] (aae.py:703/706 with which = 0, :741 with which = 1). */
+int aae_w1_rows_update(const int32_t* uniq, const int32_t* n_uniq, int cap, const int32_t* csc_off,
+                       const int32_t* csc_row, const int32_t* indptr, int normalize, const float* dh1, float* W,
+                       float* m, float* v, int H, const aae_step_state* st, int which, int32_t* last,
+                       void* stream);
+/* End of a fused step: aae_step_end, then the loss accumulators are cleared and the step state is advanced
+ * (aae_step_tick) for the NEXT step -- so a step starts with its Adam constants and Philox counter in place
+ * and needs no begin launch.  Call aae_step_tick once after aae_step_state_init when using this flow. */
+int aae_step_finish(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, double* sums, int n_sums,
+                    double n_total, int B, float* losses, aae_step_state* st, float* ktab /* may be NULL */,
+                    void* stream);
 
 /* Weight/bias gradients of the small layers (reductions over the batch): block-shaped outputs matching
  * the parameter blocks.  With an aae_adam_block whose p is non-NULL the optimizer step of that block
@@ -215,6 +293,15 @@ int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int spl
 /* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);
+
+/* ---- step timeline (profiling aid) ---------------------------------------------------------------
+ * With a device buffer of aae_trace_slots() uint64 installed, block 0 of every kernel of the step writes
+ * %globaltimer (ns) at its start (slot 2*id) and end (slot 2*id+1); ids in the order: batch_prepare,
+ * w1_sweep_untouched, ae_fwd, dec_out_train, ae_bwd, ae_wgrad, w1_rows_update(enc_optim), disc_phase,
+ * disc_wgrad, gen_phase, gen_wgrad, w1_rows_update(gen_optim), step_finish, bag_fwd, w1_catchup.  buf == NULL: off.
+ * Synchronises the device. */
+int aae_trace_set(uint64_t* buf);
+int aae_trace_slots(void);
 
 /* finalise the three losses on device: out[0]=R/(n_total), out[1]=D/B, out[2]=G/B (float32). */
 int aae_finish_losses(const double* sums, double n_total, int B, float* out, void* stream);

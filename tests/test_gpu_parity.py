@@ -189,6 +189,10 @@ def test_native_rng_statistics():
     eng.load_params(O.init_params(V, H, C, seed=3))
     X = synth_sets(B, V, 8, seed=1)
     eng.upload_csr(X.indptr.astype(np.int32), X.indices.astype(np.int32))
+    # the step gathers h1pre inside its kernels: compute it separately (same weights) for the statistics
+    from aaerec_b200._native import call, ptr
+    call("aae_bag_fwd", ptr(eng.indptr), ptr(eng.indices), B, ptr(eng.W1t), ptr(eng.enc), H, 1, 0, V, 1,
+         ptr(eng.h1pre), eng._stream())
     eng.train_step(B)
     torch.cuda.synchronize()
     h1 = eng.h1pre[:B]
