@@ -8,11 +8,11 @@ from .condition import (ConditionList, ConditionBase, ConcatenationBasedConditio
                         PrecomputedEmbeddingCondition, _check_conditions)
 
 __all__ = ["Recommender", "ConditionList", "ConditionBase", "ConcatenationBasedConditioning",
-           "PrecomputedEmbeddingCondition", "AAERecommender", "AdversarialAutoEncoder", "AAEEngine"]
+           "PrecomputedEmbeddingCondition", "AAERecommender", "AdversarialAutoEncoder", "AutoEncoder", "AAEEngine"]
 
 
 def __getattr__(name):
-    if name in ("AAERecommender", "AdversarialAutoEncoder"):
+    if name in ("AAERecommender", "AdversarialAutoEncoder", "AutoEncoder"):
         from . import aae
         return getattr(aae, name)
     if name == "AAEEngine":

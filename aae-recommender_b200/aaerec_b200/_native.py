@@ -35,6 +35,11 @@ class AdamBlock(C.Structure):
     _fields_ = [("p", P), ("m", P), ("v", P), ("which", I)]
 
 
+class AaePeers(C.Structure):
+    """Mirror of ``aae_peers``: every rank's exchange buffer as mapped in this process."""
+    _fields_ = [("base", P * 8), ("rank", I), ("world", I)]
+
+
 class StepState(C.Structure):
     """Mirror of ``aae_step_state`` (device resident; used for size and for debugging reads)."""
     _fields_ = [("t", C.c_int32), ("rng_step", C.c_uint32), ("step_size_gen", F), ("step_size_reg", F),
@@ -85,6 +90,13 @@ _SIGS = {
     "aae_tc_selftest": (I, [I, P, P, P, I, P]),
     "aae_upload_batch": (I, [P, P, I, I, P, P, P]),
     "aae_finish_losses": (I, [P, D, I, P, P]),
+    "aae_peer_buffer_bytes": (I64, [I64]),
+    "aae_peer_alloc": (I, [I64, C.POINTER(P), C.c_char_p]),
+    "aae_peer_open": (I, [C.c_char_p, C.POINTER(P)]),
+    "aae_peer_close": (I, [P]),
+    "aae_peer_free": (I, [P]),
+    "aae_peer_allreduce": (I, [AaePeers, I, P, I, P, I, I64, P]),
+    "aae_peer_error": (I, [P, C.POINTER(I)]),
     "aae_trace_set": (I, [P]),
     "aae_trace_slots": (I, []),
 }
@@ -121,7 +133,8 @@ def last_error():
 
 
 # kernels launched per entry point (for the bench's gpu_launches claim); memcpy-only calls count 0
-KERNELS = {"aae_upload_batch": 0, "aae_masked_topk": 2, "aae_trace_set": 0, "aae_trace_slots": 0}
+KERNELS = {"aae_upload_batch": 0, "aae_masked_topk": 2, "aae_trace_set": 0, "aae_trace_slots": 0,
+           "aae_peer_alloc": 0, "aae_peer_open": 0, "aae_peer_close": 0, "aae_peer_free": 0, "aae_peer_error": 0}
 TRACE_NAMES = ("batch_prepare", "w1_sweep_untouched", "ae_fwd", "dec_out_train", "ae_bwd", "ae_wgrad", "w1_rows_update_1",
                "disc_phase", "disc_wgrad", "gen_phase", "gen_wgrad", "w1_rows_update_2", "step_finish", "bag_fwd", "w1_catchup")
 _launches = 0
@@ -134,6 +147,12 @@ def reset_launch_count():
 
 def launch_count():
     return _launches
+
+
+def count_launch(n=1):
+    """Account for kernels launched outside ``call`` (the peer-exchange kernel)."""
+    global _launches
+    _launches += n
 
 
 _timing = None   # list of (name, start_event, end_event) while timing is enabled

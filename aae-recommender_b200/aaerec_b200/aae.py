@@ -34,20 +34,25 @@ PRIOR_ACTIVATIONS = {'categorical': 'softmax', 'bernoulli': 'sigmoid', 'gauss': 
 SUPPORTED_OPTIMIZERS = {'adam'}   # the reference's table also has 'sgd' (aae.py:216-219)
 
 
-def _init_linear_params(n_items, n_hidden, n_code, code_size):
-    """Same construction order and stock nn.Linear init as aae.py:782-792, on the CPU generator."""
+def _init_linear_params(n_items, n_hidden, n_code, code_size, adversarial=True):
+    """Same construction order and stock nn.Linear init as aae.py:782-792, on the CPU generator.  The plain
+    AutoEncoder builds no discriminator (aae.py:368-387) and so draws nothing for it."""
     out = {}
     for name, fin, fout in (
             ("enc.lin1", n_items, n_hidden), ("enc.lin2", n_hidden, n_hidden), ("enc.lin3", n_hidden, n_code),
             ("dec.lin1", code_size, n_hidden), ("dec.lin2", n_hidden, n_hidden), ("dec.lin3", n_hidden, n_items),
             ("disc.lin1", n_code, n_hidden), ("disc.lin2", n_hidden, n_hidden), ("disc.lin3", n_hidden, 1)):
+        if name.startswith("disc") and not adversarial:
+            out[name + ".weight"] = torch.zeros(fout, fin)
+            out[name + ".bias"] = torch.zeros(fout)
+            continue
         lin = torch.nn.Linear(fin, fout)
         out[name + ".weight"] = lin.weight.detach()
         out[name + ".bias"] = lin.bias.detach()
     return out
 
 
-def _draw_step_rng(B, n_hidden, n_code, dropout, prior_scale):
+def _draw_step_rng(B, n_hidden, n_code, dropout, prior_scale, adversarial=True):
     """The reference's draws for one partial_fit, same calls in the same order on torch's global CPU
     generator: nn.Dropout == x * empty_like(x).bernoulli_(1-p).div_(1-p); p == 0 draws
     nothing; z_real = torch.randn (aae.py:716)."""
@@ -61,6 +66,8 @@ def _draw_step_rng(B, n_hidden, n_code, dropout, prior_scale):
     def pair():
         return (mask(p1), mask(p2))
     r = {"ae_enc": pair(), "ae_dec": pair()}
+    if not adversarial:       # AutoEncoder.ae_step draws the four reconstruction-phase masks only (aae.py:267-306)
+        return r
     z = torch.randn((B, n_code))
     if prior_scale is not None:
         z = z * prior_scale
@@ -92,6 +99,7 @@ class _ModuleView(object):
 
 class AdversarialAutoEncoder(object):
     """ Adversarial Autoencoder (aae.py:589) """
+    adversarial = True
 
     def __init__(self,
                  n_hidden=100,
@@ -203,13 +211,13 @@ class AdversarialAutoEncoder(object):
     # -- helpers
     def _build(self, n_items, code_size, params=None):
         if params is None:
-            params = _init_linear_params(n_items, self.n_hidden, self.n_code, code_size)
+            params = _init_linear_params(n_items, self.n_hidden, self.n_code, code_size, self.adversarial)
         self.engine = AAEEngine(n_items, self.n_hidden, self.n_code, cond_dim=code_size - self.n_code,
                                 gen_lr=self.gen_lr, reg_lr=self.reg_lr, dropout=self.dropout,
                                 prior_scale=self.prior_scale, normalize_inputs=self.normalize_inputs,
                                 device=self.device, rank=self.rank, world=self.world, group=self.group,
                                 impl=self.impl, seed=self.seed, max_batch=self.batch_size,
-                                use_graph=self.use_graph)
+                                use_graph=self.use_graph, adversarial=self.adversarial)
         self.engine.load_params(params)
         self.last_losses = None
 
@@ -256,7 +264,7 @@ class AdversarialAutoEncoder(object):
         B, _ = eng.upload_csr(indptr, indices, cond_rows)
         injected = False
         if self.rng == 'oracle':
-            draws = _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale)
+            draws = _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale, self.adversarial)
             eng.set_rng_draws(B, draws)
             injected = True
         eng.train_step(B, injected=injected)
@@ -273,10 +281,10 @@ class AdversarialAutoEncoder(object):
         use_condition = _check_conditions(self.conditions, condition_data)
         if use_condition:
             code_size = self.n_code + self.conditions.size_increment()
-            print("Using condition, code size:", code_size)
+            print(("" if self.adversarial else "[ae] ") + "Using condition, code size:", code_size)
         else:
             code_size = self.n_code
-            print("Not using condition, code size:", code_size)
+            print(("" if self.adversarial else "[ae] ") + "Not using condition, code size:", code_size)
         X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
         if not X.has_sorted_indices:
             X = X.sorted_indices()
@@ -364,6 +372,38 @@ class AdversarialAutoEncoder(object):
         return (idx, val) if return_scores else idx
 
 
+class AutoEncoder(AdversarialAutoEncoder):
+    """Plain (non-adversarial) autoencoder, aae.py:221-458: the reconstruction phase of the AAE alone, enc_optim
+    and dec_optim both at ``lr`` (aae.py:393-394), no discriminator, no prior.  Same kernels, same engine with the
+    adversarial phases switched off; the losses read (R, 0, 0) as the reference logs them (aae.py:341-342)."""
+    adversarial = False
+
+    def __init__(self, n_hidden=100, n_code=50, lr=0.001, batch_size=100, n_epochs=500, optimizer='adam',
+                 normalize_inputs=True, activation='ReLU', dropout=(.2, .2), conditions=None, verbose=True,
+                 rng='native', impl='auto', device=None, rank=0, world=1, group=None, seed=0, use_graph=True):
+        # reg_lr = 0: the second Adam state of enc.lin1 (gen_optim in the AAE) is never stepped and stays exactly zero
+        super().__init__(n_hidden=n_hidden, n_code=n_code, gen_lr=lr, reg_lr=0.0, prior='gauss', prior_scale=None,
+                         batch_size=batch_size, n_epochs=n_epochs, optimizer=optimizer,
+                         normalize_inputs=normalize_inputs, activation=activation, dropout=dropout,
+                         conditions=conditions, verbose=verbose, rng=rng, impl=impl, device=device, rank=rank,
+                         world=world, group=group, seed=seed, use_graph=use_graph)
+        self.lr = lr
+
+    def __str__(self):
+        # the reference class defines no __str__; AAERecommender.train prints the object (aae.py:958)
+        return "Autoencoder ({0}, {0}, {1}, {0}, {0}) optimized by {2} with learning rate {3}, batch size {4}".format(
+            self.n_hidden, self.n_code, self.optimizer, self.lr, self.batch_size)
+
+    def partial_fit(self, X, y=None, condition_data=None, step=None):
+        if y is not None:
+            raise ValueError("(Semi-)supervised usage not supported")     # aae.py:321-322 (ValueError here)
+        return super().partial_fit(X, y=None, condition_data=condition_data, step=step)
+
+    @property
+    def disc(self):
+        return None
+
+
 class AAERecommender(Recommender):
     """Adversarially Regularized Recommender (aae.py:873-977)."""
 
@@ -399,8 +439,7 @@ class AAERecommender(Recommender):
         if self.adversarial:
             self.model = AdversarialAutoEncoder(conditions=self.conditions, **self.model_params)
         else:
-            raise NotImplementedError("adversarial=False (plain AutoEncoder, aae.py:221-458) is not on the "
-                                      "accelerated path yet (SURVEY 8(f) rank 1)")
+            self.model = AutoEncoder(conditions=self.conditions, **self.model_params)
         print(self.model)
         print(self.conditions)
         self.model.fit(X, condition_data=condition_data)

@@ -77,7 +77,7 @@ class AAEEngine(object):
     def __init__(self, n_items, n_hidden=100, n_code=50, cond_dim=0, gen_lr=1e-3, reg_lr=1e-3,
                  dropout=(.2, .2), prior_scale=None, normalize_inputs=True, device=None,
                  rank=0, world=1, group=None, impl="auto", seed=0, max_batch=128, max_nnz=None,
-                 use_graph=True, overlap_sweep=True):
+                 use_graph=True, overlap_sweep=True, adversarial=True, exchange="auto"):
         N.require_device(0 if device is None else (torch.device(device).index or 0))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.V, self.H, self.C, self.D = int(n_items), int(n_hidden), int(n_code), int(cond_dim)
@@ -90,7 +90,12 @@ class AAEEngine(object):
         self.v_begin, self.v_end = shard_range(self.V, self.rank, self.world)
         self.Vloc = self.v_end - self.v_begin
         self.seed = int(seed)
-        self.use_graph = bool(use_graph) and self.world == 1
+        # adversarial=False: the plain AutoEncoder of aae.py:221-458 -- the reconstruction phase alone (enc_optim and
+        # dec_optim at one learning rate; pass reg_lr=0 so that the unused second Adam state of W1t stays exactly zero)
+        self.adversarial = bool(adversarial)
+        self.use_graph = bool(use_graph)
+        self.peer = None
+        self._exchange_kind = "none"
         self.overlap_sweep = bool(overlap_sweep)
         self.branches = os.environ.get("AAE_B200_NO_BRANCH", "") == ""   # parallel graph branches (debug switch)
         # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
@@ -136,8 +141,30 @@ class AAEEngine(object):
         self._ev_join2 = torch.cuda.Event()
         self._init_state()
         self._ensure_ws(max_batch, max_nnz or max_batch * 64)
+        if self.world > 1:
+            self._setup_exchange(exchange, max(int(max_batch), 128) * self.H)
 
     # ------------------------------------------------------------------ plumbing
+    def _setup_exchange(self, exchange, n_max):
+        """Item shards exchange [B,H] partial sums three times per step: through our own one-shot all-reduce kernel
+        over NVLink peer memory (``PeerExchange``; graph-capturable), or -- when CUDA IPC mapping is not possible or
+        ``exchange='nccl'`` / AAE_B200_EXCHANGE=nccl -- through NCCL all-reduces (eager, no CUDA graph)."""
+        kind = os.environ.get("AAE_B200_EXCHANGE", exchange)
+        if kind in ("auto", "peer"):
+            try:
+                from .dist import PeerExchange
+                self.peer = PeerExchange(self.rank, self.world, self.group, n_max, self.dev)
+                self._exchange_kind = "peer"
+            except Exception as e:   # noqa: BLE001
+                if kind == "peer":
+                    raise
+                if self.rank == 0:
+                    print("aaerec_b200: peer-memory exchange unavailable (%s); using NCCL all-reduce" % (e,))
+                self.peer = None
+        if self.peer is None:
+            self._exchange_kind = "nccl"
+            self.use_graph = self.use_graph and os.environ.get("AAE_B200_NCCL_GRAPH", "") == "1"
+
     def _init_state(self):
         """Step state for step 1 (aae_step_finish advances it at the end of every step), loss sums cleared."""
         call("aae_step_state_init", ptr(self.state), self.gen_lr, self.reg_lr, C.c_uint64(self.seed), self._stream())
@@ -240,6 +267,10 @@ class AAEEngine(object):
                            (self.disc, disc_block_sizes(self.H, self.C))):
             off = 0
             for name, sz in sizes:
+                if name not in params and name.startswith("disc.") and not self.adversarial:
+                    blk[off:off + sz].zero_()      # the plain AutoEncoder has no discriminator
+                    off += sz
+                    continue
                 v = t(name).reshape(-1)
                 assert v.numel() == sz, (name, v.numel(), sz)
                 blk[off:off + sz].copy_(v)
@@ -317,11 +348,14 @@ class AAEEngine(object):
                  ("disc_fake", 0), ("disc_fake", 1), ("gen_enc", 0), ("gen_enc", 1), ("gen_disc", 0), ("gen_disc", 1)]
         have = False
         for i, (k, j) in enumerate(order):
+            if k not in draws:      # plain AutoEncoder: only the four masks of the reconstruction phase exist
+                continue
             m = draws[k][j]
             if m is not None:
                 self.masks[i, :B].copy_(torch.as_tensor(m, dtype=torch.float32), non_blocking=False)
                 have = True
-        self.z_real[:B].copy_(torch.as_tensor(draws["z_real"], dtype=torch.float32))
+        if "z_real" in draws:
+            self.z_real[:B].copy_(torch.as_tensor(draws["z_real"], dtype=torch.float32))
         return have
 
     # ------------------------------------------------------------------ one partial_fit
@@ -345,10 +379,19 @@ class AAEEngine(object):
         if self.branches:
             torch.cuda.current_stream(self.dev).wait_event(self._ev_join2)
 
-    def _allreduce(self, t):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(t, group=self.group)
+    def _allreduce(self, t, exchange=0, extra=None):
+        """Sum of the shards' partial results, in place: exchange ids 0 (ae-phase h1pre), 1 (dh2 + loss partial),
+        2 (disc/gen-phase h1pre), 3 (predict)."""
+        if self.world == 1:
+            return
+        if self.peer is not None and t.numel() <= self.peer.n_max:
+            self.peer.allreduce(t, exchange, extra)
+            N.count_launch(1)
+            return
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
+        if extra is not None:
+            dist.all_reduce(extra, group=self.group)
 
     def launches_per_step(self):
         """Kernels of ours launched by one train_step (counted while enqueueing; a graph replay
@@ -396,7 +439,7 @@ class AAEEngine(object):
         if not fused:
             call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
                  lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
-            self._allreduce(self.h1pre[:B])
+            self._allreduce(self.h1pre[:B], 0)
         call("aae_ae_fwd_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
              dr["ae_e2"], dr["ae_d1"], dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1),
              ptr(self.h2), ptr(self.dh2), s())
@@ -411,8 +454,7 @@ class AAEEngine(object):
             with torch.cuda.stream(self.side):
                 sweep()
         if self.world > 1:
-            self._allreduce(self.dh2[:B])
-            self._allreduce(self.loss_sums[:1])
+            self._allreduce(self.dh2[:B], 1, self.loss_sums[:1])
         call("aae_ae_bwd", dims, ptr(self.dh2), ptr(self.enc), ptr(self.dec), dr["ae_e1"], dr["ae_e2"], dr["ae_d1"],
              dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.dd1), ptr(self.h2), ptr(self.g_d2), ptr(self.g_d1),
              ptr(self.g_z), ptr(self.g_e2), ptr(self.g_h1), s())
@@ -426,13 +468,29 @@ class AAEEngine(object):
         cur.wait_event(self._ev_prep)
         call("aae_w1_rows_update", ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.csc_off), ptr(self.csc_row),
              ptr(self.indptr), self.normalize, ptr(self.g_h1), ptr(self.W1t), ptr(self.W1_m1), ptr(self.W1_v1), H, st,
-             0, None, s())
+             0, None if self.adversarial else ptr(self.w1_last), s())
         self._join()
+        if self.adversarial:
+            self._enqueue_adversarial(B, dims, bag, dr, fused, cap, injected)
+        if self.overlap_sweep:
+            self._ev_join.record(self.side)
+            cur.wait_event(self._ev_join)
+        else:
+            cur.wait_event(self._ev_prep)
+            sweep()
+        call("aae_step_finish", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), 3,
+             n_total, B, ptr(self.losses), st, ptr(self.ktab), s())
+
+    def _enqueue_adversarial(self, B, dims, bag, dr, fused, cap, injected):
+        """disc_step (aae.py:713-732) and gen_step (aae.py:734-743) of one partial_fit."""
+        s = self._stream
+        H, st = self.H, ptr(self.state)
+        lo, hi = self.v_begin, self.v_end
         # ---- disc_step (aae.py:713-732) and gen_step (734-743)
         if not fused:
             call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
                  lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
-            self._allreduce(self.h1pre2[:B])
+            self._allreduce(self.h1pre2[:B], 2)
         call("aae_disc_phase_bag", dims, bag, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
              C.c_float(self.prior_scale), ptr(self.enc), ptr(self.disc), dr["disc_r1"], dr["disc_r2"], dr["disc_f1"],
              dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
@@ -448,14 +506,6 @@ class AAEEngine(object):
              ptr(self.indptr), self.normalize, ptr(self.gg_h1), ptr(self.W1t), ptr(self.W1_m2), ptr(self.W1_v2), H, st,
              1, ptr(self.w1_last), s())
         self._join()
-        if self.overlap_sweep:
-            self._ev_join.record(self.side)
-            cur.wait_event(self._ev_join)
-        else:
-            cur.wait_event(self._ev_prep)
-            sweep()
-        call("aae_step_finish", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), 3,
-             n_total, B, ptr(self.losses), st, ptr(self.ktab), s())
 
     def train_step(self, B, injected=False):
         """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses
@@ -524,7 +574,7 @@ class AAEEngine(object):
             bag = N.bag()
             call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H,
                  self.normalize, self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(self.h1pre), self._stream())
-            self._allreduce(self.h1pre[:B])
+            self._allreduce(self.h1pre[:B], 3)
         call("aae_predict_tail_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec),
              ptr(self.h2), self._stream())
         return self.h2[:B]

@@ -285,6 +285,33 @@ int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, co
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
                    float* val_out, void* stream);
 
+/* ---- item-sharded exchange over NVLink peer memory (multi-GPU) -------------------------------------
+ * What one device does inside a single dense GEMM in the reference (aae.py:132-135 X.W1^T, aae.py:176-177/703 the
+ * decoder output layer and its input gradient) becomes, for item shards, an all-reduce(sum) of [B,H] partial sums.
+ * Each rank owns one exchange buffer (cudaMalloc + CUDA IPC) that its peers map; aae_peer_allreduce is ONE kernel:
+ * publish the local partial, signal/wait through flags in peer memory, sum the peers' slots in rank order (bit-identical
+ * result on every rank).  No host synchronisation, capturable in a CUDA graph.  See csrc/peer.cu. */
+#define AAE_PEER_MAX_WORLD 8
+#define AAE_PEER_EXCHANGES 4       /* independent exchange ids (each with its own flags, sequence number and slots) */
+#define AAE_PEER_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
+typedef struct {
+  void* base[AAE_PEER_MAX_WORLD];  /* exchange buffer of every rank as mapped in THIS process (own buffer at [rank]) */
+  int rank, world;
+} aae_peers;
+/* Bytes of one rank's exchange buffer for messages of up to n_max floats. */
+int64_t aae_peer_buffer_bytes(int64_t n_max);
+/* Allocate + clear this rank's exchange buffer, return its IPC handle (these two calls allocate and synchronise). */
+int aae_peer_alloc(int64_t n_max, void** base_out, unsigned char* handle_out);
+int aae_peer_open(const unsigned char* handle, void** base_out);
+int aae_peer_close(void* base);
+int aae_peer_free(void* base);
+/* data[0..n) <- sum over ranks (in place); extra[0..n_extra) (doubles, n_extra <= 4, may be NULL) likewise.  Every rank
+ * must call with the same exchange id, n and n_max, in the same order.  A wait that exceeds ~2 s sets an error flag
+ * (aae_peer_error) instead of hanging. */
+int aae_peer_allreduce(aae_peers peers, int exchange, float* data, int n, double* extra, int n_extra, int64_t n_max,
+                       void* stream);
+int aae_peer_error(const void* base, int* err_host);
+
 /* Self-test of the tcgen05 operand views used by the tensor-core kernel (one GEMM, one CTA):
  * mode 1: D[128,32] = A[128,104].Bm[32,104]^T; mode 2: D[128,112] = A[128,32].Bm[32,112];
  * mode 3: D[128,32] = A[128,104]^T.Bm[128,32] (rows >= 104 undefined).  split = 3 (3xTF32) or 1. */

@@ -43,7 +43,7 @@ def _names(layers):
     return out
 
 
-def init_params(n_items, n_hidden=100, n_code=50, code_size=None, seed=42):
+def init_params(n_items, n_hidden=100, n_code=50, code_size=None, seed=42, adversarial=True):
     """Initial weights exactly as the reference builds them (aae.py:27, 782-792):
     ``torch.manual_seed(42)`` then Encoder(lin1, lin2, lin3) -> Decoder -> Discriminator,
     each ``nn.Linear`` with its stock init, on the CPU generator.  (``lin3`` of the
@@ -57,6 +57,8 @@ def init_params(n_items, n_hidden=100, n_code=50, code_size=None, seed=42):
         ("dec.lin1", code_size, n_hidden), ("dec.lin2", n_hidden, n_hidden), ("dec.lin3", n_hidden, n_items),
         ("disc.lin1", n_code, n_hidden), ("disc.lin2", n_hidden, n_hidden), ("disc.lin3", n_hidden, 1),
     ]
+    if not adversarial:     # AutoEncoder.fit builds Encoder and Decoder only (aae.py:368-387)
+        shapes = shapes[:6]
     params = {}
     for name, fin, fout in shapes:
         lin = torch.nn.Linear(fin, fout)
@@ -121,7 +123,7 @@ def draw_masks(shape, p, n):
     return [torch.empty(shape, dtype=torch.float32).bernoulli_(1 - p).div_(1 - p) for _ in range(n)]
 
 
-def draw_step_rng(B, n_hidden, n_code, dropout=(.2, .2), prior_scale=None):
+def draw_step_rng(B, n_hidden, n_code, dropout=(.2, .2), prior_scale=None, adversarial=True):
     """All random draws of one partial_fit in the reference's order:
     ae: enc.drop1, enc.drop2, dec.drop1, dec.drop2 | disc: randn[B,C], disc.drop1/2 on
     z_real, disc.drop1/2 on z_fake | gen: enc.drop1, enc.drop2, disc.drop1, disc.drop2."""
@@ -134,6 +136,8 @@ def draw_step_rng(B, n_hidden, n_code, dropout=(.2, .2), prior_scale=None):
     r = {}
     r["ae_enc"] = pair()
     r["ae_dec"] = pair()
+    if not adversarial:     # AutoEncoder.ae_step (aae.py:267-306): the four masks of the reconstruction phase only
+        return r
     z_real = torch.randn((B, n_code))  # aae.py:716, CPU generator
     if prior_scale is not None:
         z_real = z_real * prior_scale
@@ -304,6 +308,25 @@ class OracleAAE(object):
         _, cache = self._mlp3_fwd("dec", z, (None, None))
         h2 = cache[3]
         return _linear(h2, self.p["dec.lin3.weight"], self.p["dec.lin3.bias"]).numpy()
+
+
+class OracleAE(OracleAAE):
+    """Dense restatement of the plain AutoEncoder (aae.py:221-458): ``ae_step`` alone (aae.py:267-306 is the same
+    computation as AdversarialAutoEncoder.ae_step), enc_optim and dec_optim both at ``lr`` (aae.py:393-394)."""
+
+    def __init__(self, params, n_code=50, lr=0.001, normalize_inputs=True):
+        params = dict(params)
+        for name, shape in (("disc.lin1.weight", (1, n_code)), ("disc.lin1.bias", (1,)), ("disc.lin2.weight", (1, 1)),
+                            ("disc.lin2.bias", (1,)), ("disc.lin3.weight", (1, 1)), ("disc.lin3.bias", (1,))):
+            params.pop(name, None)
+        OracleAAE.__init__(self, params, n_code=n_code, gen_lr=lr, reg_lr=lr, normalize_inputs=normalize_inputs)
+        self.gen_optim = self.disc_optim = None
+
+    def partial_fit(self, X, cond=None, rng=None):
+        X = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+        if cond is not None:
+            cond = [torch.as_tensor(np.asarray(c), dtype=torch.float32) for c in cond]
+        return (self.ae_step(X, cond, rng),)
 
 
 def fit_epoch_order(n):

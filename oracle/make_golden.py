@@ -32,15 +32,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def _state(model):
     out = {}
-    for pre, mod in (("enc", model.enc), ("dec", model.dec), ("disc", model.disc)):
+    for pre, mod in (("enc", model.enc), ("dec", model.dec), ("disc", getattr(model, "disc", None))):
+        if mod is None:     # plain AutoEncoder: no discriminator
+            continue
         for k, v in mod.state_dict().items():
             out[pre + "." + k] = v.detach().cpu().numpy().copy()
     return out
 
 
 def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0, mean_len=6,
-             store_weights=True, k=10):
+             store_weights=True, k=10, adversarial=True):
     aae = ref.aae
+    cls = aae.AdversarialAutoEncoder if adversarial else aae.AutoEncoder
+    steps_per_fit = ("ae_step", "disc_step", "gen_step") if adversarial else ("ae_step",)
     X = synth_sets(n, V, mean_len, min_len=2, seed=data_seed)
     conditions = None
     cond_data = None
@@ -63,7 +67,7 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
         cond_data = [cond]
 
     losses = []
-    orig = {k_: getattr(aae.AdversarialAutoEncoder, k_) for k_ in ("ae_step", "disc_step", "gen_step")}
+    orig = {k_: getattr(cls, k_) for k_ in steps_per_fit}
 
     def wrap(fn_name):
         fn = orig[fn_name]
@@ -74,13 +78,13 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
             return val
         return inner
     for k_ in orig:
-        setattr(aae.AdversarialAutoEncoder, k_, wrap(k_))
+        setattr(cls, k_, wrap(k_))
     init = {}
     try:
         torch.manual_seed(42)     # aae.py:27 executes this at import; redo it per case
         np.random.seed(42)
-        model = aae.AdversarialAutoEncoder(n_hidden=H, n_code=C, batch_size=B, n_epochs=epochs,
-                                           dropout=dropout, conditions=conditions, verbose=False)
+        model = cls(n_hidden=H, n_code=C, batch_size=B, n_epochs=epochs, dropout=dropout, conditions=conditions,
+                    verbose=False)
         # capture the initial weights: replay the same construction order under the same seed
         from oracle.aae_oracle import init_params
         init = {k_: v.numpy().copy() for k_, v in init_params(V, H, C, C + cond_dim, seed=42).items()}
@@ -92,15 +96,15 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
             pred = model.predict(X[:40], condition_data=[cond[:40]] if cond_dim else None)
     finally:
         for k_, fn in orig.items():
-            setattr(aae.AdversarialAutoEncoder, k_, fn)
+            setattr(cls, k_, fn)
     Xd = X[:40].toarray()
     masked = ref.evaluation.remove_non_missing(pred, Xd, copy=True)
     topk = ref.evaluation.argtopk(masked, k)[1]
     out = dict(
         n=n, V=V, H=H, C=C, B=B, epochs=epochs, dropout=np.asarray(dropout, dtype=np.float64),
-        cond_dim=cond_dim, k=k,
+        cond_dim=cond_dim, k=k, adversarial=int(adversarial),
         indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32),
-        losses=np.asarray(losses, dtype=np.float64).reshape(-1, 3),
+        losses=np.asarray(losses, dtype=np.float64).reshape(-1, len(steps_per_fit)),
         pred=pred.astype(np.float32), masked=masked.astype(np.float32), topk=topk.astype(np.int64),
     )
     if cond_dim:
@@ -114,7 +118,7 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
         for k_, v in final.items():
             out["abssum/" + k_] = np.float64(np.abs(v.astype(np.float64)).sum())
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
-    print(name, "steps", len(losses) // 3, "first", out["losses"][0], "last", out["losses"][-1])
+    print(name, "steps", len(losses) // len(steps_per_fit), "first", out["losses"][0], "last", out["losses"][-1])
     return out
 
 
@@ -135,6 +139,13 @@ def ranking_case(ref):
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = load_reference()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""     # optional name prefix: regenerate a subset
+    global run_case
+    _run = run_case
+
+    def run_case(ref_, name, **kw):
+        if name.startswith(only):
+            return _run(ref_, name, **kw)
     run_case(ref, "aae_small_dropout", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2))
     run_case(ref, "aae_small_nodrop", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(0, 0))
     run_case(ref, "aae_small_cond", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2), cond_dim=7)
@@ -144,6 +155,10 @@ def main():
              mean_len=8, store_weights=False)
     run_case(ref, "aae_survey_dropout", n=300, V=1000, H=100, C=50, B=100, epochs=1, dropout=(.2, .2),
              mean_len=8, store_weights=False)
+    # plain AutoEncoder (aae.py:221-458; AAERecommender(adversarial=False)): reconstruction phase only
+    run_case(ref, "ae_small_dropout", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2), adversarial=False)
+    run_case(ref, "ae_h100_cond", n=96, V=520, H=100, C=50, B=32, epochs=2, dropout=(.2, .2), mean_len=8, cond_dim=7,
+             adversarial=False)
     ranking_case(ref)
 
 

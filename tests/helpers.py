@@ -9,6 +9,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 AAE_CASES = ["aae_small_dropout", "aae_small_nodrop", "aae_small_cond", "aae_h100_dropout",
              "aae_survey_nodrop", "aae_survey_dropout"]
+AE_CASES = ["ae_small_dropout", "ae_h100_cond"]      # the plain AutoEncoder (AAERecommender(adversarial=False))
 
 
 def load_case(name):
@@ -18,6 +19,7 @@ def load_case(name):
     g["dropout"] = tuple(float(x) for x in g["dropout"])
     for k in ("n", "V", "H", "C", "B", "epochs", "cond_dim", "k"):
         g[k] = int(g[k])
+    g["adversarial"] = bool(int(g.get("adversarial", 1)))
     return g
 
 
@@ -33,8 +35,9 @@ def oracle_replay(g, record_rng=False):
     cond = g.get("cond")
     torch.manual_seed(42)
     np.random.seed(42)
-    params = O.init_params(V, H, C, C + g["cond_dim"], seed=None)
-    model = O.OracleAAE(params, n_code=C)
+    adv = g["adversarial"]
+    params = O.init_params(V, H, C, C + g["cond_dim"], seed=None, adversarial=adv)
+    model = O.OracleAAE(params, n_code=C) if adv else O.OracleAE(params, n_code=C)
     X = g["X"]
     losses, rngs, batches = [], [], []
     for _ in range(g["epochs"]):
@@ -44,7 +47,7 @@ def oracle_replay(g, record_rng=False):
         for s in range(0, X.shape[0], B):
             xb = Xs[s:s + B]
             cb = [cs[s:s + B]] if cs is not None else None
-            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"])
+            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"], adversarial=adv)
             losses.append(model.partial_fit(xb.toarray(), cb, rng))
             if record_rng:
                 rngs.append(rng)

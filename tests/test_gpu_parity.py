@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import AAE_CASES, load_case, group, oracle_replay, rel_err
+from helpers import AAE_CASES, AE_CASES, load_case, group, oracle_replay, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -14,18 +14,21 @@ IMPLS = ["simt", "tc"]
 
 
 def _make_model(g, impl, **kw):
-    from aaerec_b200.aae import AdversarialAutoEncoder
+    from aaerec_b200.aae import AdversarialAutoEncoder, AutoEncoder
     from aaerec_b200.condition import ConditionList, PrecomputedEmbeddingCondition
     conditions = None
     if g["cond_dim"]:
         conditions = ConditionList([("title", PrecomputedEmbeddingCondition(g["cond_dim"]))])
+    if not g["adversarial"]:
+        return AutoEncoder(n_hidden=g["H"], n_code=g["C"], batch_size=g["B"], n_epochs=g["epochs"],
+                           dropout=g["dropout"], conditions=conditions, verbose=False, rng="oracle", impl=impl, **kw)
     return AdversarialAutoEncoder(n_hidden=g["H"], n_code=g["C"], batch_size=g["B"], n_epochs=g["epochs"],
                                   dropout=g["dropout"], conditions=conditions, verbose=False, rng="oracle",
                                   impl=impl, **kw)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("name", AAE_CASES)
+@pytest.mark.parametrize("name", AAE_CASES + AE_CASES)
 def test_fit_matches_reference_golden(name, impl, capsys):
     """Whole fit loop (shuffle, ragged last batch, three phases, four Adam states) against the
     reference's recorded losses and final weights."""
@@ -36,6 +39,9 @@ def test_fit_matches_reference_golden(name, impl, capsys):
     model.record_losses = True
     model.fit(g["X"], condition_data=[g["cond"]] if g["cond_dim"] else None)
     losses = np.asarray(model.loss_history)
+    if not g["adversarial"]:       # the plain AutoEncoder logs (R, 0, 0) (aae.py:341-342)
+        assert np.all(losses[:, 1:] == 0)
+        losses = losses[:, :1]
     assert losses.shape == g["losses"].shape
     np.testing.assert_allclose(losses, g["losses"], rtol=LOSS_RTOL, atol=0)
     sd = model.state_dict()

@@ -3,17 +3,18 @@
 import numpy as np
 import pytest
 
-from helpers import AAE_CASES, load_case, group, oracle_replay, rel_err, GOLDEN
+from helpers import AAE_CASES, AE_CASES, load_case, group, oracle_replay, rel_err, GOLDEN
 from oracle import aae_oracle as O
 
 
-@pytest.mark.parametrize("name", AAE_CASES)
+@pytest.mark.parametrize("name", AAE_CASES + AE_CASES)
 def test_partial_fit_matches_reference(name):
     g = load_case(name)
     model, losses, _, _ = oracle_replay(g)
     assert losses.shape == g["losses"].shape
     np.testing.assert_allclose(losses, g["losses"], rtol=2e-6, atol=1e-7)
     final = group(g, "final")
+    assert len(final) == (18 if g["adversarial"] else 12) or not final
     for k, ref in final.items():
         assert rel_err(model.p[k].numpy(), ref) < 2e-6, k
     for k, ref in group(g, "abssum").items():
