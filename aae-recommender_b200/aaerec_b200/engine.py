@@ -281,6 +281,35 @@ class AAEEngine(object):
         self._init_state()
         self.steps_done = 0
 
+    def init_uniform(self, seed=42):
+        """Random-init weights of the reference architecture directly in HBM (nn.Linear's law: U(-1/sqrt(fan_in),
+        1/sqrt(fan_in)) for weight and bias), without building the full [V,H] matrices on the host: the item-sharded
+        layers are drawn per shard, the replicated small layers identically on every rank.  For synthetic benchmarks
+        at vocabulary sizes where a host-side state dict is impractical (MPD shape, 2M items)."""
+        gs = torch.Generator(device=self.dev).manual_seed(int(seed))                      # same on every rank
+        gl = torch.Generator(device=self.dev).manual_seed(int(seed) * 1000003 + 17 + self.rank)
+
+        def fill(t, fan_in, g):
+            bound = 1.0 / float(np.sqrt(fan_in))
+            t.uniform_(-bound, bound, generator=g)
+        fill(self.W1t, self.V, gl)
+        fill(self.Wd3, self.H, gl)
+        fill(self.bd3, self.H, gl)
+        fan = {"enc.lin1.bias": self.V, "enc.lin2": self.H, "enc.lin3": self.H, "dec.lin1": self.Cp, "dec.lin2": self.H,
+               "disc.lin1": self.C, "disc.lin2": self.H, "disc.lin3": self.H}
+        for blk, sizes in ((self.enc, enc_block_sizes(self.H, self.C)), (self.dec, dec_block_sizes(self.H, self.Cp)),
+                           (self.disc, disc_block_sizes(self.H, self.C))):
+            off = 0
+            for name, sz in sizes:
+                key = name if name in fan else name.rsplit(".", 1)[0]
+                fill(blk[off:off + sz], fan[key], gs)
+                off += sz
+        for m in (self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2, self.Wd3_m, self.Wd3_v, self.bd3_m, self.bd3_v,
+                  self.enc_m1, self.enc_v1, self.enc_m2, self.enc_v2, self.dec_m, self.dec_v, self.disc_m, self.disc_v):
+            m.zero_()
+        self._init_state()
+        self.steps_done = 0
+
     def _gather_items(self, local):
         """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export / dense predict)."""
         return gather_item_shards(local[: self.Vloc], self.V, self.world, self.group)

@@ -796,6 +796,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
+#ifndef K3_PF_MV
+#define K3_PF_MV 1
+#endif
+#ifndef K3_PF_AHEAD
+#define K3_PF_AHEAD 4
+#endif
 // CWT = accumulator columns per epilogue thread (8: 16 epilogue warps, 16: 8 fatter warps with twice the
 // instruction-level parallelism and half the per-warp fixed work)
 template <int CWT> struct Tc2Cfg {
@@ -895,17 +901,30 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         mbar_arrive(&bar_stage);
       }
     };
-    // L2 prefetch of the W rows that the loader warps read two tiles ahead
+    // L2 prefetch, K3_PF_AHEAD tiles ahead: the W rows that the loader warps read, and (K3_PF_MV) the m/v rows and
+    // bias triplets that the single-buffered E2 stage is refilled from.  The stage copy is issued only once the
+    // previous tile has been read out of it, so without the prefetch its HBM latency + transfer is exposed every
+    // tile and each SM has bytes in flight only part of the time; with it the refill is an L2 hit and the HBM
+    // streams of the next tiles stay open all the time.
     auto prefetch_w = [&](int j) {
       if (j >= n_my) return;
       const int v0 = ((int)blockIdx.x + j * G) * TN;
       const int nv = min(TN, Vloc - v0);
-      prefetch_l2_bulk(Wd3 + (size_t)v0 * H, (uint32_t)nv * (uint32_t)H * 4u);
+      const uint32_t wbytes = (uint32_t)nv * (uint32_t)H * 4u;
+      if (j >= 2) prefetch_l2_bulk(Wd3 + (size_t)v0 * H, wbytes);
+#if K3_PF_MV
+      prefetch_l2_bulk(mW + (size_t)v0 * H, wbytes);
+      prefetch_l2_bulk(vW + (size_t)v0 * H, wbytes);
+      if (nv == TN) {
+        prefetch_l2_bulk(bd3 + v0, TN * 4u);
+        prefetch_l2_bulk(mb + v0, TN * 4u);
+        prefetch_l2_bulk(vb + v0, TN * 4u);
+      }
+#endif
     };
     if (elect_one()) {
       stage_copy(0);
-      prefetch_w(2);
-      prefetch_w(3);
+      for (int j = 1; j < K3_PF_AHEAD; ++j) prefetch_w(j);
     }
     __syncwarp();
     for (int it = 0; it <= n_my; ++it) {
@@ -921,7 +940,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
           issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2, it > 1 ? 1u : 0u);
         }
         mma_commit(&bar_g23);
-        prefetch_w(it + 4);
+        prefetch_w(it + K3_PF_AHEAD);
       }
       __syncwarp();
       if (it >= 2) {

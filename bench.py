@@ -157,12 +157,109 @@ def time_kernel(fn, iters, stream):
     return [a.elapsed_time(b) * 1e-3 for a, b in evs]
 
 
+def _uniform_params(V, seed=42):
+    """random-init weights of the reference architecture (same init law as nn.Linear), torch layout, host"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        bound = 1.0 / np.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return {"enc.lin1.weight": uni((H, V), V), "enc.lin1.bias": uni((H,), V),
+            "enc.lin2.weight": uni((H, H), H), "enc.lin2.bias": uni((H,), H),
+            "enc.lin3.weight": uni((C, H), H), "enc.lin3.bias": uni((C,), H),
+            "dec.lin1.weight": uni((H, C), C), "dec.lin1.bias": uni((H,), C),
+            "dec.lin2.weight": uni((H, H), H), "dec.lin2.bias": uni((H,), H),
+            "dec.lin3.weight": uni((V, H), H), "dec.lin3.bias": uni((V,), H),
+            "disc.lin1.weight": uni((H, C), C), "disc.lin1.bias": uni((H,), C),
+            "disc.lin2.weight": uni((H, H), H), "disc.lin2.bias": uni((H,), H),
+            "disc.lin3.weight": uni((1, H), H), "disc.lin3.bias": uni((1,), H)}
+
+
+def train_leg(eng, dev_batches, B, K, W, barrier, stream):
+    """K partial_fit steps on batches already resident in HBM, after W warm-up steps; device seconds."""
+    import torch
+    n = len(dev_batches)
+    for i in range(W):
+        eng.set_batch_device(*dev_batches[i % n])
+        eng.train_step(B)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        eng.set_batch_device(*dev_batches[(W + i) % n])
+        eng.train_step(B)
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def e2e_leg(eng, batches, B, K, W, barrier, stream):
+    """The same steps through the host-buffer entry: pinned CSR batch H2D + the three losses D2H every step, inside
+    the timed region; the host consumes the losses every 4th step (the reference's .item() forces that every step,
+    a 4-deep pinned ring keeps the copy engine busy instead)."""
+    import torch
+    n = len(batches)
+    loss_pin = torch.zeros(4, 3, dtype=torch.float32).pin_memory()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = 0
+    t0.record(stream)
+    for i in range(K):
+        ip, ii, _ = batches[(W + i) % n]
+        eng.upload_csr(ip, ii)
+        eng.train_step(B)
+        loss_pin[i % 4].copy_(eng.losses, non_blocking=True)
+        h2d += ip.nbytes + ii.nbytes
+        if i % 4 == 3:
+            stream.synchronize()
+    t1.record(stream)
+    barrier()
+    return t0.elapsed_time(t1) * 1e-3, h2d // max(K, 1)
+
+
+def predict_leg(eng, Xq, k, iters, barrier, stream, tf_peak):
+    """top-k predict (reconstruction + known-item mask + top-k, aae.py:840-870 + evaluation.py:183-199, 20-58) of
+    one query batch: device-resident and end-to-end (host CSR in, [B,k] item ids out)."""
+    import torch
+    Bq = Xq.shape[0]
+    ip = Xq.indptr.astype(np.int32)
+    ii = Xq.indices.astype(np.int32)
+    eng.upload_csr(ip, ii)
+    scratch = torch.empty(Bq, eng.Vloc, dtype=torch.float32, device=eng.dev)
+    for _ in range(2):
+        eng.topk(Bq, k, scratch=scratch)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        eng.topk(Bq, k, scratch=scratch)
+    e1.record(stream)
+    barrier()
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    out_pin = torch.zeros(Bq, min(k, eng.V), dtype=torch.int32).pin_memory()
+    barrier()
+    e0.record(stream)
+    for _ in range(iters):
+        eng.upload_csr(ip, ii)
+        idx, _ = eng.topk(Bq, k, scratch=scratch)
+        out_pin.copy_(idx, non_blocking=True)
+        stream.synchronize()
+    e1.record(stream)
+    barrier()
+    sec_e2e = e0.elapsed_time(e1) * 1e-3 / iters
+    return {"sec": sec, "sec_e2e": sec_e2e, "Bq": Bq, "h2d": ip.nbytes + ii.nbytes, "d2h": out_pin.numel() * 4,
+            "tflops": 2.0 * Bq * eng.Vloc * H / sec / 1e12, "tf_peak": tf_peak}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from aaerec_b200 import _native as N
     from aaerec_b200.engine import AAEEngine
     from aaerec_b200._native import call, ptr
+    from aaerec_b200.synth import synth_sets
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,22 +272,10 @@ def run_ours(args):
     _, batches, V, B = make_batches(args.workload, n_batches)
     eng = AAEEngine(V, H, C, rank=rank, world=world, impl=args.kernel, seed=1, max_batch=B,
                     max_nnz=max(len(b[1]) for b in batches) + 8, use_graph=not args.no_graph)
-    # random-init weights of the reference architecture (same init law as nn.Linear)
-    g = torch.Generator().manual_seed(42)
-
-    def uni(shape, fan_in):
-        bound = 1.0 / np.sqrt(fan_in)
-        return (torch.rand(shape, generator=g) * 2 - 1) * bound
-    params = {"enc.lin1.weight": uni((H, V), V), "enc.lin1.bias": uni((H,), V),
-              "enc.lin2.weight": uni((H, H), H), "enc.lin2.bias": uni((H,), H),
-              "enc.lin3.weight": uni((C, H), H), "enc.lin3.bias": uni((C,), H),
-              "dec.lin1.weight": uni((H, C), C), "dec.lin1.bias": uni((H,), C),
-              "dec.lin2.weight": uni((H, H), H), "dec.lin2.bias": uni((H,), H),
-              "dec.lin3.weight": uni((V, H), H), "dec.lin3.bias": uni((V,), H),
-              "disc.lin1.weight": uni((H, C), C), "disc.lin1.bias": uni((H,), C),
-              "disc.lin2.weight": uni((H, H), H), "disc.lin2.bias": uni((H,), H),
-              "disc.lin3.weight": uni((1, H), H), "disc.lin3.bias": uni((1,), H)}
-    eng.load_params(params)
+    if V <= 500000:
+        eng.load_params(_uniform_params(V))
+    else:
+        eng.init_uniform(42)
     dev_batches = [(torch.as_tensor(ip, device=eng.dev), torch.as_tensor(ii, device=eng.dev)) for ip, ii, _ in batches]
     stream = torch.cuda.current_stream()
 
@@ -199,7 +284,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: batches resident in HBM ----------------
+    def max_over_ranks(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, device=torch.device("cuda", local), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    # ---------------- value: batches resident in HBM; e2e: host CSR buffers in, losses out ----------------
     for i in range(W):
         eng.set_batch_device(*dev_batches[i % n_batches])
         eng.train_step(B)
@@ -208,39 +300,13 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(K):
-        eng.set_batch_device(*dev_batches[(W + i) % n_batches])
-        eng.train_step(B)
-    e1.record(stream)
-    barrier()
-    sec = e0.elapsed_time(e1) * 1e-3
+    sec = train_leg(eng, dev_batches, B, K, 0, barrier, stream)
     launches = eng.launches_per_step() * K
-    # ---------------- e2e: host CSR buffers in, losses out, every step ----------------
-    loss_pin = torch.zeros(4, 3, dtype=torch.float32).pin_memory()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    h2d = 0
-    t0.record(stream)
-    for i in range(K):
-        ip, ii, _ = batches[(W + i) % n_batches]
-        eng.upload_csr(ip, ii)
-        eng.train_step(B)
-        loss_pin[i % 4].copy_(eng.losses, non_blocking=True)
-        h2d += ip.nbytes + ii.nbytes
-        if i % 4 == 3:
-            stream.synchronize()       # the host consumes the losses (as the reference's .item() does)
-    t1.record(stream)
-    barrier()
-    sec_e2e = t0.elapsed_time(t1) * 1e-3
+    sec_e2e, h2d = e2e_leg(eng, batches, B, K, W, barrier, stream)
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([sec, sec_e2e], device=eng.dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec, sec_e2e = t.tolist()
+    sec, sec_e2e = max_over_ranks(sec, sec_e2e)
+    if eng.peer is not None and eng.peer.error():
+        raise RuntimeError("peer exchange timed out (ranks diverged)")
     if args.kernel_times and world == 1:
         # eager (non-graph) pass with CUDA events around every entry point: warm per-kernel times
         eng2_graph = eng.use_graph
@@ -292,6 +358,57 @@ def run_ours(args):
                                 "frac": v["bytes"] / v["sec"] / 1e9 / hbm_peak} for k, v in kern.items()},
                 "step_algorithmic_bytes": 64.0 * Vl * H,
                 "step_frac": 64.0 * Vl * H / (sec / K) / 1e9 / hbm_peak}
+    # ---------------- predict: reconstruction + masked top-100 of a query batch (the metric's second half) ----------
+    extra = {}
+    if not args.no_extra:
+        Bq = args.predict_batch
+        Xq = synth_sets(Bq, V, WORKLOADS[args.workload][1], WORKLOADS[args.workload][2], WORKLOADS[args.workload][3],
+                        seed=1234)
+        pr = predict_leg(eng, Xq, 100, 10, barrier, stream, tf_peak)
+        ps, pe = max_over_ranks(pr["sec"], pr["sec_e2e"])
+        extra["predict"] = {
+            "metric": "top-100 predict sets/sec", "value": Bq / ps, "unit": "sets/s", "ms_per_batch": ps * 1e3,
+            "e2e": {"value": Bq / pe, "unit": "sets/s", "h2d_bytes_per_step": pr["h2d"], "d2h_bytes_per_step": pr["d2h"]},
+            "config": {"workload": "%s-shaped: V=%d items, query batch %d sets, k=100, known items masked"
+                                   % (args.workload, V, Bq)},
+            "roofline": {"bound": "tensor", "achieved": 2.0 * Bq * V * H / ps / 1e12, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": 2.0 * Bq * V * H / ps / 1e12 / tf_peak,
+                         "note": "algorithmic 2*B*V*H flops of the decoder output layer; peak = measured dense bf16 "
+                                 "(sustained); the kernel runs fp32-accurate 3xTF32 (3 MMAs per product at half the "
+                                 "bf16 rate), and the scores still round-trip HBM once before the top-k"}}
+    # ---------------- MPD-shaped secondary workload (BASELINE configs[3]): V = 2M items, item-sharded ----------------
+    if not args.no_extra and args.workload == "pubmed":
+        torch.cuda.empty_cache()
+        Vm, _, _, _, _, Bm = WORKLOADS["mpd"]
+        Km = max(10, min(K, 50))
+        _, mb, _, _ = make_batches("mpd", min(Km + 3, 16))
+        engm = AAEEngine(Vm, H, C, rank=rank, world=world, impl=args.kernel, seed=1, max_batch=Bm,
+                         max_nnz=max(len(b[1]) for b in mb) + 8, use_graph=not args.no_graph)
+        engm.init_uniform(42)
+        mdev = [(torch.as_tensor(ip, device=engm.dev), torch.as_tensor(ii, device=engm.dev)) for ip, ii, _ in mb]
+        secm = train_leg(engm, mdev, Bm, Km, 3, barrier, stream)
+        secm_e2e, h2dm = e2e_leg(engm, mb, Bm, Km, 3, barrier, stream)
+        secm, secm_e2e = max_over_ranks(secm, secm_e2e)
+        extra["mpd"] = {
+            "metric": "AAE train item-sets/sec", "value": Bm * Km / secm, "unit": "sets/s", "steps": Km,
+            "ms_per_step": secm / Km * 1e3,
+            "e2e": {"value": Bm * Km / secm_e2e, "unit": "sets/s", "h2d_bytes_per_step": h2dm, "d2h_bytes_per_step": 12},
+            "config": {"workload": "mpd-shaped (BASELINE configs[3]): V=%d items, batch %d sets, item-sharded x%d"
+                                   % (Vm, Bm, world)},
+            "step_algorithmic_bytes_per_gpu": 64.0 * engm.Vloc * H,
+            "step_frac": 64.0 * engm.Vloc * H / (secm / Km) / 1e9 / hbm_peak}
+        Xq = synth_sets(args.predict_batch, Vm, 25, 1, 100, seed=4321)
+        pr = predict_leg(engm, Xq, 100, 5, barrier, stream, tf_peak)
+        ps, pe = max_over_ranks(pr["sec"], pr["sec_e2e"])
+        extra["mpd_predict"] = {
+            "metric": "top-100 predict sets/sec", "value": args.predict_batch / ps, "unit": "sets/s",
+            "ms_per_batch": ps * 1e3, "e2e": {"value": args.predict_batch / pe, "unit": "sets/s",
+                                               "h2d_bytes_per_step": pr["h2d"], "d2h_bytes_per_step": pr["d2h"]},
+            "config": {"workload": "mpd-shaped (BASELINE configs[4]): V=%d items, query batch %d sets, k=100, "
+                                   "item-sharded x%d" % (Vm, args.predict_batch, world)},
+            "tensor_frac": 2.0 * args.predict_batch * Vm * H / ps / 1e12 / tf_peak / world}
+    exchange = eng._exchange_kind
+    graph = eng.use_graph
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,18 +426,22 @@ def run_ours(args):
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s-shaped (BASELINE configs[1]): V=%d items, batch %d sets (mean %.0f items/set), "
                                "n_hidden %d, n_code %d, dropout (.2,.2) in-kernel Philox, dense-Adam-equivalent W1 "
-                               "policy; one partial_fit (ae+disc+gen) per step" % (args.workload, V, B, nnz_mean / B, H, C),
-                   "parallelism": "item-sharded x%d" % world if world > 1 else "single GPU",
-                   "decoder_kernel": {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[eng.impl_for(B)],
-                   "cuda_graph": eng.use_graph,
+                               "policy (time-blocked, exact); one partial_fit (ae+disc+gen) per step"
+                               % (args.workload, V, B, nnz_mean / B, H, C),
+                   "parallelism": ("item-sharded x%d (Wd3/bd3/W1t by item range; exchange: %s)" % (world, exchange))
+                   if world > 1 else "single GPU",
+                   "decoder_kernel": {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[
+                       1 if (args.kernel == "auto") else {"simt": 0, "tc": 1, "tf32": 2}.get(args.kernel, 1)],
+                   "cuda_graph": graph,
                    "l2": "per-step working set %.2f GB >> 126 MB L2 (no flush needed)" % (64.0 * Vl * H / 1e9)},
-        "e2e": {"value": B * K / sec_e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 12,
+        "e2e": {"value": B * K / sec_e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                 "ms_per_step": sec_e2e / K * 1e3},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
+    line.update(extra)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -337,6 +458,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--kernel-times", action="store_true", help="print warm per-kernel device times to stderr")
+    ap.add_argument("--no-extra", action="store_true", help="skip the predict and MPD-shaped secondary measurements")
+    ap.add_argument("--predict-batch", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -106,3 +106,30 @@ def test_synth_sets_are_binary_sorted_unique():
         row = X.indices[X.indptr[r]:X.indptr[r + 1]]
         assert np.all(np.diff(row) > 0)
     assert (np.diff(X.indptr) >= 1).all()
+
+
+def test_plain_autoencoder_api_surface():
+    # aae.py:221-247 constructor (lr instead of gen_lr/reg_lr), :321-322 ValueError on y, AAERecommender(adversarial=False)
+    from aaerec_b200.aae import AutoEncoder, AAERecommender
+    m = AutoEncoder(n_hidden=7, lr=0.01, verbose=False)
+    assert (m.n_hidden, m.n_code, m.lr, m.batch_size, m.n_epochs) == (7, 50, 0.01, 100, 500)
+    assert m.gen_lr == 0.01 and m.reg_lr == 0.0 and not m.adversarial and m.disc is None
+    X = sp.csr_matrix(np.eye(3, dtype=np.float32))
+    with pytest.raises(ValueError):
+        m.partial_fit(X, y=np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        m.fit(X, y=np.zeros(3))
+    r = AAERecommender(adversarial=False, lr=0.01, verbose=False)
+    assert str(r).startswith("Autoencoder") and not r.adversarial
+
+
+def test_peer_exchange_buffer_layout():
+    # the exchange buffer holds a header (flags of 4 exchanges x 32 blocks x 8 ranks, counters) and 2 slots per
+    # exchange, each n_max floats + 4 doubles, 256-byte aligned
+    from aaerec_b200 import _native as N
+    lib = N.load()
+    n = 12800
+    slot = (n * 4 + 32 + 255) // 256 * 256
+    header = (4 * 32 * 8 * 4 + 4 * 4 + 4 * 4 + 32 + 255) // 256 * 256
+    assert lib.aae_peer_buffer_bytes(n) == header + 8 * slot
+    assert lib.aae_peer_buffer_bytes(0) == 0
