@@ -126,6 +126,9 @@ class AAEEngine(object):
         self.ktab = torch.zeros(64 * 4, **f32)
         self._w1_dirty = False
         self.loss_sums = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self._topk_work = None
+        self._n_bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.topk_fallbacks = 0
         self.losses = torch.zeros(3, **f32)
         self._ws_B = 0
         self._ws_nnz = 0
@@ -615,18 +618,37 @@ class AAEEngine(object):
              1 if apply_sigmoid else 0, ptr(out), out.stride(0), self.impl_for_scores(), self._stream())
         return out
 
-    def topk(self, B, k, scratch=None, mask_known=True):
+    def topk(self, B, k, scratch=None, mask_known=True, fused=None):
         """Masked top-k of the batch in the device buffers: returns (idx int32 [B,k] global item ids,
-        val float32 [B,k] logits), descending.  Item-sharded: local top-k + all-gather + merge."""
-        if scratch is None or scratch.shape[0] < B or scratch.shape[1] < self.Vloc:
-            scratch = torch.empty(B, self.Vloc, dtype=torch.float32, device=self.dev)
-        self.scores(B, scratch, apply_sigmoid=False)
+        val float32 [B,k] logits), descending.  Item-sharded: local top-k + all-gather + merge.
+
+        Large shards take the fused path (``aae_predict_topk``: candidates selected in the GEMM epilogue, no
+        [B, Vloc] score matrix); its per-batch status word is read back (one 4-byte synchronising copy) and a
+        batch it could not rank exactly is redone through the dense path.  ``fused=False`` forces the dense path."""
         kl = min(k, self.Vloc)
         idx = torch.empty(B, kl, dtype=torch.int32, device=self.dev)
         val = torch.empty(B, kl, dtype=torch.float32, device=self.dev)
-        call("aae_masked_topk", ptr(scratch), scratch.stride(0), B, self.Vloc, self.v_begin,
-             ptr(self.indptr) if mask_known else None, ptr(self.indices) if mask_known else None, kl, ptr(idx),
-             ptr(val), None, self._stream())
+        impl = self.impl_for_scores()
+        need = 0
+        if fused is not False and impl in (1, 2) and os.environ.get("AAE_B200_TOPK", "") != "dense":
+            need = int(N.load().aae_predict_topk_work_bytes(B, self.Vloc, kl))
+        done = False
+        if need > 0:
+            if self._topk_work is None or self._topk_work.numel() < need:
+                self._topk_work = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            self.predict_h2(B)
+            call("aae_predict_topk", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), self.Vloc, self.v_begin,
+                 ptr(self.indptr) if mask_known else None, ptr(self.indices) if mask_known else None, kl, impl,
+                 ptr(self._topk_work), need, ptr(idx), ptr(val), ptr(self._n_bad), self._stream())
+            done = int(self._n_bad.item()) == 0
+            self.topk_fallbacks += 0 if done else 1
+        if not done:
+            if scratch is None or scratch.shape[0] < B or scratch.shape[1] < self.Vloc:
+                scratch = torch.empty(B, self.Vloc, dtype=torch.float32, device=self.dev)
+            self.scores(B, scratch, apply_sigmoid=False)
+            call("aae_masked_topk", ptr(scratch), scratch.stride(0), B, self.Vloc, self.v_begin,
+                 ptr(self.indptr) if mask_known else None, ptr(self.indices) if mask_known else None, kl, ptr(idx),
+                 ptr(val), None, self._stream())
         if self.world == 1:
             return idx, val
         kmax = min(k, (self.V + self.world - 1) // self.world)

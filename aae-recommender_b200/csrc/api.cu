@@ -110,6 +110,8 @@ int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const fl
   if (impl == 0) return dec_out_scores_simt(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo, as_stream(stream));
   if (impl == 1 || impl == 2)
     return dec_out_scores_tc(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo, impl == 1 ? 3 : 1, as_stream(stream));
+  if (impl == 3 || impl == 4)   // the first-cut, unpipelined tensor-core kernel (A/B reference)
+    return dec_out_scores_tc(h2, B, H, Wd3, bd3, Vloc, apply_sigmoid, out, ldo, impl == 3 ? 13 : 11, as_stream(stream));
   set_error("dec_out_scores: unknown impl %d", impl);
   return AAE_E_ARG;
 }

@@ -1423,6 +1423,197 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K5: pipelined scores kernel with a selection epilogue (predict + ranking without the [B,V] round trip).
+//
+// One CTA = one chunk of 128 query rows (Hb resident in shared memory) x a strided subset of 64-item tiles.
+// Warp 16 issues the MMAs; warps 0-15 are loaders (W' tile -> tf32 hi/lo operand, two shared-memory stages) and
+// epilogue (two TMEM accumulator buffers): while tile i is drained and tile i+2 is staged, the tensor pipe runs
+// tile i+1.  Per stage s one mbarrier pair: ready[s] (one arrival per loader warp: stage filled AND accumulator s
+// drained) and mma[s] (tcgen05.commit: logits of the tile in TMEM, stage s free again).
+// Epilogues: DENSE (scores, optionally sigmoid, to out[b, col]; col = item, or the visit order for the threshold
+// sample) and FILTER (z > tau[b]: append (z, item) to the row's candidate list; ~0.05 % of the elements).
+// Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
+// (evaluation.py:183-199, 20-58).
+// ---------------------------------------------------------------------------------------------
+constexpr int PN = 64;                 // items per tile
+constexpr int P_NWE = 16;              // loader / epilogue warps
+constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
+constexpr int P_CW = PN / 4;           // accumulator columns per epilogue thread (4 warps per TMEM lane quarter)
+constexpr int P_WCH = 4;               // 16-byte W' chunks per loader thread (64 rows x Kp/4 <= 32 column groups)
+
+struct SelArgs {
+  const float* h2; int B, H;
+  const float* Wd3; const float* bd3; int Vloc, v_begin;
+  int tile_stride, n_sel;              // tiles visited: j * tile_stride, j < n_sel
+  int filter;                          // 0: dense scores, 1: threshold filter
+  float* out; long long ldo; int out_by_visit, apply_sigmoid;
+  const float* tau; int tau_stride; int32_t* cnt; float* cand_val; int32_t* cand_idx; int cap;
+};
+
+__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int cgb, int ncg) {
+  const bool rv = v0 + row < a.Vloc;
+#pragma unroll
+  for (int j = 0; j < P_WCH; ++j) {
+    const int cg = cgb + 8 * j, c = cg * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rv && cg < ncg) {
+      if (c + 3 < a.H) x = __ldg(reinterpret_cast<const float4*>(a.Wd3 + (size_t)(v0 + row) * a.H + c));
+      else if (c == a.H) x.x = __ldg(a.bd3 + v0 + row);
+    }
+    wr[j] = x;
+  }
+}
+__device__ __forceinline__ void p_store_w(const float4* wr, unsigned char* hi, unsigned char* lo, uint32_t sbo, int row,
+                                          int cgb, int ncg, bool with_lo) {
+#pragma unroll
+  for (int j = 0; j < P_WCH; ++j) {
+    const int cg = cgb + 8 * j;
+    if (cg < ncg) store_split4(hi, lo, row, cg, sbo, wr[j], with_lo);
+  }
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_mma[2], bar_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  constexpr bool with_lo = (SPLIT == 3);
+  const Geom g = make_geom(a.H);
+  const uint32_t wb_bytes = (PN / 8) * g.wb_sbo;
+  unsigned char* hb_hi = smem;
+  unsigned char* hb_lo = hb_hi + g.hb_bytes;
+  unsigned char* wst = hb_lo + g.hb_bytes;         // stage s: hi at wst + 2*s*wb_bytes, lo right after
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncg = g.Kp / 4;
+  const int n_chunks = (a.B + BM - 1) / BM;
+  const int n_my = ((int)blockIdx.x < a.n_sel) ? (a.n_sel - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (warp == P_NWE) tmem_alloc(&tmem_base_s, 2 * PN);
+  if (tid == 0) {
+    mbar_init(&bar_mma[0], 1);
+    mbar_init(&bar_mma[1], 1);
+    mbar_init(&bar_ready[0], P_NWE);
+    mbar_init(&bar_ready[1], P_NWE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = make_idesc(BM, PN, 0, 0);
+  uint32_t ph0 = 0, ph1 = 0;                       // parity of the barrier this role waits on, per stage
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int b0 = chunk * BM, nb = min(BM, a.B - b0);
+    __syncthreads();                               // the previous chunk is drained: Hb may be rebuilt
+    fill_hb(hb_hi, hb_lo, g, a.h2, b0, nb, with_lo, P_NT);
+    fence_async_smem();
+    __syncthreads();
+    if (warp == P_NWE) {
+      // ================= MMA issuer =================
+      const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
+      const SmemOp op_w0 = make_op(wst, wst + wb_bytes, CORE, g.wb_sbo, 2 * CORE);
+      const SmemOp op_w1 = make_op(wst + 2 * wb_bytes, wst + 3 * wb_bytes, CORE, g.wb_sbo, 2 * CORE);
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it & 1;
+        mbar_wait(&bar_ready[s], s ? ph1 : ph0);
+        if (s) ph1 ^= 1; else ph0 ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+          issue_gemm<SPLIT>(tmem + (uint32_t)(s * PN), op_hb, s ? op_w1 : op_w0, g.Kp / 8, idesc, 0u);
+          mma_commit(&bar_mma[s]);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ================= loaders + epilogue =================
+      const int q4 = warp & 3, cpart = warp >> 2;
+      const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+      const int brow = q4 * 32 + lane;
+      const int lrow = (warp & 1) * 32 + lane, cgb = warp >> 1;      // loader mapping: item row, first column group
+      const bool rowv = brow < nb;
+      float tau = __int_as_float(0x7f800000);
+      if (a.filter && rowv) tau = a.tau[(size_t)(b0 + brow) * a.tau_stride];
+      auto tile_v0 = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) * a.tile_stride) * PN; };
+      float4 wr[P_WCH];
+      for (int p = 0; p < 2 && p < n_my; ++p) {
+        p_load_w(wr, a, tile_v0(p), lrow, cgb, ncg);
+        p_store_w(wr, wst + 2 * p * wb_bytes, wst + (2 * p + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ready[p]);
+      }
+      if (n_my > 2) p_load_w(wr, a, tile_v0(2), lrow, cgb, ncg);
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        mbar_wait(&bar_mma[s], s ? ph1 : ph0);
+        if (s) ph1 ^= 1; else ph0 ^= 1;
+        tc_fence_after();
+        uint32_t zr[P_CW];
+        TmemIO<P_CW>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW), zr);
+        TmemIO<P_CW>::ld_wait(zr);
+        tc_fence_before();
+        if (i + 2 < n_my) {
+          p_store_w(wr, wst + 2 * s * wb_bytes, wst + (2 * s + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_ready[s]);
+          if (i + 3 < n_my) p_load_w(wr, a, tile_v0(i + 3), lrow, cgb, ncg);
+        }
+        // ---- epilogue of tile i
+        const int v0 = tile_v0(i);
+        const int vm = a.Vloc - v0 - cpart * P_CW;               // valid columns among this thread's 16
+        if (a.filter) {
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < P_CW; ++j) any |= (__uint_as_float(zr[j]) > tau);
+          if (any) {
+            const size_t rb = (size_t)(b0 + brow);
+#pragma unroll
+            for (int j = 0; j < P_CW; ++j) {
+              const float z = __uint_as_float(zr[j]);
+              if (z > tau && j < vm) {
+                const int slot = atomicAdd(a.cnt + rb, 1);
+                if (slot < a.cap) {
+                  a.cand_val[rb * a.cap + slot] = z;
+                  a.cand_idx[rb * a.cap + slot] = a.v_begin + v0 + cpart * P_CW + j;
+                }
+              }
+            }
+          }
+        } else if (rowv) {
+          const int colbase = a.out_by_visit ? ((int)blockIdx.x + i * (int)gridDim.x) * PN : v0;
+          float* orow = a.out + (size_t)(b0 + brow) * a.ldo + colbase + cpart * P_CW;
+          if (vm >= P_CW && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < P_CW; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(zr[j]); o.y = __uint_as_float(zr[j + 1]);
+              o.z = __uint_as_float(zr[j + 2]); o.w = __uint_as_float(zr[j + 3]);
+              if (a.apply_sigmoid) {
+                o.x = 1.0f / (1.0f + expf(-o.x)); o.y = 1.0f / (1.0f + expf(-o.y));
+                o.z = 1.0f / (1.0f + expf(-o.z)); o.w = 1.0f / (1.0f + expf(-o.w));
+              }
+              __stcs(reinterpret_cast<float4*>(orow + j), o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < P_CW; ++j) {
+              if (j < vm) {
+                float sc = __uint_as_float(zr[j]);
+                if (a.apply_sigmoid) sc = 1.0f / (1.0f + expf(-sc));
+                orow[j] = sc;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == P_NWE) tmem_dealloc(tmem, 2 * PN);
+}
+
 }  // namespace tc
 
 static bool tc_supported(int B, int H, const char* what) {
@@ -1495,9 +1686,39 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
   return check_launch("dec_out_train(tc)");
 }
 
+// K5 launcher: dense scores (filter == 0) or threshold filter (filter == 1) over the tiles j * tile_stride, j < n_sel.
+int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
+                      int tile_stride, int n_sel, int filter, float* out, int64_t ldo, int out_by_visit,
+                      int apply_sigmoid, const float* tau, int tau_stride, int32_t* cnt, float* cand_val,
+                      int32_t* cand_idx, int cap, int split, cudaStream_t s) {
+  if (!tc_supported(B, H, "dec_out_select")) return AAE_E_UNSUPPORTED;
+  tc::Geom g = tc::make_geom(H);
+  const size_t smem = 2 * (size_t)g.hb_bytes + 4 * (size_t)(tc::PN / 8) * g.wb_sbo + 256;
+  auto kern = (split == 3) ? tc::dec_out_select_kernel<3> : tc::dec_out_select_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("dec_out_select: smem %zu: %s", smem, cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  tc::SelArgs a;
+  a.h2 = h2; a.B = B; a.H = H; a.Wd3 = Wd3; a.bd3 = bd3; a.Vloc = Vloc; a.v_begin = v_begin;
+  a.tile_stride = tile_stride; a.n_sel = n_sel; a.filter = filter;
+  a.out = out; a.ldo = ldo; a.out_by_visit = out_by_visit; a.apply_sigmoid = apply_sigmoid;
+  a.tau = tau; a.tau_stride = tau_stride; a.cnt = cnt; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cap = cap;
+  const int n_chunks = (B + tc::BM - 1) / tc::BM;
+  const int gy = std::min(n_chunks, sm_count());
+  const int gx = std::max(1, std::min(n_sel, sm_count() / gy));
+  kern<<<dim3(gx, gy), tc::P_NT, smem, s>>>(a);
+  return check_launch("dec_out_select");
+}
+
 int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
                       float* out, int64_t ldo, int split, cudaStream_t s) {
   if (!tc_supported(B, H, "dec_out_scores")) return AAE_E_UNSUPPORTED;
+  if (split < 10)
+    return dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, 0, 1, (Vloc + tc::PN - 1) / tc::PN, 0, out, ldo, 0, apply_sigmoid,
+                             nullptr, 0, nullptr, nullptr, nullptr, 0, split, s);
+  split -= 10;
   tc::Geom g = tc::make_geom(H);
   size_t smem = 2 * ((size_t)g.hb_bytes + g.wb_bytes) + 256;
   auto kern = (split == 3) ? tc::dec_out_scores_tc_kernel<3> : tc::dec_out_scores_tc_kernel<1>;

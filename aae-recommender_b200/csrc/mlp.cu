@@ -168,7 +168,9 @@ __device__ __forceinline__ void layer_fwd(Stager& sg, int layer, const float* xs
   }
 }
 // dx[r][i] = sum_o dy[r][o] * W[o][i] for layer `layer`: thread (i, part) walks the chunk's rows o == part
-// (mod parts), partial sums meet in shared memory (atomicAdd; dxs is zeroed first).  Ends with a barrier.
+// (mod parts); the partial sums meet in shared memory in a FIXED order (chunk by chunk, part by part), so the
+// result is bit-reproducible -- the item shards of a multi-GPU run compute the replicated small layers redundantly
+// and must not drift apart.  dxs is zeroed first.  Ends with a barrier.
 template <int R>
 __device__ __forceinline__ void layer_bwd(Stager& sg, int layer, const float* dys, int ldy, float* dxs, int ldx) {
   const int I = sg.L[layer].I;
@@ -179,9 +181,12 @@ __device__ __forceinline__ void layer_bwd(Stager& sg, int layer, const float* dy
   while (sg.cl == layer) {
     const Chunk c = sg.acquire();          // barrier inside: the zeroing above is visible
     const int nrows = c.r1 - c.r0;
+    // parts > 1 implies lanes >= I: at most one i per thread, its partial sums stay in registers until its turn
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
     if (part < parts) {
       for (int i = il; i < I; i += lanes) {
-        float acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.f;
         int o = part;
@@ -202,11 +207,23 @@ __device__ __forceinline__ void layer_bwd(Stager& sg, int layer, const float* dy
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[r] = fmaf(w0, dys[r * ldy + c.r0 + o], acc[r]);
         }
+        if (parts == 1) {                  // single owner of column i: plain accumulation
 #pragma unroll
-        for (int r = 0; r < R; ++r) atomicAdd(&dxs[r * ldx + i], acc[r]);
+          for (int r = 0; r < R; ++r) dxs[r * ldx + i] += acc[r];
+        }
       }
     }
-    __syncthreads();
+    if (parts > 1) {
+      for (int p = 0; p < parts; ++p) {
+        if (part == p && il < I) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) dxs[r * ldx + il] += acc[r];
+        }
+        __syncthreads();
+      }
+    } else {
+      __syncthreads();
+    }
   }
 }
 

@@ -12,6 +12,7 @@
 // a lower / higher sample rank; pathological rows (huge tie groups) fall back to an exact
 // bit-by-bit radix bisection.
 #include <float.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace aae {
@@ -119,9 +120,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
   const float* row = scores + (size_t)rowi * lds;
   const int kk = min(k, n);
   int total = 0;
+  const bool direct_ids = idx_map != nullptr && n <= TK_CAP;   // composites carry the item id itself
   if (n <= TK_CAP) {
     for (int i = threadIdx.x; i < TK_CAP; i += blockDim.x)
-      buf[i] = (i < n) ? compose(f2key(row[i]), (uint32_t)i) : 0ull;
+      buf[i] = (i < n) ? compose(f2key(row[i]), direct_ids ? (uint32_t)idx_map[(size_t)rowi * lds + i] : (uint32_t)i)
+                       : 0ull;
     total = n;
     __syncthreads();
   } else {
@@ -183,13 +186,72 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
     if (i < kk) {
       unsigned long long c = buf[i];
       uint32_t pos = 0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull);
-      id = idx_map ? idx_map[(size_t)rowi * lds + pos] : (int32_t)pos + idx_offset;
+      id = direct_ids ? (int32_t)pos : (idx_map ? idx_map[(size_t)rowi * lds + pos] : (int32_t)pos + idx_offset);
       val = key2f((uint32_t)(c >> 32));
     }
     idx_out[(size_t)rowi * k + i] = id;
     if (val_out) val_out[(size_t)rowi * k + i] = val;
   }
 }
+
+// Candidate lists of the fused predict path -> ready for the final sort: known items of the row (sorted CSR columns)
+// and unused slots are pushed to the bottom; rows whose list overflowed or holds fewer than k unknown items are
+// counted in n_bad (the caller then re-ranks the batch through the dense path -- exactness never depends on the
+// threshold estimate).  One CTA per row.
+__global__ void __launch_bounds__(256) cand_finish_kernel(float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                                                          const int32_t* __restrict__ cnt, int cap, int B, int k,
+                                                          const int32_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ indices, int32_t* n_bad) {
+  __shared__ int valid_s;
+  for (int row = blockIdx.x; row < B; row += gridDim.x) {
+    if (threadIdx.x == 0) valid_s = 0;
+    __syncthreads();
+    const int c = cnt[row], n = min(c, cap);
+    const int p0 = indptr ? indptr[row] : 0, p1 = indptr ? indptr[row + 1] : 0;
+    int valid = 0;
+    for (int sl = threadIdx.x; sl < cap; sl += blockDim.x) {
+      const size_t o = (size_t)row * cap + sl;
+      if (sl >= n) { cand_val[o] = -FLT_MAX; continue; }
+      const int id = cand_idx[o];
+      int lo = p0, hi = p1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(indices + mid) < id) lo = mid + 1; else hi = mid;
+      }
+      if (lo < p1 && __ldg(indices + lo) == id) cand_val[o] = -FLT_MAX;
+      else ++valid;
+    }
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&valid_s, valid);
+    __syncthreads();
+    if (threadIdx.x == 0 && (c > cap || valid_s < k)) atomicAdd(n_bad, 1);
+    __syncthreads();
+  }
+}
+
+int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
+                      int tile_stride, int n_sel, int filter, float* out, int64_t ldo, int out_by_visit,
+                      int apply_sigmoid, const float* tau, int tau_stride, int32_t* cnt, float* cand_val,
+                      int32_t* cand_idx, int cap, int split, cudaStream_t s);
+
+// Plan of the fused predict + top-k path for one (Vloc, k): sample tiles, threshold rank, candidate capacity.
+struct TopkPlan {
+  int n_tiles, n_samp, stride, S, T, J, cap;
+  bool ok;
+};
+static TopkPlan make_plan(int Vloc, int k) {
+  TopkPlan p;
+  p.n_tiles = (Vloc + 63) / 64;
+  p.n_samp = std::min(1024, p.n_tiles / 8);
+  p.ok = p.n_samp >= 64 && k <= 1024;          // Vloc >= 32768; below that the dense path is as cheap
+  p.stride = p.ok ? p.n_tiles / p.n_samp : 1;
+  p.S = p.n_samp * 64;
+  p.T = std::max(1024, std::min(4096, 4 * (k + 256)));
+  p.cap = TK_CAP;
+  p.J = p.ok ? std::max(8, (int)(((int64_t)p.T * p.S + Vloc - 1) / Vloc)) : 8;
+  return p;
+}
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace aae
 
@@ -223,6 +285,60 @@ int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, co
     if (rc) return rc;
   }
   return launch_row_topk(scores, lds, B, Vloc, k, v_begin, nullptr, idx_out, val_out, as_stream(stream));
+}
+
+int64_t aae_predict_topk_work_bytes(int B, int Vloc, int k) {
+  if (B <= 0 || Vloc <= 0 || k <= 0) return 0;
+  TopkPlan p = make_plan(Vloc, k);
+  if (!p.ok) return 0;
+  return (int64_t)(al256((size_t)B * p.S * 4) + 2 * al256((size_t)B * p.J * 4) + al256((size_t)B * 4) + 256 +
+                   2 * al256((size_t)B * p.cap * 4));
+}
+
+int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
+                     const int32_t* indptr, const int32_t* indices, int k, int impl, void* work, int64_t work_bytes,
+                     int32_t* idx_out, float* val_out, int32_t* n_bad, void* stream) {
+  AAE_REQUIRE(h2 && Wd3 && bd3 && idx_out && n_bad && work, "null pointer");
+  AAE_REQUIRE(B > 0 && H > 0 && Vloc > 0 && k > 0, "bad size");
+  AAE_REQUIRE((indptr == nullptr) == (indices == nullptr), "indptr and indices go together");
+  if (impl != 1 && impl != 2) {
+    set_error("aae_predict_topk: the fused path runs on the tensor-core kernel (impl 1 or 2), got %d", impl);
+    return AAE_E_UNSUPPORTED;
+  }
+  const TopkPlan p = make_plan(Vloc, k);
+  if (!p.ok) {
+    set_error("aae_predict_topk: shard of %d items / k = %d is outside the fused envelope (use the dense path)", Vloc, k);
+    return AAE_E_UNSUPPORTED;
+  }
+  AAE_REQUIRE(work_bytes >= aae_predict_topk_work_bytes(B, Vloc, k), "workspace too small");
+  cudaStream_t s = as_stream(stream);
+  unsigned char* w = reinterpret_cast<unsigned char*>(work);
+  float* samp = reinterpret_cast<float*>(w);        w += al256((size_t)B * p.S * 4);
+  float* thr_val = reinterpret_cast<float*>(w);     w += al256((size_t)B * p.J * 4);
+  int32_t* thr_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.J * 4);
+  int32_t* cnt = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * 4);
+  w += 256;
+  float* cand_val = reinterpret_cast<float*>(w);    w += al256((size_t)B * p.cap * 4);
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(w);
+  const int split = impl == 1 ? 3 : 1;
+  // (1) scores of a strided sample of the tiles -> (2) per-row threshold = J-th largest sample score, chosen so that
+  // about T of the shard's items pass it -> (3) full pass, candidates appended from the GEMM epilogue -> (4) known
+  // items masked, candidates sorted, first k emitted
+  int rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, p.stride, p.n_samp, 0, samp, p.S, 1, 0, nullptr, 0,
+                             nullptr, nullptr, nullptr, 0, split, s);
+  if (rc) return rc;
+  rc = launch_row_topk(samp, p.S, B, p.S, p.J, 0, nullptr, thr_idx, thr_val, s);
+  if (rc) return rc;
+  cudaMemsetAsync(cnt, 0, (size_t)B * 4, s);
+  cudaMemsetAsync(n_bad, 0, 4, s);
+  rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, 1, p.n_tiles, 1, nullptr, 0, 0, 0, thr_val + (p.J - 1), p.J,
+                         cnt, cand_val, cand_idx, p.cap, split, s);
+  if (rc) return rc;
+  cand_finish_kernel<<<std::min(B, 8 * sm_count()), 256, 0, s>>>(cand_val, cand_idx, cnt, p.cap, B, std::min(k, Vloc),
+                                                                 indptr, indices, n_bad);
+  rc = check_launch("cand_finish");
+  if (rc) return rc;
+  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s);
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,

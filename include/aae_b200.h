@@ -281,6 +281,20 @@ int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const fl
 int64_t aae_topk_work_bytes(int B, int k);
 int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
                     const int32_t* indices, int k, int32_t* idx_out, float* val_out, void* work, void* stream);
+/* Fused predict + ranking for large vocabularies (K5): reconstruction logits and the masked top-k WITHOUT the
+ * [B, Vloc] score matrix.  Replaces predict's dense lin3 (aae.py:866-868) followed by remove_non_missing + argtopk
+ * (evaluation.py:183-199, 20-58).  Four launches on the stream: (1) logits of a strided sample of 64-item tiles,
+ * (2) per-row threshold = the J-th largest sample score (about T = max(1024, 4(k+256)) items of the shard pass it),
+ * (3) the full tcgen05 pass whose epilogue appends (logit, item) pairs above the threshold to per-row candidate
+ * lists, (4) known items masked, candidates sorted, first k emitted (descending, ties by lower item id).
+ * Exactness never depends on the estimate: n_bad[0] (device) counts rows whose list overflowed or held fewer than
+ * k unknown items; if it is non-zero the caller must rank the batch through aae_dec_out_scores + aae_masked_topk.
+ * Envelope: impl 1 (3xTF32) or 2 (TF32), Vloc >= 32768, k <= 1024; otherwise AAE_E_UNSUPPORTED.
+ * work: aae_predict_topk_work_bytes(B, Vloc, k) bytes of device scratch (0 = outside the envelope). */
+int64_t aae_predict_topk_work_bytes(int B, int Vloc, int k);
+int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
+                     const int32_t* indptr, const int32_t* indices, int k, int impl, void* work, int64_t work_bytes,
+                     int32_t* idx_out, float* val_out, int32_t* n_bad, void* stream);
 /* k-way merge of per-shard results: cand_val/cand_idx [B, n_cand] -> top k (descending). */
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
                    float* val_out, void* stream);
