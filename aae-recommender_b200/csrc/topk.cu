@@ -109,6 +109,7 @@ __device__ int block_count_ge(const float* __restrict__ row, int n, uint32_t thr
 __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __restrict__ scores, int64_t lds, int n,
                                                                  int k, int idx_offset,
                                                                  const int32_t* __restrict__ idx_map,
+                                                                 const int32_t* __restrict__ n_valid,
                                                                  int32_t* __restrict__ idx_out,
                                                                  float* __restrict__ val_out) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
   __shared__ int scratch;
   const int rowi = blockIdx.x;
   const float* row = scores + (size_t)rowi * lds;
+  if (n_valid) n = max(0, min(n, n_valid[rowi]));     // only the first n_valid[row] entries of the row are live
   const int kk = min(k, n);
   int total = 0;
   const bool direct_ids = idx_map != nullptr && n <= TK_CAP;   // composites carry the item id itself
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
 }
 
 // Candidate lists of the fused predict path -> ready for the final sort: known items of the row (sorted CSR columns)
-// and unused slots are pushed to the bottom; rows whose list overflowed or holds fewer than k unknown items are
+// are pushed to the bottom; rows whose list overflowed or holds fewer than k unknown items are
 // counted in n_bad (the caller then re-ranks the batch through the dense path -- exactness never depends on the
 // threshold estimate).  One CTA per row.
 __global__ void __launch_bounds__(256) cand_finish_kernel(float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
@@ -209,9 +211,8 @@ __global__ void __launch_bounds__(256) cand_finish_kernel(float* __restrict__ ca
     const int c = cnt[row], n = min(c, cap);
     const int p0 = indptr ? indptr[row] : 0, p1 = indptr ? indptr[row + 1] : 0;
     int valid = 0;
-    for (int sl = threadIdx.x; sl < cap; sl += blockDim.x) {
+    for (int sl = threadIdx.x; sl < n; sl += blockDim.x) {     // the final sort reads the first n slots only
       const size_t o = (size_t)row * cap + sl;
-      if (sl >= n) { cand_val[o] = -FLT_MAX; continue; }
       const int id = cand_idx[o];
       int lo = p0, hi = p1;
       while (lo < hi) {
@@ -227,6 +228,42 @@ __global__ void __launch_bounds__(256) cand_finish_kernel(float* __restrict__ ca
     if (threadIdx.x == 0 && (c > cap || valid_s < k)) atomicAdd(n_bad, 1);
     __syncthreads();
   }
+}
+
+// Threshold of the fused predict path: (approximately) the J-th largest of the row's S sample scores.  Every
+// thread keeps the 4 largest of its strided share in registers, the 256 x 4 survivors are sorted in shared memory
+// and the J-th is taken.  A thread that holds more than 4 of the row's top J makes the result slightly LOWER than
+// the true order statistic -- a few more candidates pass the filter, nothing else: exactness is guarded by n_bad.
+constexpr int KTH_THREADS = 256, KTH_KEEP = 4;
+__global__ void __launch_bounds__(KTH_THREADS) row_kth_approx_kernel(const float* __restrict__ samp, int64_t lds, int S,
+                                                                     int J, float* __restrict__ tau) {
+  __shared__ unsigned long long buf[KTH_THREADS * KTH_KEEP];
+  const float* row = samp + (size_t)blockIdx.x * lds;
+  float t0 = -FLT_MAX, t1 = -FLT_MAX, t2 = -FLT_MAX, t3 = -FLT_MAX;      // t0 >= t1 >= t2 >= t3
+  auto push = [&](float x) {
+    if (x > t3) {
+      if (x > t1) {
+        t3 = t2; t2 = t1;
+        if (x > t0) { t1 = t0; t0 = x; } else t1 = x;
+      } else {
+        if (x > t2) { t3 = t2; t2 = x; } else t3 = x;
+      }
+    }
+  };
+  if ((S & 3) == 0 && (lds & 3) == 0) {
+    for (int i = threadIdx.x; i < (S >> 2); i += KTH_THREADS) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(row) + i);
+      push(x.x); push(x.y); push(x.z); push(x.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < S; i += KTH_THREADS) push(__ldcs(row + i));
+  }
+  buf[threadIdx.x * KTH_KEEP + 0] = compose(f2key(t0), 0u);
+  buf[threadIdx.x * KTH_KEEP + 1] = compose(f2key(t1), 0u);
+  buf[threadIdx.x * KTH_KEEP + 2] = compose(f2key(t2), 0u);
+  buf[threadIdx.x * KTH_KEEP + 3] = compose(f2key(t3), 0u);
+  bitonic_desc(buf, KTH_THREADS * KTH_KEEP);
+  if (threadIdx.x == 0) tau[blockIdx.x] = key2f((uint32_t)(buf[min(J, KTH_THREADS * KTH_KEEP) - 1] >> 32));
 }
 
 int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
@@ -262,14 +299,15 @@ extern "C" {
 int64_t aae_topk_work_bytes(int B, int k) { return 16; }
 
 static int launch_row_topk(const float* scores, int64_t lds, int B, int n, int k, int idx_offset,
-                           const int32_t* idx_map, int32_t* idx_out, float* val_out, cudaStream_t s) {
+                           const int32_t* idx_map, int32_t* idx_out, float* val_out, cudaStream_t s,
+                           const int32_t* n_valid = nullptr) {
   size_t smem = sizeof(unsigned long long) * (TK_CAP + TK_SAMPLE);
   cudaError_t e = cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("row_topk: %s", cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
-  row_topk_kernel<<<B, TK_THREADS, smem, s>>>(scores, lds, n, k, idx_offset, idx_map, idx_out, val_out);
+  row_topk_kernel<<<B, TK_THREADS, smem, s>>>(scores, lds, n, k, idx_offset, idx_map, n_valid, idx_out, val_out);
   return check_launch("row_topk");
 }
 
@@ -327,18 +365,25 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
   int rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, p.stride, p.n_samp, 0, samp, p.S, 1, 0, nullptr, 0,
                              nullptr, nullptr, nullptr, 0, split, s);
   if (rc) return rc;
-  rc = launch_row_topk(samp, p.S, B, p.S, p.J, 0, nullptr, thr_idx, thr_val, s);
+  const bool kth_fast = p.J <= 256;      // else: exact top-J of the sample (large k on a small shard)
+  if (kth_fast) {
+    row_kth_approx_kernel<<<B, KTH_THREADS, 0, s>>>(samp, p.S, p.S, p.J, thr_val);
+    rc = check_launch("row_kth_approx");
+  } else {
+    rc = launch_row_topk(samp, p.S, B, p.S, p.J, 0, nullptr, thr_idx, thr_val, s);
+  }
   if (rc) return rc;
   cudaMemsetAsync(cnt, 0, (size_t)B * 4, s);
   cudaMemsetAsync(n_bad, 0, 4, s);
-  rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, 1, p.n_tiles, 1, nullptr, 0, 0, 0, thr_val + (p.J - 1), p.J,
-                         cnt, cand_val, cand_idx, p.cap, split, s);
+  rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, 1, p.n_tiles, 1, nullptr, 0, 0, 0,
+                         kth_fast ? thr_val : thr_val + (p.J - 1), kth_fast ? 1 : p.J, cnt, cand_val, cand_idx, p.cap,
+                         split, s);
   if (rc) return rc;
   cand_finish_kernel<<<std::min(B, 8 * sm_count()), 256, 0, s>>>(cand_val, cand_idx, cnt, p.cap, B, std::min(k, Vloc),
                                                                  indptr, indices, n_bad);
   rc = check_launch("cand_finish");
   if (rc) return rc;
-  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s);
+  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, cnt);
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
