@@ -375,7 +375,8 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": 2.0 * Bq * V * H / ps / 1e12 / tf_peak,
                          "note": "algorithmic 2*B*V*H flops of the decoder output layer; peak = measured dense bf16 "
                                  "(sustained); the kernel runs fp32-accurate 3xTF32 (3 MMAs per product at half the "
-                                 "bf16 rate), and the scores still round-trip HBM once before the top-k"}}
+                                 "bf16 rate: 6x the bf16 time per algorithmic flop); top-k candidates are selected "
+                                 "in the GEMM epilogue, the [B,V] scores never reach HBM"}}
     # ---------------- MPD-shaped secondary workload (BASELINE configs[3]): V = 2M items, item-sharded ----------------
     if not args.no_extra and args.workload == "pubmed":
         torch.cuda.empty_cache()
