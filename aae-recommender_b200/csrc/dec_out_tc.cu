@@ -218,6 +218,17 @@ template <> struct TmemIO<16> {
   static __device__ __forceinline__ void st(uint32_t taddr, const float* v) { tmem_st16(taddr, v); }
 };
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// Pins a prefetched register tile to its point of use: without it the compiler hoists the hi/lo split (pure ALU work
+// on the loaded values) up to right behind the global loads, and the warp then waits for the load latency one
+// iteration early, in the middle of the pipeline, instead of letting it overlap the MMAs of that iteration.
+#ifndef TC_PIN_PREFETCH
+#define TC_PIN_PREFETCH 1
+#endif
+__device__ __forceinline__ void pin4(float4& x) {
+#if TC_PIN_PREFETCH
+  asm volatile("" : "+f"(x.x), "+f"(x.y), "+f"(x.z), "+f"(x.w));
+#endif
+}
 
 // byte offset of element (r, c) in a core-matrix-tiled buffer whose row groups are `s_r` bytes apart
 __device__ __forceinline__ uint32_t core_off(int r, int c, uint32_t s_r) {
@@ -760,6 +771,7 @@ __device__ __forceinline__ void store_wb_regs(const float4* wr, const WChunk* wc
   for (int j = 0; j < NCH; ++j) {
     if (wc[j].goff == -2) continue;
     float4 x = wr[j];
+    pin4(x);
     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
     *reinterpret_cast<float4*>(wb_hi + wc[j].wb_off) = h;
     if (with_lo) *reinterpret_cast<float4*>(wb_lo + wc[j].wb_off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
@@ -1436,6 +1448,15 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
 // Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
 // (evaluation.py:183-199, 20-58).
 // ---------------------------------------------------------------------------------------------
+#ifndef K5_LOAD_LATE
+#define K5_LOAD_LATE 0
+#endif
+#ifndef K5_FAKE_LOAD
+#define K5_FAKE_LOAD 0
+#endif
+#ifndef K5_NO_EPI
+#define K5_NO_EPI 0
+#endif
 constexpr int PN = 64;                 // items per tile
 constexpr int P_NWE = 16;              // loader / epilogue warps
 constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
@@ -1448,27 +1469,39 @@ struct SelArgs {
   int tile_stride, n_sel;              // tiles visited: j * tile_stride, j < n_sel
   int filter;                          // 0: dense scores, 1: threshold filter
   float* out; long long ldo; int out_by_visit, apply_sigmoid;
-  const float* tau; int tau_stride; int32_t* cnt; float* cand_val; int32_t* cand_idx; int cap;
+  // filter: row b owns gridDim.x * 4 private sub-lists (one per CTA column x and 16-column part of the tile) of cap_sub
+  // slots; sub-list counters live in registers (one writer each: no atomics, deterministic order) and are stored to
+  // cnt[b * nsub + sub] at the end of the chunk (a count above cap_sub = overflow)
+  const float* tau; int tau_stride; int32_t* cnt; float* cand_val; int32_t* cand_idx; int cap_sub;
 };
 
-__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int cgb, int ncg) {
+// Loader mapping: lane = item row inside a 32-row half (warp & 1), and per thread two PAIRS of adjacent 16-byte column
+// groups (pair (warp >> 1) + 8 j): the two loads of a pair cover one 32-byte sector of the row, so the L2 -> SM traffic
+// is the useful bytes only (the row-per-lane mapping with lone 16-byte accesses fetched every sector twice -- the
+// kernel was L2-bandwidth-bound on exactly that: 8 chunks x 800 MB x 2 per pass at V = 2M).  A quarter warp still
+// writes 8 consecutive rows of one column group = one 128-byte core matrix: conflict-free.
+__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int pb, int ncg) {
   const bool rv = v0 + row < a.Vloc;
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = cgb + 8 * j, c = cg * 4;
+    const int cg = 2 * (pb + 8 * (j >> 1)) + (j & 1), c = cg * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#if K5_FAKE_LOAD
+    x.x = (float)(v0 + row + c) * 1e-6f;    // experiment: no global loads at all (results are garbage)
+#else
     if (rv && cg < ncg) {
       if (c + 3 < a.H) x = __ldg(reinterpret_cast<const float4*>(a.Wd3 + (size_t)(v0 + row) * a.H + c));
       else if (c == a.H) x.x = __ldg(a.bd3 + v0 + row);
     }
+#endif
     wr[j] = x;
   }
 }
 __device__ __forceinline__ void p_store_w(const float4* wr, unsigned char* hi, unsigned char* lo, uint32_t sbo, int row,
-                                          int cgb, int ncg, bool with_lo) {
+                                          int pb, int ncg, bool with_lo) {
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = cgb + 8 * j;
+    const int cg = 2 * (pb + 8 * (j >> 1)) + (j & 1);
     if (cg < ncg) store_split4(hi, lo, row, cg, sbo, wr[j], with_lo);
   }
 }
@@ -1533,17 +1566,23 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
       const bool rowv = brow < nb;
       float tau = __int_as_float(0x7f800000);
       if (a.filter && rowv) tau = a.tau[(size_t)(b0 + brow) * a.tau_stride];
+      const int nsub = (int)gridDim.x * 4, sub = (int)blockIdx.x * 4 + cpart;
+      const size_t sub_base = ((size_t)(b0 + brow) * nsub + sub) * (size_t)a.cap_sub;
+      int my_cnt = 0;
       auto tile_v0 = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) * a.tile_stride) * PN; };
-      float4 wr[P_WCH];
+      // W' tiles travel global -> registers -> shared memory; two register sets keep the loads of tiles i+2 / i+3
+      // in flight for two whole iterations (issued after the epilogue of the tile whose set they reuse)
+      float4 wr0[P_WCH], wr1[P_WCH];
       for (int p = 0; p < 2 && p < n_my; ++p) {
-        p_load_w(wr, a, tile_v0(p), lrow, cgb, ncg);
-        p_store_w(wr, wst + 2 * p * wb_bytes, wst + (2 * p + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
+        p_load_w(wr0, a, tile_v0(p), lrow, cgb, ncg);
+        p_store_w(wr0, wst + 2 * p * wb_bytes, wst + (2 * p + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_ready[p]);
       }
-      if (n_my > 2) p_load_w(wr, a, tile_v0(2), lrow, cgb, ncg);
-      for (int i = 0; i < n_my; ++i) {
+      if (n_my > 2) p_load_w(wr0, a, tile_v0(2), lrow, cgb, ncg);
+      if (n_my > 3) p_load_w(wr1, a, tile_v0(3), lrow, cgb, ncg);
+      auto body = [&](const int i, float4 (&wr)[P_WCH]) {
         const int s = i & 1;
         mbar_wait(&bar_mma[s], s ? ph1 : ph0);
         if (s) ph1 ^= 1; else ph0 ^= 1;
@@ -1557,7 +1596,6 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_ready[s]);
-          if (i + 3 < n_my) p_load_w(wr, a, tile_v0(i + 3), lrow, cgb, ncg);
         }
         // ---- epilogue of tile i
         const int v0 = tile_v0(i);
@@ -1567,16 +1605,15 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
 #pragma unroll
           for (int j = 0; j < P_CW; ++j) any |= (__uint_as_float(zr[j]) > tau);
           if (any) {
-            const size_t rb = (size_t)(b0 + brow);
 #pragma unroll
             for (int j = 0; j < P_CW; ++j) {
               const float z = __uint_as_float(zr[j]);
               if (z > tau && j < vm) {
-                const int slot = atomicAdd(a.cnt + rb, 1);
-                if (slot < a.cap) {
-                  a.cand_val[rb * a.cap + slot] = z;
-                  a.cand_idx[rb * a.cap + slot] = a.v_begin + v0 + cpart * P_CW + j;
+                if (my_cnt < a.cap_sub) {
+                  a.cand_val[sub_base + my_cnt] = z;
+                  a.cand_idx[sub_base + my_cnt] = a.v_begin + v0 + cpart * P_CW + j;
                 }
+                ++my_cnt;
               }
             }
           }
@@ -1606,7 +1643,13 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
             }
           }
         }
+        if (i + 4 < n_my) p_load_w(wr, a, tile_v0(i + 4), lrow, cgb, ncg);
+      };
+      for (int i = 0; i < n_my; i += 2) {
+        body(i, wr0);
+        if (i + 1 < n_my) body(i + 1, wr1);
       }
+      if (a.filter && rowv) a.cnt[(size_t)(b0 + brow) * nsub + sub] = my_cnt;
     }
   }
   tc_fence_before();
@@ -1686,6 +1729,13 @@ int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, floa
   return check_launch("dec_out_train(tc)");
 }
 
+// grid of the K5 kernel for B query rows and n_sel tiles: y = chunks of 128 rows, x = CTAs sharing a chunk
+void dec_out_select_grid(int B, int n_sel, int* gx, int* gy) {
+  const int n_chunks = (B + tc::BM - 1) / tc::BM;
+  *gy = std::min(n_chunks, sm_count());
+  *gx = std::max(1, std::min(n_sel, sm_count() / *gy));
+}
+
 // K5 launcher: dense scores (filter == 0) or threshold filter (filter == 1) over the tiles j * tile_stride, j < n_sel.
 int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int v_begin,
                       int tile_stride, int n_sel, int filter, float* out, int64_t ldo, int out_by_visit,
@@ -1704,10 +1754,9 @@ int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const flo
   a.h2 = h2; a.B = B; a.H = H; a.Wd3 = Wd3; a.bd3 = bd3; a.Vloc = Vloc; a.v_begin = v_begin;
   a.tile_stride = tile_stride; a.n_sel = n_sel; a.filter = filter;
   a.out = out; a.ldo = ldo; a.out_by_visit = out_by_visit; a.apply_sigmoid = apply_sigmoid;
-  a.tau = tau; a.tau_stride = tau_stride; a.cnt = cnt; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cap = cap;
-  const int n_chunks = (B + tc::BM - 1) / tc::BM;
-  const int gy = std::min(n_chunks, sm_count());
-  const int gx = std::max(1, std::min(n_sel, sm_count() / gy));
+  a.tau = tau; a.tau_stride = tau_stride; a.cnt = cnt; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cap_sub = cap;
+  int gx, gy;
+  dec_out_select_grid(B, n_sel, &gx, &gy);
   kern<<<dim3(gx, gy), tc::P_NT, smem, s>>>(a);
   return check_launch("dec_out_select");
 }

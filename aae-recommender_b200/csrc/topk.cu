@@ -12,6 +12,7 @@
 // a lower / higher sample rank; pathological rows (huge tie groups) fall back to an exact
 // bit-by-bit radix bisection.
 #include <float.h>
+#include <math.h>
 #include <algorithm>
 #include "common.cuh"
 
@@ -196,36 +197,88 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
   }
 }
 
-// Candidate lists of the fused predict path -> ready for the final sort: known items of the row (sorted CSR columns)
-// are pushed to the bottom; rows whose list overflowed or holds fewer than k unknown items are
-// counted in n_bad (the caller then re-ranks the batch through the dense path -- exactness never depends on the
-// threshold estimate).  One CTA per row.
-__global__ void __launch_bounds__(256) cand_finish_kernel(float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
-                                                          const int32_t* __restrict__ cnt, int cap, int B, int k,
-                                                          const int32_t* __restrict__ indptr,
-                                                          const int32_t* __restrict__ indices, int32_t* n_bad) {
-  __shared__ int valid_s;
+// Candidate sub-lists of the fused predict path -> one compact list per row, ready for the final sort.  Row b owns
+// nsub private sub-lists of cap_sub slots (written without atomics by the filter epilogue, counts in cnt[b*nsub+s]);
+// they are concatenated in sub-list order (deterministic), known items of the row (sorted CSR columns) are pushed to
+// the bottom.  Rows with an overflowed sub-list, more than cap_out candidates or fewer than k unknown ones are counted
+// in n_bad (the caller then re-ranks the batch through the dense path -- exactness never depends on the threshold
+// estimate).  One CTA per row.
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* __restrict__ cand_val,
+                                                                  const int32_t* __restrict__ cand_idx,
+                                                                  const int32_t* __restrict__ cnt, int nsub, int cap_sub,
+                                                                  float* __restrict__ out_val, int32_t* __restrict__ out_idx,
+                                                                  int cap_out, int32_t* __restrict__ tot, int B, int k,
+                                                                  const int32_t* __restrict__ indptr,
+                                                                  const int32_t* __restrict__ indices, int32_t* n_bad) {
+  extern __shared__ int off_s[];                 // [nsub + 1] exclusive prefix of the sub-list counts
+  __shared__ int warp_s[FIN_THREADS / 32];
+  __shared__ int valid_s, over_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (nsub + FIN_THREADS - 1) / FIN_THREADS;
   for (int row = blockIdx.x; row < B; row += gridDim.x) {
-    if (threadIdx.x == 0) valid_s = 0;
+    if (tid == 0) { valid_s = 0; over_s = 0; }
     __syncthreads();
-    const int c = cnt[row], n = min(c, cap);
+    // block-wide exclusive scan of min(cnt, cap_sub)
+    int mine = 0, over = 0;
+    for (int q = 0; q < per; ++q) {
+      const int sidx = tid * per + q;
+      if (sidx < nsub) {
+        const int c = cnt[(size_t)row * nsub + sidx];
+        over |= (c > cap_sub);
+        mine += min(c, cap_sub);
+      }
+    }
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_s[warp] = incl;
+    if (over) over_s = 1;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_s[w];
+    int run = wbase + incl - mine;
+    for (int q = 0; q < per; ++q) {
+      const int sidx = tid * per + q;
+      if (sidx < nsub) {
+        off_s[sidx] = run;
+        run += min(cnt[(size_t)row * nsub + sidx], cap_sub);
+      }
+    }
+    if (tid == FIN_THREADS - 1) off_s[nsub] = run;
+    __syncthreads();
+    const int total = off_s[nsub];
+    const bool fits = total <= cap_out;
     const int p0 = indptr ? indptr[row] : 0, p1 = indptr ? indptr[row + 1] : 0;
     int valid = 0;
-    for (int sl = threadIdx.x; sl < n; sl += blockDim.x) {     // the final sort reads the first n slots only
-      const size_t o = (size_t)row * cap + sl;
-      const int id = cand_idx[o];
-      int lo = p0, hi = p1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(indices + mid) < id) lo = mid + 1; else hi = mid;
+    if (fits) {
+      for (int q = tid; q < nsub * cap_sub; q += FIN_THREADS) {
+        const int sidx = q / cap_sub, sl = q - sidx * cap_sub;
+        const int o0 = off_s[sidx];
+        if (sl >= off_s[sidx + 1] - o0) continue;
+        const size_t src = ((size_t)row * nsub + sidx) * cap_sub + sl;
+        const int id = cand_idx[src];
+        float v = cand_val[src];
+        int lo = p0, hi = p1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(indices + mid) < id) lo = mid + 1; else hi = mid;
+        }
+        if (lo < p1 && __ldg(indices + lo) == id) v = -FLT_MAX;
+        else ++valid;
+        out_val[(size_t)row * cap_out + o0 + sl] = v;
+        out_idx[(size_t)row * cap_out + o0 + sl] = id;
       }
-      if (lo < p1 && __ldg(indices + lo) == id) cand_val[o] = -FLT_MAX;
-      else ++valid;
     }
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&valid_s, valid);
+    if (lane == 0 && valid) atomicAdd(&valid_s, valid);
     __syncthreads();
-    if (threadIdx.x == 0 && (c > cap || valid_s < k)) atomicAdd(n_bad, 1);
+    if (tid == 0) {
+      tot[row] = fits ? total : 0;
+      if (over_s || !fits || valid_s < k) atomicAdd(n_bad, 1);
+    }
     __syncthreads();
   }
 }
@@ -272,11 +325,14 @@ int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const flo
                       int32_t* cand_idx, int cap, int split, cudaStream_t s);
 
 // Plan of the fused predict + top-k path for one (Vloc, k): sample tiles, threshold rank, candidate capacity.
+void dec_out_select_grid(int B, int n_sel, int* gx, int* gy);
+
 struct TopkPlan {
   int n_tiles, n_samp, stride, S, T, J, cap;
+  int nsub, cap_sub;       // private candidate sub-lists per row (one per CTA column and 16-column tile part)
   bool ok;
 };
-static TopkPlan make_plan(int Vloc, int k) {
+static TopkPlan make_plan(int B, int Vloc, int k) {
   TopkPlan p;
   p.n_tiles = (Vloc + 63) / 64;
   p.n_samp = std::min(1024, p.n_tiles / 8);
@@ -286,6 +342,15 @@ static TopkPlan make_plan(int Vloc, int k) {
   p.T = std::max(1024, std::min(4096, 4 * (k + 256)));
   p.cap = TK_CAP;
   p.J = p.ok ? std::max(8, (int)(((int64_t)p.T * p.S + Vloc - 1) / Vloc)) : 8;
+  int gx = 1, gy = 1;
+  dec_out_select_grid(B, p.n_tiles, &gx, &gy);
+  p.nsub = 4 * gx;
+  // expected T / nsub candidates per sub-list; room for 8 sigma of a Poisson count, and for the worst clustering of
+  // twice T candidates in consecutive items (16 per visited tile part)
+  const double e = (double)p.T / p.nsub;
+  const int stat = (int)(e + 8.0 * sqrt(e) + 8.0);
+  const int clus = 16 * ((2 * p.T / 64 + gx - 1) / gx) + 8;
+  p.cap_sub = std::max(stat, clus);
   return p;
 }
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -327,9 +392,10 @@ int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, co
 
 int64_t aae_predict_topk_work_bytes(int B, int Vloc, int k) {
   if (B <= 0 || Vloc <= 0 || k <= 0) return 0;
-  TopkPlan p = make_plan(Vloc, k);
+  TopkPlan p = make_plan(B, Vloc, k);
   if (!p.ok) return 0;
-  return (int64_t)(al256((size_t)B * p.S * 4) + 2 * al256((size_t)B * p.J * 4) + al256((size_t)B * 4) + 256 +
+  return (int64_t)(al256((size_t)B * p.S * 4) + 2 * al256((size_t)B * p.J * 4) + al256((size_t)B * p.nsub * 4) +
+                   al256((size_t)B * 4) + 2 * al256((size_t)B * p.nsub * p.cap_sub * 4) +
                    2 * al256((size_t)B * p.cap * 4));
 }
 
@@ -343,7 +409,7 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
     set_error("aae_predict_topk: the fused path runs on the tensor-core kernel (impl 1 or 2), got %d", impl);
     return AAE_E_UNSUPPORTED;
   }
-  const TopkPlan p = make_plan(Vloc, k);
+  const TopkPlan p = make_plan(B, Vloc, k);
   if (!p.ok) {
     set_error("aae_predict_topk: shard of %d items / k = %d is outside the fused envelope (use the dense path)", Vloc, k);
     return AAE_E_UNSUPPORTED;
@@ -354,8 +420,10 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
   float* samp = reinterpret_cast<float*>(w);        w += al256((size_t)B * p.S * 4);
   float* thr_val = reinterpret_cast<float*>(w);     w += al256((size_t)B * p.J * 4);
   int32_t* thr_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.J * 4);
-  int32_t* cnt = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * 4);
-  w += 256;
+  int32_t* cnt = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * p.nsub * 4);
+  int32_t* tot = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * 4);
+  float* sub_val = reinterpret_cast<float*>(w);     w += al256((size_t)B * p.nsub * p.cap_sub * 4);
+  int32_t* sub_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.nsub * p.cap_sub * 4);
   float* cand_val = reinterpret_cast<float*>(w);    w += al256((size_t)B * p.cap * 4);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(w);
   const int split = impl == 1 ? 3 : 1;
@@ -373,17 +441,17 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
     rc = launch_row_topk(samp, p.S, B, p.S, p.J, 0, nullptr, thr_idx, thr_val, s);
   }
   if (rc) return rc;
-  cudaMemsetAsync(cnt, 0, (size_t)B * 4, s);
   cudaMemsetAsync(n_bad, 0, 4, s);
   rc = dec_out_select_tc(h2, B, H, Wd3, bd3, Vloc, v_begin, 1, p.n_tiles, 1, nullptr, 0, 0, 0,
-                         kth_fast ? thr_val : thr_val + (p.J - 1), kth_fast ? 1 : p.J, cnt, cand_val, cand_idx, p.cap,
+                         kth_fast ? thr_val : thr_val + (p.J - 1), kth_fast ? 1 : p.J, cnt, sub_val, sub_idx, p.cap_sub,
                          split, s);
   if (rc) return rc;
-  cand_finish_kernel<<<std::min(B, 8 * sm_count()), 256, 0, s>>>(cand_val, cand_idx, cnt, p.cap, B, std::min(k, Vloc),
-                                                                 indptr, indices, n_bad);
+  cand_finish_kernel<<<std::min(B, 8 * sm_count()), FIN_THREADS, (p.nsub + 1) * sizeof(int), s>>>(
+      sub_val, sub_idx, cnt, p.nsub, p.cap_sub, cand_val, cand_idx, p.cap, tot, B, std::min(k, Vloc), indptr, indices,
+      n_bad);
   rc = check_launch("cand_finish");
   if (rc) return rc;
-  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, cnt);
+  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, tot);
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,

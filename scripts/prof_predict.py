@@ -15,7 +15,7 @@ V = int(os.environ.get("P_V", 2000000))
 B = int(os.environ.get("P_B", 1000))
 k = int(os.environ.get("P_K", 100))
 iters = int(os.environ.get("P_ITERS", 3))
-eng = AAEEngine(V, 100, 50, max_batch=128)
+eng = AAEEngine(V, 100, 50, max_batch=128, impl=os.environ.get("P_IMPL", "auto"))
 eng.init_uniform(42)
 Xq = synth_sets(B, V, 25, 1, 100, seed=4321)
 eng.upload_csr(Xq.indptr.astype(np.int32), Xq.indices.astype(np.int32))
