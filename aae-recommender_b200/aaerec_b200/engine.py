@@ -96,7 +96,7 @@ class AAEEngine(object):
         self.use_graph = bool(use_graph)
         self.peer = None
         self._exchange_kind = "none"
-        self.overlap_sweep = bool(overlap_sweep)
+        self.overlap_sweep = bool(overlap_sweep) and os.environ.get("AAE_B200_NO_OVERLAP", "") == ""
         self.branches = os.environ.get("AAE_B200_NO_BRANCH", "") == ""   # parallel graph branches (debug switch)
         # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
         self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "2"))

@@ -367,17 +367,35 @@ __global__ void __launch_bounds__(256) w1_rows_update_kernel(const int32_t* __re
       // rank of this lane's row among the chunk's rows (rows are distinct)
       int rank = 0;
       for (int j = 0; j < nn; ++j) rank += (__shfl_sync(0xffffffffu, r, j) < r) ? 1 : 0;
-#pragma unroll 4
-      for (int kx = 0; kx < nn; ++kx) {
-        const int src = __ffs(__ballot_sync(0xffffffffu, lane < nn && rank == kx)) - 1;
-        const int b = __shfl_sync(0xffffffffu, r, src);
-        const float w = __shfl_sync(0xffffffffu, sc, src);
-        if (VEC4) {
-          if (lane * 4 < H) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)b * H + lane * 4));
-            g4.x = fmaf(d.x, w, g4.x); g4.y = fmaf(d.y, w, g4.y); g4.z = fmaf(d.z, w, g4.z); g4.w = fmaf(d.w, w, g4.w);
+      // rows in ascending order (deterministic sum), eight gradient rows in flight at a time: the hottest items of
+      // a Zipf batch sit in most of its rows, and their warps are the tail of this kernel
+      if (VEC4) {
+        for (int k0 = 0; k0 < nn; k0 += 8) {
+          float4 d[8];
+          float w8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int kx = k0 + u;
+            const int src = __ffs(__ballot_sync(0xffffffffu, lane < nn && rank == kx)) - 1;   // -1: past the end
+            const int b = __shfl_sync(0xffffffffu, r, src & 31);
+            w8[u] = (src >= 0) ? __shfl_sync(0xffffffffu, sc, src & 31) : 0.f;
+            d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src >= 0 && lane * 4 < H) d[u] = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)b * H + lane * 4));
           }
-        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (k0 + u < nn) {
+              g4.x = fmaf(d[u].x, w8[u], g4.x); g4.y = fmaf(d[u].y, w8[u], g4.y);
+              g4.z = fmaf(d[u].z, w8[u], g4.z); g4.w = fmaf(d[u].w, w8[u], g4.w);
+            }
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int kx = 0; kx < nn; ++kx) {
+          const int src = __ffs(__ballot_sync(0xffffffffu, lane < nn && rank == kx)) - 1;
+          const int b = __shfl_sync(0xffffffffu, r, src);
+          const float w = __shfl_sync(0xffffffffu, sc, src);
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             int c = lane + 32 * q;

@@ -1462,6 +1462,7 @@ constexpr int P_NWE = 16;              // loader / epilogue warps
 constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
 constexpr int P_CW = PN / 4;           // accumulator columns per epilogue thread (4 warps per TMEM lane quarter)
 constexpr int P_WCH = 4;               // 16-byte W' chunks per loader thread (64 rows x Kp/4 <= 32 column groups)
+constexpr uint32_t P_T_AHI = 128, P_T_ALO = 256, P_TMEM_COLS = 512;   // TMEM: accumulators 2 x PN | A hi (Kp <= 128) | A lo
 
 struct SelArgs {
   const float* h2; int B, H;
@@ -1475,16 +1476,17 @@ struct SelArgs {
   const float* tau; int tau_stride; int32_t* cnt; float* cand_val; int32_t* cand_idx; int cap_sub;
 };
 
-// Loader mapping: lane = item row inside a 32-row half (warp & 1), and per thread two PAIRS of adjacent 16-byte column
-// groups (pair (warp >> 1) + 8 j): the two loads of a pair cover one 32-byte sector of the row, so the L2 -> SM traffic
-// is the useful bytes only (the row-per-lane mapping with lone 16-byte accesses fetched every sector twice -- the
-// kernel was L2-bandwidth-bound on exactly that: 8 chunks x 800 MB x 2 per pass at V = 2M).  A quarter warp still
-// writes 8 consecutive rows of one column group = one 128-byte core matrix: conflict-free.
-__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int pb, int ncg) {
+// Loader mapping (P_NWE = 16 warps, 64 rows x Kp/4 <= 32 column groups of 16 bytes): warp w owns the 8 rows
+// 8 (w & 7) .. +7 and the column groups 16 (w >> 3) + (lane >> 3) + 4 j; lane & 7 = row inside the group.  One
+// warp-wide load then touches 8 rows x 64 contiguous bytes (8-16 cache lines) instead of 32 rows x 16 bytes (32
+// lines): with the row-per-lane mapping the kernel was bound by the L1TEX tag stage (ncu: l1tex throughput 85 %,
+// 31 sectors per request), not by the tensor pipe.  A quarter warp still writes 8 consecutive rows of one column
+// group = one 128-byte core matrix: conflict-free.
+__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int cg0, int ncg) {
   const bool rv = v0 + row < a.Vloc;
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = 2 * (pb + 8 * (j >> 1)) + (j & 1), c = cg * 4;
+    const int cg = cg0 + 4 * j, c = cg * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
 #if K5_FAKE_LOAD
     x.x = (float)(v0 + row + c) * 1e-6f;    // experiment: no global loads at all (results are garbage)
@@ -1498,10 +1500,10 @@ __device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, i
   }
 }
 __device__ __forceinline__ void p_store_w(const float4* wr, unsigned char* hi, unsigned char* lo, uint32_t sbo, int row,
-                                          int pb, int ncg, bool with_lo) {
+                                          int cg0, int ncg, bool with_lo) {
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = 2 * (pb + 8 * (j >> 1)) + (j & 1);
+    const int cg = cg0 + 4 * j;
     if (cg < ncg) store_split4(hi, lo, row, cg, sbo, wr[j], with_lo);
   }
 }
@@ -1514,14 +1516,12 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
   constexpr bool with_lo = (SPLIT == 3);
   const Geom g = make_geom(a.H);
   const uint32_t wb_bytes = (PN / 8) * g.wb_sbo;
-  unsigned char* hb_hi = smem;
-  unsigned char* hb_lo = hb_hi + g.hb_bytes;
-  unsigned char* wst = hb_lo + g.hb_bytes;         // stage s: hi at wst + 2*s*wb_bytes, lo right after
+  unsigned char* wst = smem;                       // stage s: hi at wst + 2*s*wb_bytes, lo right after
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncg = g.Kp / 4;
   const int n_chunks = (a.B + BM - 1) / BM;
   const int n_my = ((int)blockIdx.x < a.n_sel) ? (a.n_sel - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (warp == P_NWE) tmem_alloc(&tmem_base_s, 2 * PN);
+  if (warp == P_NWE) tmem_alloc(&tmem_base_s, P_TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
@@ -1537,13 +1537,34 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
   uint32_t ph0 = 0, ph1 = 0;                       // parity of the barrier this role waits on, per stage
   for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
     const int b0 = chunk * BM, nb = min(BM, a.B - b0);
-    __syncthreads();                               // the previous chunk is drained: Hb may be rebuilt
-    fill_hb(hb_hi, hb_lo, g, a.h2, b0, nb, with_lo, P_NT);
-    fence_async_smem();
+    __syncthreads();                               // the previous chunk is drained: the A operand may be rebuilt
+    if (warp < P_NWE) {
+      // H2' chunk -> TMEM (A operand of every MMA of this chunk: lane = query row, column = k; hi and lo parts).
+      // A from TMEM instead of shared memory: an SS-mode M128 x N64 x K8 tf32 MMA reads 4 KB of A + 2 KB of B per
+      // 32-cycle slot, more than the 128 B/cycle the shared memory delivers -- the kernel was operand-feed-bound.
+      const int q4 = warp & 3, cpart = warp >> 2;
+      const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+      const int brow = q4 * 32 + lane;
+      for (int c = cpart; c < g.Kp / 8; c += 4) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kk = c * 8 + j;
+          float x = 0.f;
+          if (brow < nb) x = (kk < a.H) ? __ldg(a.h2 + (size_t)(b0 + brow) * a.H + kk) : (kk == a.H ? 1.0f : 0.f);
+          hi[j] = tf32_hi(x);
+          lo[j] = x - hi[j];
+        }
+        tmem_st8(lane_addr + P_T_AHI + c * 8, hi);
+        if (with_lo) tmem_st8(lane_addr + P_T_ALO + c * 8, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
     if (warp == P_NWE) {
       // ================= MMA issuer =================
-      const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
       const SmemOp op_w0 = make_op(wst, wst + wb_bytes, CORE, g.wb_sbo, 2 * CORE);
       const SmemOp op_w1 = make_op(wst + 2 * wb_bytes, wst + 3 * wb_bytes, CORE, g.wb_sbo, 2 * CORE);
       for (int it = 0; it < n_my; ++it) {
@@ -1552,7 +1573,8 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
         if (s) ph1 ^= 1; else ph0 ^= 1;
         tc_fence_after();
         if (elect_one()) {
-          issue_gemm<SPLIT>(tmem + (uint32_t)(s * PN), op_hb, s ? op_w1 : op_w0, g.Kp / 8, idesc, 0u);
+          issue_gemm_ts<SPLIT>(tmem + (uint32_t)(s * PN), tmem + P_T_AHI, tmem + P_T_ALO, s ? op_w1 : op_w0, g.Kp / 8,
+                               idesc, 0u);
           mma_commit(&bar_mma[s]);
         }
         __syncwarp();
@@ -1562,7 +1584,7 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
       const int q4 = warp & 3, cpart = warp >> 2;
       const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
       const int brow = q4 * 32 + lane;
-      const int lrow = (warp & 1) * 32 + lane, cgb = warp >> 1;      // loader mapping: item row, first column group
+      const int lrow = (warp & 7) * 8 + (lane & 7), cgb = (warp >> 3) * 16 + (lane >> 3);   // loader mapping (see p_load_w)
       const bool rowv = brow < nb;
       float tau = __int_as_float(0x7f800000);
       if (a.filter && rowv) tau = a.tau[(size_t)(b0 + brow) * a.tau_stride];
@@ -1654,7 +1676,7 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == P_NWE) tmem_dealloc(tmem, 2 * PN);
+  if (warp == P_NWE) tmem_dealloc(tmem, P_TMEM_COLS);
 }
 
 }  // namespace tc
@@ -1743,7 +1765,7 @@ int dec_out_select_tc(const float* h2, int B, int H, const float* Wd3, const flo
                       int32_t* cand_idx, int cap, int split, cudaStream_t s) {
   if (!tc_supported(B, H, "dec_out_select")) return AAE_E_UNSUPPORTED;
   tc::Geom g = tc::make_geom(H);
-  const size_t smem = 2 * (size_t)g.hb_bytes + 4 * (size_t)(tc::PN / 8) * g.wb_sbo + 256;
+  const size_t smem = 4 * (size_t)(tc::PN / 8) * g.wb_sbo + 256;
   auto kern = (split == 3) ? tc::dec_out_select_kernel<3> : tc::dec_out_select_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
