@@ -1448,21 +1448,12 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
 // Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
 // (evaluation.py:183-199, 20-58).
 // ---------------------------------------------------------------------------------------------
-#ifndef K5_LOAD_LATE
-#define K5_LOAD_LATE 0
-#endif
-#ifndef K5_FAKE_LOAD
-#define K5_FAKE_LOAD 0
-#endif
-#ifndef K5_NO_EPI
-#define K5_NO_EPI 0
-#endif
-constexpr int PN = 64;                 // items per tile
+constexpr int PN = 128;                // items per tile
 constexpr int P_NWE = 16;              // loader / epilogue warps
 constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
 constexpr int P_CW = PN / 4;           // accumulator columns per epilogue thread (4 warps per TMEM lane quarter)
-constexpr int P_WCH = 4;               // 16-byte W' chunks per loader thread (64 rows x Kp/4 <= 32 column groups)
-constexpr uint32_t P_T_AHI = 128, P_T_ALO = 256, P_TMEM_COLS = 512;   // TMEM: accumulators 2 x PN | A hi (Kp <= 128) | A lo
+constexpr int P_WCH = 7;               // 16-byte W' chunks per loader thread (8 rows x <= 28 column groups per warp)
+constexpr uint32_t P_T_AHI = 256, P_T_ALO = 384, P_TMEM_COLS = 512;   // TMEM: accumulators 2 x PN | A hi (Kp <= 128) | A lo
 
 struct SelArgs {
   const float* h2; int B, H;
@@ -1470,41 +1461,44 @@ struct SelArgs {
   int tile_stride, n_sel;              // tiles visited: j * tile_stride, j < n_sel
   int filter;                          // 0: dense scores, 1: threshold filter
   float* out; long long ldo; int out_by_visit, apply_sigmoid;
-  // filter: row b owns gridDim.x * 4 private sub-lists (one per CTA column x and 16-column part of the tile) of cap_sub
+  // filter: row b owns gridDim.x * 4 private sub-lists (one per CTA column x and 32-column part of the tile) of cap_sub
   // slots; sub-list counters live in registers (one writer each: no atomics, deterministic order) and are stored to
   // cnt[b * nsub + sub] at the end of the chunk (a count above cap_sub = overflow)
   const float* tau; int tau_stride; int32_t* cnt; float* cand_val; int32_t* cand_idx; int cap_sub;
 };
 
-// Loader mapping (P_NWE = 16 warps, 64 rows x Kp/4 <= 32 column groups of 16 bytes): warp w owns the 8 rows
-// 8 (w & 7) .. +7 and the column groups 16 (w >> 3) + (lane >> 3) + 4 j; lane & 7 = row inside the group.  One
-// warp-wide load then touches 8 rows x 64 contiguous bytes (8-16 cache lines) instead of 32 rows x 16 bytes (32
-// lines): with the row-per-lane mapping the kernel was bound by the L1TEX tag stage (ncu: l1tex throughput 85 %,
-// 31 sectors per request), not by the tensor pipe.  A quarter warp still writes 8 consecutive rows of one column
-// group = one 128-byte core matrix: conflict-free.
-__device__ __forceinline__ void p_load_w(float4* wr, const SelArgs& a, int v0, int row, int cg0, int ncg) {
-  const bool rv = v0 + row < a.Vloc;
+// Loader mapping (16 warps, 128 rows x Kp/4 <= 28 column groups of 16 bytes): warp w owns the 8 rows 8w .. 8w+7 and
+// all column groups; lane & 7 = row inside the group, column groups (lane >> 3) + 4 j.  One warp-wide load touches
+// 8 rows x 64 contiguous bytes (8-16 cache lines) instead of 32 rows x 16 bytes (32 lines): with a row-per-lane
+// mapping the kernel was bound by the L1TEX tag stage (ncu: l1tex throughput 85 %, 31 sectors per request).  A
+// quarter warp writes 8 consecutive rows of one column group = one 128-byte core matrix: conflict-free.
+// All per-thread offsets are tile-invariant and computed once (goff: float offset inside the tile's rows, -1 = bias
+// column, -2 = unused; soff: byte offset inside a stage half).
+struct PChunks {
+  int goff[P_WCH];
+  uint32_t soff[P_WCH];
+};
+__device__ __forceinline__ void p_load_w(float4* wr, const PChunks& pc, const float* __restrict__ wtile,
+                                         const float* __restrict__ btile, bool rv) {
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = cg0 + 4 * j, c = cg * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-#if K5_FAKE_LOAD
-    x.x = (float)(v0 + row + c) * 1e-6f;    // experiment: no global loads at all (results are garbage)
-#else
-    if (rv && cg < ncg) {
-      if (c + 3 < a.H) x = __ldg(reinterpret_cast<const float4*>(a.Wd3 + (size_t)(v0 + row) * a.H + c));
-      else if (c == a.H) x.x = __ldg(a.bd3 + v0 + row);
+    if (rv) {
+      if (pc.goff[j] >= 0) x = __ldg(reinterpret_cast<const float4*>(wtile + pc.goff[j]));
+      else if (pc.goff[j] == -1) x.x = __ldg(btile);
     }
-#endif
     wr[j] = x;
   }
 }
-__device__ __forceinline__ void p_store_w(const float4* wr, unsigned char* hi, unsigned char* lo, uint32_t sbo, int row,
-                                          int cg0, int ncg, bool with_lo) {
+__device__ __forceinline__ void p_store_w(const float4* wr, const PChunks& pc, unsigned char* hi, unsigned char* lo,
+                                          bool with_lo) {
 #pragma unroll
   for (int j = 0; j < P_WCH; ++j) {
-    const int cg = cg0 + 4 * j;
-    if (cg < ncg) store_split4(hi, lo, row, cg, sbo, wr[j], with_lo);
+    if (pc.goff[j] == -2) continue;
+    const float4 x = wr[j];
+    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    *reinterpret_cast<float4*>(hi + pc.soff[j]) = h;
+    if (with_lo) *reinterpret_cast<float4*>(lo + pc.soff[j]) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
   }
 }
 
@@ -1540,8 +1534,8 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
     __syncthreads();                               // the previous chunk is drained: the A operand may be rebuilt
     if (warp < P_NWE) {
       // H2' chunk -> TMEM (A operand of every MMA of this chunk: lane = query row, column = k; hi and lo parts).
-      // A from TMEM instead of shared memory: an SS-mode M128 x N64 x K8 tf32 MMA reads 4 KB of A + 2 KB of B per
-      // 32-cycle slot, more than the 128 B/cycle the shared memory delivers -- the kernel was operand-feed-bound.
+      // A from TMEM instead of shared memory: an SS-mode M128 x K8 tf32 MMA reads 4 KB of A per slot on top of B,
+      // more than the 128 B/cycle the shared memory delivers -- with A in shared memory the kernel was feed-bound.
       const int q4 = warp & 3, cpart = warp >> 2;
       const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
       const int brow = q4 * 32 + lane;
@@ -1584,56 +1578,69 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
       const int q4 = warp & 3, cpart = warp >> 2;
       const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
       const int brow = q4 * 32 + lane;
-      const int lrow = (warp & 7) * 8 + (lane & 7), cgb = (warp >> 3) * 16 + (lane >> 3);   // loader mapping (see p_load_w)
       const bool rowv = brow < nb;
       float tau = __int_as_float(0x7f800000);
       if (a.filter && rowv) tau = a.tau[(size_t)(b0 + brow) * a.tau_stride];
       const int nsub = (int)gridDim.x * 4, sub = (int)blockIdx.x * 4 + cpart;
       const size_t sub_base = ((size_t)(b0 + brow) * nsub + sub) * (size_t)a.cap_sub;
       int my_cnt = 0;
-      auto tile_v0 = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) * a.tile_stride) * PN; };
-      // W' tiles travel global -> registers -> shared memory; two register sets keep the loads of tiles i+2 / i+3
-      // in flight for two whole iterations (issued after the epilogue of the tile whose set they reuse)
-      float4 wr0[P_WCH], wr1[P_WCH];
+      // loader role of this thread
+      const int lrow = warp * 8 + (lane & 7);
+      PChunks pc;
+#pragma unroll
+      for (int j = 0; j < P_WCH; ++j) {
+        const int cg = (lane >> 3) + 4 * j, c = cg * 4;
+        pc.goff[j] = (cg < ncg) ? ((c + 3 < a.H) ? lrow * a.H + c : (c == a.H ? -1 : -3)) : -2;
+        pc.soff[j] = (uint32_t)(lrow >> 3) * g.wb_sbo + (uint32_t)cg * CORE + (uint32_t)(lrow & 7) * 16u;
+      }
+      const int tile_step = (int)gridDim.x * a.tile_stride * PN;           // items between two tiles of this CTA
+      const int v_first = (int)blockIdx.x * a.tile_stride * PN;
+      auto load_tile = [&](float4* wr, int v0) {
+        p_load_w(wr, pc, a.Wd3 + (size_t)v0 * a.H, a.bd3 + v0 + lrow, v0 + lrow < a.Vloc);
+      };
+      float4 wr[P_WCH];
       for (int p = 0; p < 2 && p < n_my; ++p) {
-        p_load_w(wr0, a, tile_v0(p), lrow, cgb, ncg);
-        p_store_w(wr0, wst + 2 * p * wb_bytes, wst + (2 * p + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
+        load_tile(wr, v_first + p * tile_step);
+        p_store_w(wr, pc, wst + 2 * p * wb_bytes, wst + (2 * p + 1) * wb_bytes, with_lo);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_ready[p]);
       }
-      if (n_my > 2) p_load_w(wr0, a, tile_v0(2), lrow, cgb, ncg);
-      if (n_my > 3) p_load_w(wr1, a, tile_v0(3), lrow, cgb, ncg);
-      auto body = [&](const int i, float4 (&wr)[P_WCH]) {
+      if (n_my > 2) load_tile(wr, v_first + 2 * tile_step);
+      for (int i = 0; i < n_my; ++i) {
         const int s = i & 1;
-        mbar_wait(&bar_mma[s], s ? ph1 : ph0);
+        const int v0 = v_first + i * tile_step;
+        mbar_wait(&bar_mma[s], s ? ph1 : ph0);       // logits of tile i in TMEM buffer s, stage s free again
         if (s) ph1 ^= 1; else ph0 ^= 1;
         tc_fence_after();
         uint32_t zr[P_CW];
-        TmemIO<P_CW>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW), zr);
-        TmemIO<P_CW>::ld_wait(zr);
+        TmemIO<16>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW), zr);
+        TmemIO<16>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW + 16), zr + 16);
+        TmemIO<16>::ld_wait(zr);
+        TmemIO<16>::ld_wait(zr + 16);
         tc_fence_before();
         if (i + 2 < n_my) {
-          p_store_w(wr, wst + 2 * s * wb_bytes, wst + (2 * s + 1) * wb_bytes, g.wb_sbo, lrow, cgb, ncg, with_lo);
+          p_store_w(wr, pc, wst + 2 * s * wb_bytes, wst + (2 * s + 1) * wb_bytes, with_lo);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_ready[s]);
+          if (i + 3 < n_my) load_tile(wr, v0 + 3 * tile_step);
         }
         // ---- epilogue of tile i
-        const int v0 = tile_v0(i);
-        const int vm = a.Vloc - v0 - cpart * P_CW;               // valid columns among this thread's 16
+        const int c0 = cpart * P_CW;
+        const int vm = a.Vloc - v0 - c0;                         // valid columns among this thread's 32
         if (a.filter) {
-          bool any = false;
+          float zmax = __uint_as_float(zr[0]);
 #pragma unroll
-          for (int j = 0; j < P_CW; ++j) any |= (__uint_as_float(zr[j]) > tau);
-          if (any) {
+          for (int j = 1; j < P_CW; ++j) zmax = fmaxf(zmax, __uint_as_float(zr[j]));
+          if (zmax > tau) {
 #pragma unroll
             for (int j = 0; j < P_CW; ++j) {
               const float z = __uint_as_float(zr[j]);
               if (z > tau && j < vm) {
                 if (my_cnt < a.cap_sub) {
                   a.cand_val[sub_base + my_cnt] = z;
-                  a.cand_idx[sub_base + my_cnt] = a.v_begin + v0 + cpart * P_CW + j;
+                  a.cand_idx[sub_base + my_cnt] = a.v_begin + v0 + c0 + j;
                 }
                 ++my_cnt;
               }
@@ -1641,7 +1648,7 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
           }
         } else if (rowv) {
           const int colbase = a.out_by_visit ? ((int)blockIdx.x + i * (int)gridDim.x) * PN : v0;
-          float* orow = a.out + (size_t)(b0 + brow) * a.ldo + colbase + cpart * P_CW;
+          float* orow = a.out + (size_t)(b0 + brow) * a.ldo + colbase + c0;
           if (vm >= P_CW && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < P_CW; j += 4) {
@@ -1665,11 +1672,6 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
             }
           }
         }
-        if (i + 4 < n_my) p_load_w(wr, a, tile_v0(i + 4), lrow, cgb, ncg);
-      };
-      for (int i = 0; i < n_my; i += 2) {
-        body(i, wr0);
-        if (i + 1 < n_my) body(i + 1, wr1);
       }
       if (a.filter && rowv) a.cnt[(size_t)(b0 + brow) * nsub + sub] = my_cnt;
     }

@@ -334,11 +334,11 @@ struct TopkPlan {
 };
 static TopkPlan make_plan(int B, int Vloc, int k) {
   TopkPlan p;
-  p.n_tiles = (Vloc + 63) / 64;
-  p.n_samp = std::min(1024, p.n_tiles / 8);
-  p.ok = p.n_samp >= 64 && k <= 1024;          // Vloc >= 32768; below that the dense path is as cheap
+  p.n_tiles = (Vloc + 127) / 128;
+  p.n_samp = std::min(512, p.n_tiles / 8);
+  p.ok = p.n_samp >= 32 && k <= 1024;          // Vloc >= 32768; below that the dense path is as cheap
   p.stride = p.ok ? p.n_tiles / p.n_samp : 1;
-  p.S = p.n_samp * 64;
+  p.S = p.n_samp * 128;
   p.T = std::max(1024, std::min(4096, 4 * (k + 256)));
   p.cap = TK_CAP;
   p.J = p.ok ? std::max(8, (int)(((int64_t)p.T * p.S + Vloc - 1) / Vloc)) : 8;
@@ -346,10 +346,10 @@ static TopkPlan make_plan(int B, int Vloc, int k) {
   dec_out_select_grid(B, p.n_tiles, &gx, &gy);
   p.nsub = 4 * gx;
   // expected T / nsub candidates per sub-list; room for 8 sigma of a Poisson count, and for the worst clustering of
-  // twice T candidates in consecutive items (16 per visited tile part)
+  // twice T candidates in consecutive items (32 per visited tile part)
   const double e = (double)p.T / p.nsub;
   const int stat = (int)(e + 8.0 * sqrt(e) + 8.0);
-  const int clus = 16 * ((2 * p.T / 64 + gx - 1) / gx) + 8;
+  const int clus = 32 * ((2 * p.T / 128 + gx - 1) / gx) + 8;
   p.cap_sub = std::max(stat, clus);
   return p;
 }
