@@ -243,7 +243,7 @@ class AAEEngine(object):
         self.disc_grads = z(B, 2 * (2 * H + 1))
         # pinned staging ring for the host-buffer (end-to-end) entry
         self._pin = []
-        for _ in range(4):
+        for _ in range(8):
             self._pin.append(dict(
                 indptr=torch.zeros(B + 1, dtype=torch.int32).pin_memory(),
                 indices=torch.zeros(nnz, dtype=torch.int32).pin_memory(),

@@ -1448,6 +1448,9 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
 // Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
 // (evaluation.py:183-199, 20-58).
 // ---------------------------------------------------------------------------------------------
+#ifndef K5_LOAD_LATE
+#define K5_LOAD_LATE 0
+#endif
 constexpr int PN = 128;                // items per tile
 constexpr int P_NWE = 16;              // loader / epilogue warps
 constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
@@ -1624,7 +1627,9 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_ready[s]);
+#if !K5_LOAD_LATE
           if (i + 3 < n_my) load_tile(wr, v0 + 3 * tile_step);
+#endif
         }
         // ---- epilogue of tile i
         const int c0 = cpart * P_CW;
@@ -1672,6 +1677,11 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
             }
           }
         }
+#if K5_LOAD_LATE
+        // W'(i+3): issued last, so that its L2/HBM latency runs under the wait for the MMAs of tile i+1 instead of in
+        // front of the epilogue (the compiler shares load scoreboards: an epilogue behind the loads waits for them)
+        if (i + 3 < n_my) load_tile(wr, v0 + 3 * tile_step);
+#endif
       }
       if (a.filter && rowv) a.cnt[(size_t)(b0 + brow) * nsub + sub] = my_cnt;
     }

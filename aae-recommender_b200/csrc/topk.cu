@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
                                                                  int k, int idx_offset,
                                                                  const int32_t* __restrict__ idx_map,
                                                                  const int32_t* __restrict__ n_valid,
-                                                                 int32_t* __restrict__ idx_out,
+                                                                 int skip_upto, int32_t* __restrict__ idx_out,
                                                                  float* __restrict__ val_out) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(sm_raw);          // [TK_CAP]
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
   const int rowi = blockIdx.x;
   const float* row = scores + (size_t)rowi * lds;
   if (n_valid) n = max(0, min(n, n_valid[rowi]));     // only the first n_valid[row] entries of the row are live
+  if (n <= skip_upto) return;                         // rows this short are ranked by cand_sort_small_kernel
   const int kk = min(k, n);
   int total = 0;
   const bool direct_ids = idx_map != nullptr && n <= TK_CAP;   // composites carry the item id itself
@@ -283,6 +284,39 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* _
   }
 }
 
+// Final ranking of a short candidate list (the common case of the fused predict path: ~1.4 k live candidates per row):
+// 256 threads and 16 KB of shared memory per row instead of 1024 threads and 96 KB, so that eight rows are sorted per
+// SM at a time.  Rows with more than CS_CAP live candidates are left to row_topk_kernel (skip_upto = CS_CAP there).
+// Composites carry the item id: descending score, ties by lower id -- the same order as row_topk_kernel.
+constexpr int CS_THREADS = 256, CS_CAP = 2048;
+__global__ void __launch_bounds__(CS_THREADS) cand_sort_small_kernel(const float* __restrict__ val,
+                                                                     const int32_t* __restrict__ idx, int64_t lds,
+                                                                     const int32_t* __restrict__ n_valid, int k,
+                                                                     int32_t* __restrict__ idx_out,
+                                                                     float* __restrict__ val_out) {
+  __shared__ unsigned long long buf[CS_CAP];
+  const int rowi = blockIdx.x;
+  const int n = n_valid[rowi];
+  if (n > CS_CAP) return;
+  int npow = 2;
+  while (npow < n) npow <<= 1;
+  for (int i = threadIdx.x; i < npow; i += CS_THREADS)
+    buf[i] = (i < n) ? compose(f2key(val[(size_t)rowi * lds + i]), (uint32_t)idx[(size_t)rowi * lds + i]) : 0ull;
+  bitonic_desc(buf, npow);
+  const int kk = min(k, n);
+  for (int i = threadIdx.x; i < k; i += CS_THREADS) {
+    int32_t id = -1;
+    float v = -FLT_MAX;
+    if (i < kk) {
+      const unsigned long long c = buf[i];
+      id = (int32_t)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull));
+      v = key2f((uint32_t)(c >> 32));
+    }
+    idx_out[(size_t)rowi * k + i] = id;
+    if (val_out) val_out[(size_t)rowi * k + i] = v;
+  }
+}
+
 // Threshold of the fused predict path: (approximately) the J-th largest of the row's S sample scores.  Every
 // thread keeps the 4 largest of its strided share in registers, the 256 x 4 survivors are sorted in shared memory
 // and the J-th is taken.  A thread that holds more than 4 of the row's top J makes the result slightly LOWER than
@@ -365,14 +399,15 @@ int64_t aae_topk_work_bytes(int B, int k) { return 16; }
 
 static int launch_row_topk(const float* scores, int64_t lds, int B, int n, int k, int idx_offset,
                            const int32_t* idx_map, int32_t* idx_out, float* val_out, cudaStream_t s,
-                           const int32_t* n_valid = nullptr) {
+                           const int32_t* n_valid = nullptr, int skip_upto = -1) {
   size_t smem = sizeof(unsigned long long) * (TK_CAP + TK_SAMPLE);
   cudaError_t e = cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("row_topk: %s", cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
-  row_topk_kernel<<<B, TK_THREADS, smem, s>>>(scores, lds, n, k, idx_offset, idx_map, n_valid, idx_out, val_out);
+  row_topk_kernel<<<B, TK_THREADS, smem, s>>>(scores, lds, n, k, idx_offset, idx_map, n_valid, skip_upto, idx_out,
+                                              val_out);
   return check_launch("row_topk");
 }
 
@@ -451,7 +486,10 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
       n_bad);
   rc = check_launch("cand_finish");
   if (rc) return rc;
-  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, tot);
+  cand_sort_small_kernel<<<B, CS_THREADS, 0, s>>>(cand_val, cand_idx, p.cap, tot, k, idx_out, val_out);
+  rc = check_launch("cand_sort_small");
+  if (rc) return rc;
+  return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, tot, CS_CAP);
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
