@@ -268,7 +268,12 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, max(args.warmup, 3)
     n_batches = min(K + W, 64)
@@ -484,7 +489,10 @@ def run_ours(args):
         "clocks": clocks,
     }
     line.update(extra)
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
