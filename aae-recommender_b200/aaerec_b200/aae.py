@@ -145,6 +145,7 @@ class AdversarialAutoEncoder(object):
         self.use_graph = use_graph
         self.engine = None
         self._mode_train = True
+        self.predict_batch_size = 1024   # query rows per launch of predict_topk (>= batch_size)
         self.record_losses = False   # True: keep every step's (R, D, G) in .loss_history (forces a sync per step)
         # supported envelope; everything else fails loudly, there is no fallback path
         if self.prior != 'gauss':
@@ -323,7 +324,8 @@ class AdversarialAutoEncoder(object):
         return self
 
     # -- prediction
-    def _iter_batches(self, X, condition_data):
+    def _iter_batches(self, X, condition_data, batch_size=None):
+        batch_size = batch_size or self.batch_size
         use_condition = _check_conditions(self.conditions, condition_data)
         self.eval()
         X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
@@ -333,8 +335,8 @@ class AdversarialAutoEncoder(object):
         n = X.shape[0]
         indptr = X.indptr
         indices = X.indices.astype(np.int32, copy=False)
-        for start in range(0, n, self.batch_size):
-            end = min(start + self.batch_size, n)
+        for start in range(0, n, batch_size):
+            end = min(start + batch_size, n)
             lo, hi = int(indptr[start]), int(indptr[end])
             ip = (indptr[start:end + 1] - lo).astype(np.int32)
             B, _ = self.engine.upload_csr(ip, indices[lo:hi], cond_all[start:end] if cond_all is not None else None)
@@ -363,9 +365,11 @@ class AdversarialAutoEncoder(object):
         kk = min(k, eng.V)
         idx = np.empty((n, kk), dtype=np.int64)
         val = np.empty((n, kk), dtype=np.float32) if return_scores else None
-        scratch = torch.empty(self.batch_size, eng.Vloc, dtype=torch.float32, device=eng.dev)
-        for start, end, B in self._iter_batches(X, condition_data):
-            i, v = eng.topk(B, kk, scratch=scratch, mask_known=mask_known)
+        # rows are independent in eval mode: rank in query batches of >= 1024 rows whatever the training batch size
+        # (the fused path keeps no [B,V] matrix, so the batch only sizes the candidate lists)
+        pb = max(self.batch_size, self.predict_batch_size)
+        for start, end, B in self._iter_batches(X, condition_data, batch_size=pb):
+            i, v = eng.topk(B, kk, mask_known=mask_known)
             idx[start:end] = i.cpu().numpy()
             if return_scores:
                 val[start:end] = v.cpu().numpy()
