@@ -225,8 +225,12 @@ class AAEEngine(object):
         i32 = dict(dtype=torch.int32, device=self.dev)
         H, Cc, Cp, D = self.H, self.C, self.Cp, self.D
         z = lambda *s: torch.zeros(*s, **f32)
-        self.indptr = torch.zeros(B + 1, **i32)
-        self.indices = torch.zeros(nnz, **i32)
+        # CSR rows of the batch, packed: indptr block (padded to 16 bytes) directly followed by the column indices, so
+        # that the host-buffer entry moves a batch with ONE H2D copy (aae_upload_batch)
+        off = (B + 1 + 3) // 4 * 4
+        self._batch = torch.zeros(off + nnz, **i32)
+        self.indptr = self._batch[: B + 1]
+        self.indices = self._batch[off: off + nnz]
         self.cond = z(B, max(D, 1))
         self.masks = z(12, B, H)
         self.z_real = z(B, Cc)
@@ -244,9 +248,9 @@ class AAEEngine(object):
         # pinned staging ring for the host-buffer (end-to-end) entry
         self._pin = []
         for _ in range(8):
+            packed = torch.zeros(off + nnz, dtype=torch.int32).pin_memory()
             self._pin.append(dict(
-                indptr=torch.zeros(B + 1, dtype=torch.int32).pin_memory(),
-                indices=torch.zeros(nnz, dtype=torch.int32).pin_memory(),
+                packed=packed, indptr=packed[: B + 1], indices=packed[off: off + nnz],
                 cond=torch.zeros(B, max(D, 1), dtype=torch.float32).pin_memory(),
                 ev=None))
         self._pin_i = 0
