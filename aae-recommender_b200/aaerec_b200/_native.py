@@ -92,6 +92,8 @@ _SIGS = {
     "aae_tc_selftest": (I, [I, P, P, P, I, P]),
     "aae_upload_batch": (I, [P, P, I, I, P, P, P]),
     "aae_finish_losses": (I, [P, D, I, P, P]),
+    "aae_copy_words": (I, [P, P, I64, P]),
+    "aae_copy_words_sel": (I, [P, P, P, P, I64, P, I, P]),
     "aae_peer_buffer_bytes": (I64, [I64]),
     "aae_peer_alloc": (I, [I64, C.POINTER(P), C.c_char_p]),
     "aae_peer_open": (I, [C.c_char_p, C.POINTER(P)]),

@@ -262,13 +262,11 @@ class AdversarialAutoEncoder(object):
     def _partial_fit_csr(self, indptr, indices, cond_rows):
         eng = self.engine
         self.train()
-        B, _ = eng.upload_csr(indptr, indices, cond_rows)
-        injected = False
+        draws = None
         if self.rng == 'oracle':
+            B = int(indptr.shape[0]) - 1
             draws = _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale, self.adversarial)
-            eng.set_rng_draws(B, draws)
-            injected = True
-        eng.train_step(B, injected=injected)
+        eng.train_step_host(indptr, indices, cond_rows, injected=draws is not None, rng_draws=draws)
 
     def losses(self):
         """(recon, disc, gen) losses of the last step -- a device->host read (synchronises)."""

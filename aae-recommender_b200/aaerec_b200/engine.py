@@ -254,6 +254,14 @@ class AAEEngine(object):
                 cond=torch.zeros(B, max(D, 1), dtype=torch.float32).pin_memory(),
                 ev=None))
         self._pin_i = 0
+        # zero-copy staging for train_step_host: two pinned (mapped) slots that the step's graph reads / writes itself
+        self._zc = []
+        for _ in range(2):
+            self._zc.append(dict(packed=torch.zeros(off + nnz, dtype=torch.int32).pin_memory(),
+                                 cond=torch.zeros(B, max(D, 1), dtype=torch.float32).pin_memory(),
+                                 losses=torch.zeros(4, dtype=torch.float32).pin_memory(), ev=None))
+        self._zc_i = 0
+        self._zc_off = off
         self._ws_B, self._ws_nnz = B, nnz
 
     # ------------------------------------------------------------------ parameters
@@ -543,38 +551,86 @@ class AAEEngine(object):
              1, ptr(self.w1_last), s())
         self._join()
 
+    def _run(self, key, enqueue):
+        """Enqueue ``enqueue()`` eagerly, or (graph mode) capture it once per ``key`` and replay the graph."""
+        if not self.use_graph:
+            enqueue()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            # warm up once eagerly so that lazy module loading / attribute setting is done
+            snap = self._snapshot()
+            enqueue()
+            torch.cuda.synchronize(self.dev)
+            self._restore(snap)
+            g = torch.cuda.CUDAGraph()
+            # no cyclic garbage collection while capturing: collecting an old engine's CUDA graph in the
+            # middle of a capture invalidates it (torch collects once on entering the capture)
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, stream=self._cap_stream):
+                    enqueue()
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            self._restore(snap)
+            self._graphs[key] = g
+        g.replay()
+
     def train_step(self, B, injected=False):
         """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses
         (R, D, G) land in ``self.losses`` (device float32[3])."""
         if B <= 0:
             return
-        if not self.use_graph:
-            self._enqueue_step(B, injected)
-        else:
-            key = (B, bool(injected))
-            g = self._graphs.get(key)
-            if g is None:
-                # warm up once eagerly so that lazy module loading / attribute setting is done
-                snap = self._snapshot()
-                self._enqueue_step(B, injected)
-                torch.cuda.synchronize(self.dev)
-                self._restore(snap)
-                g = torch.cuda.CUDAGraph()
-                # no cyclic garbage collection while capturing: collecting an old engine's CUDA graph in the
-                # middle of a capture invalidates it (torch collects once on entering the capture)
-                gc_was_on = gc.isenabled()
-                gc.disable()
-                try:
-                    with torch.cuda.graph(g, stream=self._cap_stream):
-                        self._enqueue_step(B, injected)
-                finally:
-                    if gc_was_on:
-                        gc.enable()
-                self._restore(snap)
-                self._graphs[key] = g
-            g.replay()
+        self._run((B, bool(injected)), lambda: self._enqueue_step(B, injected))
         self.steps_done += 1
         self._w1_dirty = True
+
+    def train_step_host(self, indptr_np, indices_np, cond_np=None, injected=False, rng_draws=None):
+        """One partial_fit straight from host CSR rows (int32, row-relative indptr): the end-to-end entry.  The batch
+        is written into one of two pinned slots and moved with one H2D copy; the step's CUDA graph itself pushes the
+        three losses back into the slot's pinned ``losses`` (``aae_copy_words_sel``) -- no D2H hop behind the step.  Returns the slot: ``slot['losses']`` is valid once ``slot['ev']`` has completed;
+        ``slot['prev_losses']`` holds the (complete) losses of the step that used the slot before, two steps ago."""
+        B = int(indptr_np.shape[0]) - 1
+        nnz = int(indptr_np[-1])
+        if B <= 0:
+            return None
+        self._ensure_ws(B, nnz)
+        si = self.steps_done & 1          # the graph's copy kernels pick the slot from the device step counter: t = steps_done + 1
+        slot = self._zc[si]
+        slot["prev_losses"] = None
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()           # the launch that last read this slot is done ...
+            slot["prev_losses"] = slot["losses"][:3].clone()     # ... and these are its losses (step i-2)
+        off = self._zc_off
+        pk = slot["packed"].numpy()
+        pk[: B + 1] = indptr_np
+        pk[off: off + nnz] = indices_np[:nnz]
+        if self.D:
+            slot["cond"][:B].numpy()[:] = cond_np
+        if rng_draws is not None:
+            self.set_rng_draws(B, rng_draws)
+
+        z0, z1, st = self._zc[0], self._zc[1], ptr(self.state)
+        # batch in: ONE copy-engine transfer of the packed slot (a kernel reading the mapped slot over PCIe was measured
+        # at ~100 MB/s: +120 us per 8 KB batch); losses out: written into the slot's pinned memory by the graph itself
+        call("aae_upload_batch", ptr(slot["packed"]), ptr(slot["packed"][off:]), B, nnz, ptr(self.indptr),
+             ptr(self.indices), self._stream())
+        if self.D:
+            self.cond[:B].copy_(slot["cond"][:B], non_blocking=True)
+
+        def enqueue():
+            self._enqueue_step(B, injected)
+            call("aae_copy_words_sel", ptr(self.losses), ptr(self.losses), ptr(z0["losses"]), ptr(z1["losses"]), 3, st, 0,
+                 self._stream())
+        self._run((B, bool(injected), "host"), enqueue)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        slot["ev"] = ev
+        self.steps_done += 1
+        self._w1_dirty = True
+        return slot
 
     def flush_w1(self):
         """Apply every pending zero-gradient Adam step to W1t (time-blocked policy): after this the weights are

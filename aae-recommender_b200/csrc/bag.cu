@@ -3,6 +3,7 @@
 // Reference: aaerec/aae.py:132-135 (F.normalize(p=1) + lin1), :703/:741 (backward), :706/:741
 // (enc_optim / gen_optim steps over the same parameters).
 #include <stdlib.h>
+#include <algorithm>
 #include <stddef.h>
 #include "common.cuh"
 
@@ -790,6 +791,45 @@ int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, in
   }
   return AAE_OK;
 }
+// 4-byte words from src to dst; either side may be pinned (mapped) host memory -- used INSIDE the step's CUDA graph
+// instead of memcpy nodes: a kernel-to-kernel edge costs ~1.5 us, a copy-engine hop several.
+__global__ void __launch_bounds__(256) copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                         int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+int aae_copy_words(const void* src, void* dst, int64_t n_words, void* stream) {
+  AAE_REQUIRE(src && dst && n_words >= 0, "bad argument");
+  if (n_words == 0) return AAE_OK;
+  int blocks = (int)std::min<int64_t>(2 * sm_count(), (n_words + 255) / 256);
+  copy_words_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(src),
+                                                           reinterpret_cast<uint32_t*>(dst), n_words);
+  return check_launch("copy_words");
+}
+
+// Same copy, with the pinned slot chosen ON THE DEVICE from the step counter: slot = (t + bias) & 1.  One captured
+// graph then serves both slots (alternating between two instantiated graphs costs ~100 us per launch).
+__global__ void __launch_bounds__(256) copy_words_sel_kernel(const uint32_t* __restrict__ src0,
+                                                             const uint32_t* __restrict__ src1, uint32_t* dst0,
+                                                             uint32_t* dst1, int64_t n,
+                                                             const aae_step_state* __restrict__ st, int bias) {
+  const int sel = (st->t + bias) & 1;
+  const uint32_t* __restrict__ src = sel ? src1 : src0;
+  uint32_t* __restrict__ dst = sel ? dst1 : dst0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+int aae_copy_words_sel(const void* src0, const void* src1, void* dst0, void* dst1, int64_t n_words,
+                       const aae_step_state* st, int bias, void* stream) {
+  AAE_REQUIRE(src0 && src1 && dst0 && dst1 && st && n_words >= 0, "bad argument");
+  if (n_words == 0) return AAE_OK;
+  int blocks = (int)std::min<int64_t>(2 * sm_count(), (n_words + 255) / 256);
+  copy_words_sel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(src0), reinterpret_cast<const uint32_t*>(src1),
+      reinterpret_cast<uint32_t*>(dst0), reinterpret_cast<uint32_t*>(dst1), n_words, st, bias);
+  return check_launch("copy_words_sel");
+}
+
 int aae_finish_losses(const double* sums, double n_total, int B, float* out, void* stream) {
   AAE_REQUIRE(sums && out, "null pointer");
   finish_losses_kernel<<<1, 1, 0, as_stream(stream)>>>(sums, n_total, B, out);

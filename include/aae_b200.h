@@ -335,6 +335,15 @@ int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int spl
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);
 
+/* Copy n 4-byte words with a kernel; src or dst may be pinned (mapped) host memory.  Lets the host-buffer entry live
+ * INSIDE the step's CUDA graph (batch in, losses out) without copy-engine hops; the pinned source must stay
+ * untouched until the launch that reads it has completed. */
+int aae_copy_words(const void* src, void* dst, int64_t n_words, void* stream);
+/* The same with two source / destination candidates, chosen on the device: index (st->t + bias) & 1.  One captured
+ * graph then alternates between two pinned slots (batch in: bias -1 before the step; losses out: bias 0 after it). */
+int aae_copy_words_sel(const void* src0, const void* src1, void* dst0, void* dst1, int64_t n_words,
+                       const aae_step_state* st, int bias, void* stream);
+
 /* ---- step timeline (profiling aid) ---------------------------------------------------------------
  * With a device buffer of aae_trace_slots() uint64 installed, block 0 of every kernel of the step writes
  * %globaltimer (ns) at its start (slot 2*id) and end (slot 2*id+1); ids in the order: batch_prepare,
