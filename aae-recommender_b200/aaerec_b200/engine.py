@@ -101,7 +101,7 @@ class AAEEngine(object):
         # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
         self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "2"))
         # W1t Adam policy: rows outside the batch are swept in G time-blocked groups (1 = dense sweep every step)
-        self.w1_groups = max(1, min(32, int(os.environ.get("AAE_B200_W1_GROUPS", "4"))))
+        self.w1_groups = max(1, min(32, int(os.environ.get("AAE_B200_W1_GROUPS", "8"))))
         self.impl = self._pick_impl(impl)
         self.steps_done = 0
         self._launches_per_step = 0
