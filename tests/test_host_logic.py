@@ -133,3 +133,19 @@ def test_peer_exchange_buffer_layout():
     header = (4 * 32 * 8 * 4 + 4 * 4 + 4 * 4 + 32 + 255) // 256 * 256
     assert lib.aae_peer_buffer_bytes(n) == header + 8 * slot
     assert lib.aae_peer_buffer_bytes(0) == 0
+
+
+def test_fused_topk_envelope_and_workspace():
+    # aae_predict_topk_work_bytes is a pure host function: 0 outside the fused envelope (small shards, huge k),
+    # positive and growing with the batch inside it
+    from aaerec_b200 import _native as N
+    lib = N.load()
+    assert lib.aae_predict_topk_work_bytes(100, 20000, 100) == 0          # shard below 32,768 items: dense path
+    assert lib.aae_predict_topk_work_bytes(100, 200000, 2000) == 0        # k above 1024
+    assert lib.aae_predict_topk_work_bytes(0, 200000, 100) == 0
+    a = lib.aae_predict_topk_work_bytes(100, 200000, 100)
+    b = lib.aae_predict_topk_work_bytes(1000, 200000, 100)
+    c = lib.aae_predict_topk_work_bytes(1000, 2000000, 100)
+    assert 0 < a < b <= c
+    # the score matrix the fused path avoids would be far larger than its whole workspace
+    assert c < 1000 * 2000000 * 4 / 8
