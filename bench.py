@@ -368,7 +368,11 @@ def run_ours(args):
                 "kernels": {k: {"ms": v["sec"] * 1e3, "GBps": v["bytes"] / v["sec"] / 1e9,
                                 "frac": v["bytes"] / v["sec"] / 1e9 / hbm_peak} for k, v in kern.items()},
                 "step_algorithmic_bytes": 64.0 * Vl * H,
-                "step_frac": 64.0 * Vl * H / (sec / K) / 1e9 / hbm_peak}
+                "step_frac": 64.0 * Vl * H / (sec / K) / 1e9 / hbm_peak,
+                # what the time-blocked (exact) W1 policy really moves per step: lin3 + its Adam state once, 1/G of the
+                # W1 rows with both Adam states
+                "step_moved_bytes": (24.0 + 40.0 / eng.w1_groups) * Vl * H,
+                "step_frac_moved": (24.0 + 40.0 / eng.w1_groups) * Vl * H / (sec / K) / 1e9 / hbm_peak}
     # ---------------- predict: reconstruction + masked top-100 of a query batch (the metric's second half) ----------
     extra = {}
     if not args.no_extra:
@@ -442,7 +446,9 @@ def run_ours(args):
             "config": {"workload": "mpd-shaped (BASELINE configs[3]): V=%d items, batch %d sets, item-sharded x%d"
                                    % (Vm, Bm, world)},
             "step_algorithmic_bytes_per_gpu": 64.0 * engm.Vloc * H,
-            "step_frac": 64.0 * engm.Vloc * H / (secm / Km) / 1e9 / hbm_peak}
+            "step_frac": 64.0 * engm.Vloc * H / (secm / Km) / 1e9 / hbm_peak,
+            "step_moved_bytes_per_gpu": (24.0 + 40.0 / engm.w1_groups) * engm.Vloc * H,
+            "step_frac_moved": (24.0 + 40.0 / engm.w1_groups) * engm.Vloc * H / (secm / Km) / 1e9 / hbm_peak}
         Xq = synth_sets(args.predict_batch, Vm, 25, 1, 100, seed=4321)
         pr = predict_leg(engm, Xq, 100, 5, barrier, stream, tf_peak)
         ps, pe = max_over_ranks(pr["sec"], pr["sec_e2e"])
