@@ -149,3 +149,28 @@ def test_fused_topk_envelope_and_workspace():
     assert 0 < a < b <= c
     # the score matrix the fused path avoids would be far larger than its whole workspace
     assert c < 1000 * 2000000 * 4 / 8
+
+
+def test_reference_arm_prints_contract_line():
+    # bench.py --impl reference runs the CPU port of the reference's algorithm (no GPU needed) and prints ONE JSON
+    # line with the contract's keys
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "econbiz",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "sets/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_peer_struct_layout():
+    import ctypes
+    from aaerec_b200 import _native as N
+    assert ctypes.sizeof(N.AaePeers) == 8 * 8 + 8      # void* base[8]; int rank, world
