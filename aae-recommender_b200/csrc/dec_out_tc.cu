@@ -1438,13 +1438,16 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
 // ---------------------------------------------------------------------------------------------
 // K5: pipelined scores kernel with a selection epilogue (predict + ranking without the [B,V] round trip).
 //
-// One CTA = one chunk of 128 query rows (Hb resident in shared memory) x a strided subset of 64-item tiles.
-// Warp 16 issues the MMAs; warps 0-15 are loaders (W' tile -> tf32 hi/lo operand, two shared-memory stages) and
-// epilogue (two TMEM accumulator buffers): while tile i is drained and tile i+2 is staged, the tensor pipe runs
-// tile i+1.  Per stage s one mbarrier pair: ready[s] (one arrival per loader warp: stage filled AND accumulator s
-// drained) and mma[s] (tcgen05.commit: logits of the tile in TMEM, stage s free again).
+// One CTA = one chunk of 128 query rows x a strided subset of 128-item tiles.  The A operand (the H2' chunk, hi and lo
+// parts) lives in TMEM for the whole chunk (ts-form MMAs: lane = query row, column = k): an SS-mode M128 MMA would
+// re-read 4 KB of A from shared memory per instruction, more than the 128 B/cycle shared memory delivers.
+// Warp 16 issues the MMAs (39 x M128.N128.K8 per tile with the 3xTF32 split); warps 0-15 are loaders (W' tile -> tf32
+// hi/lo K-major operand, two 106 KB shared-memory stages) and epilogue (two 128-column TMEM accumulator buffers):
+// while tile i is drained and tile i+2 is staged, the tensor pipe runs tile i+1.  Per stage s one mbarrier pair:
+// ready[s] (one arrival per loader warp: stage filled AND accumulator s drained) and mma[s] (tcgen05.commit: logits
+// of the tile in TMEM, stage s free again).
 // Epilogues: DENSE (scores, optionally sigmoid, to out[b, col]; col = item, or the visit order for the threshold
-// sample) and FILTER (z > tau[b]: append (z, item) to the row's candidate list; ~0.05 % of the elements).
+// sample) and FILTER (z > tau[b]: append (z, item) to a private sub-list of the row; ~0.07 % of the elements).
 // Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
 // (evaluation.py:183-199, 20-58).
 // ---------------------------------------------------------------------------------------------
