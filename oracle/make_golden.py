@@ -41,7 +41,7 @@ def _state(model):
 
 
 def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0, mean_len=6,
-             store_weights=True, k=10, adversarial=True):
+             store_weights=True, k=10, adversarial=True, model_kwargs=None):
     aae = ref.aae
     cls = aae.AdversarialAutoEncoder if adversarial else aae.AutoEncoder
     steps_per_fit = ("ae_step", "disc_step", "gen_step") if adversarial else ("ae_step",)
@@ -84,7 +84,7 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
         torch.manual_seed(42)     # aae.py:27 executes this at import; redo it per case
         np.random.seed(42)
         model = cls(n_hidden=H, n_code=C, batch_size=B, n_epochs=epochs, dropout=dropout, conditions=conditions,
-                    verbose=False)
+                    verbose=False, **(model_kwargs or {}))
         # capture the initial weights: replay the same construction order under the same seed
         from oracle.aae_oracle import init_params
         init = {k_: v.numpy().copy() for k_, v in init_params(V, H, C, C + cond_dim, seed=42).items()}
@@ -103,6 +103,10 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
     out = dict(
         n=n, V=V, H=H, C=C, B=B, epochs=epochs, dropout=np.asarray(dropout, dtype=np.float64),
         cond_dim=cond_dim, k=k, adversarial=int(adversarial),
+        normalize_inputs=int((model_kwargs or {}).get("normalize_inputs", True)),
+        prior_scale=np.float64((model_kwargs or {}).get("prior_scale") or 0.0),
+        gen_lr=np.float64((model_kwargs or {}).get("gen_lr", 0.001)),
+        reg_lr=np.float64((model_kwargs or {}).get("reg_lr", 0.001)),
         indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32),
         losses=np.asarray(losses, dtype=np.float64).reshape(-1, len(steps_per_fit)),
         pred=pred.astype(np.float32), masked=masked.astype(np.float32), topk=topk.astype(np.int64),
@@ -159,6 +163,10 @@ def main():
     run_case(ref, "ae_small_dropout", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2), adversarial=False)
     run_case(ref, "ae_h100_cond", n=96, V=520, H=100, C=50, B=32, epochs=2, dropout=(.2, .2), mean_len=8, cond_dim=7,
              adversarial=False)
+    # non-default model options (pins the oracle only; the CUDA path is checked against the oracle in these modes by
+    # tests/test_gpu_parity.py::test_edge_cases_empty_rows_unnormalized_prior_scale)
+    run_case(ref, "aae_opts_unnorm_scale_lrs", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2),
+             model_kwargs=dict(normalize_inputs=False, prior_scale=0.5, gen_lr=0.002, reg_lr=0.0005))
     ranking_case(ref)
 
 

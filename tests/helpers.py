@@ -10,6 +10,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 AAE_CASES = ["aae_small_dropout", "aae_small_nodrop", "aae_small_cond", "aae_h100_dropout",
              "aae_survey_nodrop", "aae_survey_dropout"]
 AE_CASES = ["ae_small_dropout", "ae_h100_cond"]      # the plain AutoEncoder (AAERecommender(adversarial=False))
+OPTION_CASES = ["aae_opts_unnorm_scale_lrs"]         # non-default normalize_inputs / prior_scale / learning rates
 
 
 def load_case(name):
@@ -20,6 +21,10 @@ def load_case(name):
     for k in ("n", "V", "H", "C", "B", "epochs", "cond_dim", "k"):
         g[k] = int(g[k])
     g["adversarial"] = bool(int(g.get("adversarial", 1)))
+    g["normalize_inputs"] = bool(int(g.get("normalize_inputs", 1)))
+    g["prior_scale"] = float(g.get("prior_scale", 0.0)) or None
+    g["gen_lr"] = float(g.get("gen_lr", 0.001))
+    g["reg_lr"] = float(g.get("reg_lr", 0.001))
     return g
 
 
@@ -37,7 +42,11 @@ def oracle_replay(g, record_rng=False):
     np.random.seed(42)
     adv = g["adversarial"]
     params = O.init_params(V, H, C, C + g["cond_dim"], seed=None, adversarial=adv)
-    model = O.OracleAAE(params, n_code=C) if adv else O.OracleAE(params, n_code=C)
+    if adv:
+        model = O.OracleAAE(params, n_code=C, gen_lr=g["gen_lr"], reg_lr=g["reg_lr"],
+                            normalize_inputs=g["normalize_inputs"])
+    else:
+        model = O.OracleAE(params, n_code=C)
     X = g["X"]
     losses, rngs, batches = [], [], []
     for _ in range(g["epochs"]):
@@ -47,7 +56,7 @@ def oracle_replay(g, record_rng=False):
         for s in range(0, X.shape[0], B):
             xb = Xs[s:s + B]
             cb = [cs[s:s + B]] if cs is not None else None
-            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"], adversarial=adv)
+            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"], prior_scale=g["prior_scale"], adversarial=adv)
             losses.append(model.partial_fit(xb.toarray(), cb, rng))
             if record_rng:
                 rngs.append(rng)
