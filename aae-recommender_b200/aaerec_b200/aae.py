@@ -8,6 +8,7 @@ defaults, ``fit`` / ``partial_fit`` / ``predict`` / ``eval`` / ``train`` / ``__s
 
 Additions that are not in the reference (defaults keep the reference's behaviour):
   ``predict_topk(X, k)``  fused predict + remove_non_missing + argtopk without the dense [n,V] matrix
+  ``evaluate_topk(X, Y, metrics)``  the harness' ranking metrics (evaluation.py:70-164, 202-240) on the device
   ``rng='native'|'oracle'``  in-kernel Philox dropout / prior sampling, or the reference's CPU-generator
                            draws in the reference's order (bit-identical masks; used by parity tests)
   ``impl``  decoder-output kernel: 'simt' (exact fp32 CUDA cores), 'tc' (tcgen05 3xTF32), 'tf32'
@@ -18,7 +19,7 @@ import scipy.sparse as sp
 import torch
 
 from .base import Recommender
-from .condition import _check_conditions, ConditionList
+from .condition import _check_conditions, CondAdapter
 from .engine import AAEEngine
 
 torch.manual_seed(42)   # aae.py:27 -- the reference seeds the CPU generator at import
@@ -97,6 +98,56 @@ class _ModuleView(object):
         return dict(self._sd)
 
 
+def _canonical_csr(X, what="input"):
+    """Any 2-D batch (dense ndarray as the reference passes to partial_fit, or scipy sparse) -> CSR with duplicates
+    summed, explicit zeros dropped and sorted column indices.  The kernels train on *binary* sets (indptr/indices
+    only): the reference's BCE rejects targets outside [0,1] (``RuntimeError``), and fractional values,
+    which the reference would use as soft targets, are outside the accelerated envelope."""
+    if not sp.issparse(X):
+        X = sp.csr_matrix(np.asarray(X))
+    X = X.tocsr()
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    if X.nnz and (X.data == 0).any():
+        X = X.copy()
+        X.eliminate_zeros()
+    if not X.has_sorted_indices:
+        X = X.sorted_indices()
+    if X.nnz:
+        if X.data.max() > 1 or X.data.min() < 0:
+            raise RuntimeError("all elements of target should be between 0 and 1")
+        if (X.data != 1).any():
+            raise NotImplementedError("%s has fractional entries: the accelerated path handles binary item sets only"
+                                      % what)
+    return X
+
+
+class _OptimView(object):
+    """Read-only stand-in for the reference's ``torch.optim.Adam`` attributes (``enc_optim`` ... aae.py:798-804):
+    hyper-parameters in ``param_groups`` and the Adam moments in ``state_dict()`` (torch's key names)."""
+
+    def __init__(self, model, which, lr):
+        self._model, self._which = model, which
+        self.param_groups = [{"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False}]
+        self.defaults = dict(self.param_groups[0])
+
+    def state_dict(self):
+        eng = self._model.engine
+        state = {}
+        if eng is not None:
+            for name, (m, v) in eng.optim_state(self._which).items():
+                state[name] = {"step": eng.steps_done, "exp_avg": m, "exp_avg_sq": v}
+        return {"state": state, "param_groups": [dict(self.param_groups[0])]}
+
+    def zero_grad(self):
+        """Gradients never persist between kernels."""
+
+    def step(self):
+        raise NotImplementedError("the optimizer updates are fused into the step kernels; call partial_fit or the "
+                                  "phase methods ae_step / disc_step / gen_step")
+
+
 class AdversarialAutoEncoder(object):
     """ Adversarial Autoencoder (aae.py:589) """
     adversarial = True
@@ -144,9 +195,11 @@ class AdversarialAutoEncoder(object):
         self.seed = seed
         self.use_graph = use_graph
         self.engine = None
+        self._adapter = None
         self._mode_train = True
         self.predict_batch_size = 1024   # query rows per launch of predict_topk (>= batch_size)
         self.record_losses = False   # True: keep every step's (R, D, G) in .loss_history (forces a sync per step)
+        self.last_losses = None
         # supported envelope; everything else fails loudly, there is no fallback path
         if self.prior != 'gauss':
             raise NotImplementedError("accelerated path supports prior='gauss' only (got %r)" % prior)
@@ -158,6 +211,12 @@ class AdversarialAutoEncoder(object):
             raise KeyError(optimizer)
         if rng not in ('native', 'oracle'):
             raise ValueError("rng must be 'native' or 'oracle'")
+        # aae.py:798-804: enc_optim and dec_optim at gen_lr, gen_optim and disc_optim at reg_lr
+        self.enc_optim = _OptimView(self, "enc", gen_lr)
+        self.dec_optim = _OptimView(self, "dec", gen_lr)
+        if self.adversarial:
+            self.gen_optim = _OptimView(self, "gen", reg_lr)
+            self.disc_optim = _OptimView(self, "disc", reg_lr)
 
     def __str__(self):
         desc = "Adversarial Autoencoder"
@@ -186,12 +245,6 @@ class AdversarialAutoEncoder(object):
 
     def zero_grad(self):
         """Gradients never persist between kernels; nothing to clear."""
-
-    def ae_step(self, batch, condition_data=None):
-        raise NotImplementedError("the three phases are fused into partial_fit on the device; "
-                                  "call partial_fit and read .last_losses")
-
-    disc_step = gen_step = ae_step
 
     # -- weights in the reference's layout
     @property
@@ -222,27 +275,45 @@ class AdversarialAutoEncoder(object):
         self.engine.load_params(params)
         self.last_losses = None
 
-    @staticmethod
-    def _csr_batch(X):
-        """Any 2-D batch (dense ndarray as the reference passes to partial_fit, or scipy sparse) ->
-        (indptr int32, indices int32) with sorted unique columns.  Values must be binary: the
-        reference's BCE rejects targets outside [0,1]."""
-        if not sp.issparse(X):
-            X = sp.csr_matrix(np.asarray(X))
-        X = X.tocsr()
-        if not X.has_sorted_indices:
-            X = X.sorted_indices()
-        if X.nnz and (X.data.max() > 1 or X.data.min() < 0):
-            raise RuntimeError("all elements of target should be between 0 and 1")
-        if X.nnz and (X.data == 0).any():
-            X = X.copy()
-            X.eliminate_zeros()
-        return X.indptr.astype(np.int32, copy=False), X.indices.astype(np.int32, copy=False)
-
-    def _cond_rows(self, condition_data):
+    def _cond_adapter(self):
         if not self.conditions:
             return None
-        return self.conditions.fused_rows(condition_data)
+        if self._adapter is None or self._adapter.conditions is not self.conditions:
+            self._adapter = CondAdapter(self.conditions)
+        return self._adapter
+
+    @staticmethod
+    def _csr_batch(X):
+        X = _canonical_csr(X, "batch")
+        return X.indptr.astype(np.int32, copy=False), X.indices.astype(np.int32, copy=False)
+
+    def _draws(self, B):
+        if self.rng != 'oracle':
+            return None
+        return _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale, self.adversarial)
+
+    # -- condition plumbing of one training batch
+    def _cond_begin(self, cond_batch, B):
+        """Before the step: row conditions hand over their float rows (host), generic ones are encoded through their
+        own protocol after ``conditions.zero_grad()`` (aae.py:698-700).  Returns (host rows or None, autograd leaves)."""
+        ad = self._cond_adapter()
+        if ad is None or cond_batch is None:
+            return None, None
+        if ad.all_rows:
+            return ad.encode_all_rows(cond_batch), None
+        self.conditions.zero_grad()
+        rows_dev, leaves = ad.encode_batch(cond_batch, self.engine.dev, want_grad=True)
+        self.engine.set_cond_rows(rows_dev, B)
+        if leaves:
+            self.engine.snapshot_dec_lin1()
+        return None, leaves
+
+    def _cond_end(self, leaves, B):
+        """After the reconstruction phase: the conditions' backward and ``conditions.step()`` (aae.py:703-709)."""
+        if leaves is None:
+            return
+        ad = self._cond_adapter()
+        ad.backward_and_step(leaves, self.engine.cond_grad(B) if leaves else None)
 
     # -- training
     def partial_fit(self, X, y=None, condition_data=None, step=None):
@@ -254,27 +325,66 @@ class AdversarialAutoEncoder(object):
             code_size = self.n_code + (self.conditions.size_increment() if use_condition else 0)
             self._build(X.shape[1], code_size)
         indptr, indices = self._csr_batch(X)
-        self._partial_fit_csr(indptr, indices, self._cond_rows(condition_data) if use_condition else None)
+        B = int(indptr.shape[0]) - 1
+        self.train()
+        rows, leaves = self._cond_begin(condition_data if use_condition else None, B)
+        draws = self._draws(B)
+        self.engine.train_step_host(indptr, indices, rows, injected=draws is not None, rng_draws=draws,
+                                    cond_on_device=leaves is not None)
+        self._cond_end(leaves, B)
         if self.verbose:
             log_losses(*self.losses())
         return self
 
-    def _partial_fit_csr(self, indptr, indices, cond_rows):
+    def _phase(self, phase, batch, condition_data):
+        """One of the reference's three phase methods (aae.py:676-743) on its own: same argument (the batch; a dense
+        tensor/ndarray as the reference passes, or scipy sparse), same return value (the phase's loss as float)."""
+        if torch.is_tensor(batch):
+            batch = batch.detach().cpu().numpy()
         eng = self.engine
-        self.train()
-        draws = None
-        if self.rng == 'oracle':
+        if phase == "ae":
+            use_condition = _check_conditions(self.conditions, condition_data)
+            if eng is None:
+                code_size = self.n_code + (self.conditions.size_increment() if use_condition else 0)
+                self._build(batch.shape[1], code_size)
+                eng = self.engine
+            indptr, indices = self._csr_batch(batch)
             B = int(indptr.shape[0]) - 1
-            draws = _draw_step_rng(B, self.n_hidden, self.n_code, self.dropout, self.prior_scale, self.adversarial)
-        eng.train_step_host(indptr, indices, cond_rows, injected=draws is not None, rng_draws=draws)
+            rows, leaves = self._cond_begin(condition_data if use_condition else None, B)
+            eng.upload_csr(indptr, indices, rows)
+            self._phase_B = B
+            draws = self._draws(B)
+            self._phase_injected = draws is not None and eng.set_rng_draws(B, draws)
+            loss = eng.phase_step("ae", B, self._phase_injected)
+            self._cond_end(leaves, B)
+            return loss
+        if eng is None:
+            raise RuntimeError("%s_step before ae_step: the model is built by the first reconstruction step" % phase)
+        return eng.phase_step(phase, self._phase_B, self._phase_injected)
+
+    def ae_step(self, batch, condition_data=None):
+        """aae.py:676-711.  The four optimizers share one Adam step counter, so the three phase methods must be
+        called in partial_fit's order (ae_step, disc_step, gen_step on the same batch)."""
+        return self._phase("ae", batch, condition_data)
+
+    def disc_step(self, batch):
+        """aae.py:713-732 (on the batch ae_step saw)."""
+        return self._phase("disc", batch, None)
+
+    def gen_step(self, batch):
+        """aae.py:734-743 (on the batch ae_step saw)."""
+        return self._phase("gen", batch, None)
 
     def losses(self):
         """(recon, disc, gen) losses of the last step -- a device->host read (synchronises)."""
         self.last_losses = tuple(float(x) for x in self.engine.losses.cpu().tolist())
+        self.engine.check_exchange()
         return self.last_losses
 
     def fit(self, X, y=None, condition_data=None):
-        """aae.py:768-837: build, then per epoch shuffle and walk the batches."""
+        """aae.py:768-837: build, then per epoch shuffle and walk the batches.  The training matrix (and the matrix of
+        row conditions) is uploaded once; every epoch the host draws the reference's permutation and the batches are
+        assembled on the device (``aae_batch_gather``)."""
         if y is not None:
             raise NotImplementedError("(Semi-)supervised usage not supported")
         use_condition = _check_conditions(self.conditions, condition_data)
@@ -284,60 +394,74 @@ class AdversarialAutoEncoder(object):
         else:
             code_size = self.n_code
             print(("" if self.adversarial else "[ae] ") + "Not using condition, code size:", code_size)
-        X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
-        if not X.has_sorted_indices:
-            X = X.sorted_indices()
-        if X.nnz and (X.data.max() > 1 or X.data.min() < 0):
-            raise RuntimeError("all elements of target should be between 0 and 1")
+        X = _canonical_csr(X, "training matrix")
         self._build(X.shape[1], code_size)
-        cond_all = self._cond_rows(condition_data) if use_condition else None
+        eng = self.engine
+        ad = self._cond_adapter() if use_condition else None
+        cond_all = ad.encode_all_rows(condition_data) if (ad is not None and ad.all_rows) else None
+        eng.set_epoch_data(X.indptr, X.indices, cond_all)
         n = X.shape[0]
         self.loss_history = []
-        step = 0
+        self.epoch_seconds = []          # wall-clock of every epoch (one synchronisation per epoch)
+        self.train()
+        import time
         for epoch in range(self.n_epochs):
+            t_epoch = time.perf_counter()
             if self.verbose:
                 print("Epoch", epoch + 1)
             # sklearn.utils.shuffle(X, *condition_data) with random_state=None permutes arange(n) with the
             # global numpy generator (aae.py:815-817); same stream consumption here.
             perm = np.arange(n)
             np.random.shuffle(perm)
-            X_shuf = X[perm]
-            c_shuf = cond_all[perm] if cond_all is not None else None
-            indptr = X_shuf.indptr
-            indices = X_shuf.indices.astype(np.int32, copy=False)
+            eng.set_epoch_perm(perm)
             for start in range(0, n, self.batch_size):
                 end = min(start + self.batch_size, n)
-                lo, hi = int(indptr[start]), int(indptr[end])
-                ip = (indptr[start:end + 1] - lo).astype(np.int32)
-                self._partial_fit_csr(ip, indices[lo:hi], c_shuf[start:end] if c_shuf is not None else None)
+                B = end - start
+                leaves = None
+                if ad is not None and not ad.all_rows:
+                    rows = perm[start:end]
+                    _, leaves = self._cond_begin([ad.take(c, rows) for c in condition_data], B)
+                eng.gather_batch(start, B)
+                draws = self._draws(B)
+                injected = draws is not None and eng.set_rng_draws(B, draws)
+                eng.train_step(B, injected)
+                self._cond_end(leaves, B)
                 if self.verbose or self.record_losses:
                     cur = self.losses()
                     if self.record_losses:
                         self.loss_history.append(cur)
                     if self.verbose:
                         log_losses(*cur)
-                step += 1
             if self.verbose:
                 print()
+            torch.cuda.synchronize(eng.dev)
+            self.epoch_seconds.append(time.perf_counter() - t_epoch)
+        eng.check_exchange()
         return self
 
     # -- prediction
     def _iter_batches(self, X, condition_data, batch_size=None):
+        """Query batches of an eval-mode pass: the query matrix (and row-condition matrix) is uploaded once and the
+        batches are built on the device; generic conditions are encoded per batch through their protocol."""
         batch_size = batch_size or self.batch_size
         use_condition = _check_conditions(self.conditions, condition_data)
         self.eval()
-        X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
-        if not X.has_sorted_indices:
-            X = X.sorted_indices()
-        cond_all = self._cond_rows(condition_data) if use_condition else None
+        X = _canonical_csr(X, "query matrix")
+        eng = self.engine
+        ad = self._cond_adapter() if use_condition else None
+        cond_all = ad.encode_all_rows(condition_data) if (ad is not None and ad.all_rows) else None
+        eng.set_epoch_data(X.indptr, X.indices, cond_all)
+        eng.set_epoch_perm(None)
         n = X.shape[0]
-        indptr = X.indptr
-        indices = X.indices.astype(np.int32, copy=False)
         for start in range(0, n, batch_size):
             end = min(start + batch_size, n)
-            lo, hi = int(indptr[start]), int(indptr[end])
-            ip = (indptr[start:end + 1] - lo).astype(np.int32)
-            B, _ = self.engine.upload_csr(ip, indices[lo:hi], cond_all[start:end] if cond_all is not None else None)
+            B = end - start
+            eng.gather_batch(start, B)
+            if ad is not None and not ad.all_rows:
+                rows = np.arange(start, end)
+                with torch.no_grad():
+                    rows_dev, _ = ad.encode_batch([ad.take(c, rows) for c in condition_data], eng.dev, want_grad=False)
+                eng.set_cond_rows(rows_dev, B)
             yield start, end, B
 
     def predict(self, X, condition_data=None):
@@ -353,6 +477,7 @@ class AdversarialAutoEncoder(object):
                 out[start:end] = dev[:B].cpu().numpy()
             else:
                 out[start:end] = eng._gather_items(dev[:B].t().contiguous()).t().cpu().numpy()
+        eng.check_exchange()
         return out
 
     def predict_topk(self, X, k, condition_data=None, mask_known=True, return_scores=False):
@@ -371,7 +496,34 @@ class AdversarialAutoEncoder(object):
             idx[start:end] = i.cpu().numpy()
             if return_scores:
                 val[start:end] = v.cpu().numpy()
+        eng.check_exchange()
         return (idx, val) if return_scores else idx
+
+
+
+    def gold_ranks(self, X, Y, condition_data=None, batch_size=256):
+        """Rank (1-based) of every held-out item of ``Y`` (scipy sparse [n, n_items], the harness' ``y_test``) in the
+        ranking of remove_non_missing(predict(X), X): (indptr, ranks) aligned with ``Y.tocsr()``'s entries.  The score
+        matrix is built and ranked on the device batch by batch; only the ranks travel to the host."""
+        eng = self.engine
+        Y = _canonical_csr(Y, "gold matrix")
+        assert Y.shape == (X.shape[0], eng.V), (Y.shape, X.shape, eng.V)
+        ranks = np.zeros(Y.nnz, dtype=np.int64)
+        scratch = torch.empty(min(batch_size, X.shape[0]), eng.Vloc, dtype=torch.float32, device=eng.dev)
+        for start, end, B in self._iter_batches(X, condition_data, batch_size=batch_size):
+            lo, hi = int(Y.indptr[start]), int(Y.indptr[end])
+            gp = (Y.indptr[start:end + 1] - lo).astype(np.int32)
+            ranks[lo:hi] = eng.gold_ranks(B, gp, Y.indices[lo:hi], scratch=scratch)
+        eng.check_exchange()
+        return Y.indptr.astype(np.int64), ranks
+
+    def evaluate_topk(self, X, Y, metrics, condition_data=None, batch_size=256):
+        """The harness' ``evaluate(y_test, remove_non_missing(predict(X), X), metrics)`` (evaluation.py:202-240, 395)
+        without the dense [n, n_items] matrix ever reaching the host: [(mean, std)] per metric.  ``metrics``: keys of
+        evaluation.py:166-180 ('mrr@5', 'map', 'P@1' ...) or the reference's metric objects."""
+        from .ranking import metrics_from_ranks
+        indptr, ranks = self.gold_ranks(X, Y, condition_data=condition_data, batch_size=batch_size)
+        return metrics_from_ranks(indptr, ranks, metrics, self.engine.V)
 
 
 class AutoEncoder(AdversarialAutoEncoder):
@@ -455,3 +607,10 @@ class AAERecommender(Recommender):
         X = test_set.tocsr()
         condition_data = self._condition_data(test_set, fit=False)
         return self.model.predict_topk(X, k, condition_data=condition_data, mask_known=mask_known)
+
+    def evaluate_topk(self, test_set, gold, metrics):
+        """Ranking metrics of the harness (evaluation.py:70-164, 202-240) on the device: ``gold`` is the sparse
+        [n, n_items] matrix of held-out items (``Evaluation.y_test``)."""
+        X = test_set.tocsr()
+        condition_data = self._condition_data(test_set, fit=False)
+        return self.model.evaluate_topk(X, gold, metrics, condition_data=condition_data)

@@ -1,36 +1,54 @@
-"""Condition protocol as the hot path sees it (reference: aaerec/condition.py).
+"""Conditions as the AAE hot path sees them (reference: aaerec/condition.py).
 
-The AAE only ever calls ``conditions.encode_impose(z, c_batch)``, ``.size_increment()``,
-``.zero_grad()``, ``.step()``, ``.train()/.eval()``, ``.keys()``, ``.fit_transform()`` and
-``.transform()`` (aae.py:688-709, 778-780, 863-865, 944-946, 969-971).  This module mirrors the classes
-on that protocol: ``ConditionList`` (condition.py:59-137), ``ConditionBase`` (140-255),
-``ConcatenationBasedConditioning`` (300-316) and a precomputed-embedding condition equivalent to
-``PretrainedWordEmbeddingCondition`` (345-369) once its TF-IDF-weighted word vectors exist.
+The autoencoder only ever talks to its ``conditions`` object through a small protocol (aae.py:688-709,
+778-780, 863-865, 944-946, 969-971): ``keys() / values() / __len__``, ``size_increment()``,
+``fit_transform(raw) / transform(raw)``, ``encode(batch)``, ``zero_grad() / step()``, ``train() / eval()``.
+Everything here is **duck-typed on that protocol**: the reference's own ``aaerec.condition.ConditionList``
+holding ``PretrainedWordEmbeddingCondition`` / ``CategoricalCondition`` / ``EmbeddingBagCondition`` objects is
+accepted as it is (``main.py:103-110`` builds exactly that), and so is this module's small stand-alone
+``ConditionList`` for users without the reference package.
 
-Only concatenation conditions whose ``encode`` is a pure float-matrix lookup are fused into the CUDA
-path (the condition rows are copied to the device and concatenated on the code inside
-``aae_ae_fwd``).  Trainable conditions keep their own torch modules/optimizers in the reference; they
-are outside the accelerated envelope and raise ``NotImplementedError`` here.
+How a condition reaches the kernels (``CondAdapter``):
+  * *row conditions* -- concatenation conditions whose ``encode`` is a parameter-free float-matrix lookup
+    (``PretrainedWordEmbeddingCondition.encode`` = ``as_tensor(float32)``, condition.py:363-365; this module's
+    ``PrecomputedEmbeddingCondition``): the whole [n, D] matrix is encoded once, kept in HBM and its rows are
+    gathered per batch by ``aae_batch_gather`` and concatenated on the code inside ``aae_ae_fwd_bag``;
+  * *generic concatenation conditions* (trainable: ``CategoricalCondition``, ``EmbeddingBagCondition``, or any other
+    object whose ``impose`` concatenates along dim 1): called through their Python protocol between kernels --
+    ``encode`` per batch (torch, wherever the condition keeps its parameters), rows copied into the step's
+    condition buffer, and after the step the gradient of the loss w.r.t. those rows (``dec.lin1`` slice of the
+    reconstruction backward, computed by the kernels) is pushed back through the condition's autograd graph
+    before ``conditions.step()`` -- the reference's ``zero_grad / backward / step`` sequence (aae.py:698-709);
+  * anything that does not concatenate (``ConditionalBiasing`` / ``ConditionalScaling``) would need the fused
+    encoder->decoder kernel split at the code; that raises ``NotImplementedError`` (no silent CPU path).
 """
-from abc import ABC, abstractmethod
 from collections import OrderedDict
 
 import numpy as np
 
+ROW_CONDITION_CLASS_NAMES = ("PretrainedWordEmbeddingCondition", "PrecomputedEmbeddingCondition")
+_PROTOCOL = ("values", "keys", "size_increment", "encode")
+
+
+def _is_condition_list(obj):
+    return all(hasattr(obj, a) for a in _PROTOCOL) and hasattr(obj, "__len__")
+
 
 def _check_conditions(conditions, condition_data):
-    """condition.py:31-57 -- same return value and the same AssertionErrors."""
+    """condition.py:31-57 -- same return value and the same AssertionErrors, but any object that speaks the
+    ConditionList protocol passes (the reference's class, this module's, or a user's)."""
     if not conditions and not condition_data:
         return False
-    assert isinstance(conditions, ConditionList), "`conditions` no instance of ConditionList"
+    assert _is_condition_list(conditions), "`conditions` no instance of ConditionList"
     assert condition_data and conditions, "Mismatch between condition spec and supplied condition data."
     assert len(condition_data) == len(conditions), "Unexpected number of supplied condition data"
     return True
 
 
-class ConditionBase(ABC):
-    """condition.py:140-255: fit/transform on raw inputs, encode/impose on batches, optional
-    optimizer callbacks (no-ops for parameter-free conditions)."""
+class ConditionBase(object):
+    """Default behaviour of one condition (condition.py:140-255): identity fit/transform/encode, no-op optimizer
+    and mode hooks.  Subclasses provide ``impose`` and ``size_increment``."""
+    fusable = False   #: True when ``encode`` is a parameter-free float-matrix lookup (row condition)
 
     def fit(self, raw_inputs):
         return self
@@ -41,20 +59,17 @@ class ConditionBase(ABC):
     def fit_transform(self, raw_inputs):
         return self.fit(raw_inputs).transform(raw_inputs)
 
-    @abstractmethod
     def encode(self, inputs):
-        """ batch of transformed inputs -> float rows """
+        return inputs
 
-    @abstractmethod
     def impose(self, inputs, encoded_condition, dim=None):
-        """ combine code and encoded condition """
+        raise NotImplementedError
 
     def encode_impose(self, inputs, condition_input, dim=None):
-        return self.impose(inputs, self.encode(condition_input), dim)
+        return self.impose(inputs, self.encode(condition_input), dim=None)
 
-    @abstractmethod
     def size_increment(self):
-        """ how much the code grows """
+        raise NotImplementedError
 
     def zero_grad(self):
         return self
@@ -68,22 +83,27 @@ class ConditionBase(ABC):
     def eval(self):
         return self
 
-    #: True when ``encode`` is a parameter-free float-matrix lookup (fusable into the kernels)
-    fusable = False
-
 
 class ConcatenationBasedConditioning(ConditionBase):
-    """condition.py:300-316: impose = concatenate along dim 1."""
+    """condition.py:300-316: impose = concatenate along dim 1 (numpy or torch inputs)."""
     dim = 1
 
     def impose(self, inputs, encoded_condition, dim=None):
-        return np.concatenate([np.asarray(inputs), np.asarray(encoded_condition)], axis=self.dim if dim is None else dim)
+        axis = self.dim if dim is None else dim
+        try:
+            import torch
+            if torch.is_tensor(inputs) or torch.is_tensor(encoded_condition):
+                return torch.cat([torch.as_tensor(inputs), torch.as_tensor(encoded_condition).to(
+                    torch.as_tensor(inputs).device)], dim=axis)
+        except ImportError:   # pragma: no cover
+            pass
+        return np.concatenate([np.asarray(inputs), np.asarray(encoded_condition)], axis=axis)
 
 
 class PrecomputedEmbeddingCondition(ConcatenationBasedConditioning):
-    """Rows of a precomputed float matrix (e.g. TF-IDF-weighted word2vec title embeddings,
-    ub.py:58-62), concatenated on the code -- what PretrainedWordEmbeddingCondition.encode yields
-    (condition.py:363-365): ``as_tensor(inputs, float32)``."""
+    """Rows of a precomputed float matrix (e.g. TF-IDF-weighted word2vec title embeddings, ub.py:58-62),
+    concatenated on the code -- what PretrainedWordEmbeddingCondition.encode yields once its vectoriser has run
+    (condition.py:363-365)."""
     fusable = True
 
     def __init__(self, dim):
@@ -99,65 +119,145 @@ class PrecomputedEmbeddingCondition(ConcatenationBasedConditioning):
 
 
 class ConditionList(OrderedDict):
-    """condition.py:59-137: ordered name -> condition mapping; order is meaningful."""
+    """Ordered ``name -> condition`` mapping speaking the protocol of condition.py:59-137; order is meaningful.
+    Every list-level call fans out over the members in order."""
 
     def __init__(self, items):
         super(ConditionList, self).__init__(items)
-        assert all(isinstance(v, ConditionBase) for v in self.values())
+        for name, c in self.items():
+            assert all(hasattr(c, a) for a in ("encode", "impose", "size_increment")), \
+                "condition %r does not implement the condition protocol" % (name,)
+
+    def _each(self, method, inputs=None):
+        if inputs is None:
+            return [getattr(c, method)() for c in self.values() if hasattr(c, method)]
+        assert len(inputs) == len(self)
+        return [getattr(c, method)(x) for c, x in zip(self.values(), inputs)]
 
     def fit(self, raw_inputs):
-        assert len(raw_inputs) == len(self)
-        for cond, cond_inp in zip(self.values(), raw_inputs):
-            cond.fit(cond_inp)
+        self._each("fit", raw_inputs)
         return self
 
     def transform(self, raw_inputs):
-        assert len(raw_inputs) == len(self)
-        return [c.transform(inp) for c, inp in zip(self.values(), raw_inputs)]
+        return self._each("transform", raw_inputs)
 
     def fit_transform(self, raw_inputs):
-        assert len(raw_inputs) == len(self)
-        return [cond.fit_transform(inp) for cond, inp in zip(self.values(), raw_inputs)]
+        return self._each("fit_transform", raw_inputs)
+
+    def encode(self, condition_inputs):
+        return self._each("encode", condition_inputs)
 
     def encode_impose(self, x, condition_inputs, dim=None):
         assert len(condition_inputs) == len(self)
-        for condition, condition_input in zip(self.values(), condition_inputs):
-            x = condition.encode_impose(x, condition_input, dim)
+        for c, ci in zip(self.values(), condition_inputs):
+            x = c.encode_impose(x, ci, dim)
         return x
 
-    def encode(self, condition_inputs):
-        assert len(condition_inputs) == len(self)
-        return [c.encode(ci) for c, ci in zip(self.values(), condition_inputs)]
+    def size_increment(self):
+        return sum(self._each("size_increment"))
 
     def zero_grad(self):
-        for condition in self.values():
-            condition.zero_grad()
+        self._each("zero_grad")
         return self
 
     def step(self):
-        for condition in self.values():
-            condition.step()
+        self._each("step")
         return self
 
-    def size_increment(self):
-        return sum(v.size_increment() for v in self.values())
-
     def train(self):
-        for condition in self.values():
-            if hasattr(condition, 'train'):
-                condition.train()
+        self._each("train")
 
     def eval(self):
-        for condition in self.values():
-            if hasattr(condition, 'eval'):
-                condition.eval()
+        self._each("eval")
 
-    def fused_rows(self, condition_inputs):
-        """Concatenate the encoded rows of all (fusable) conditions: float32 [B, size_increment()]."""
-        for name, c in self.items():
-            if not getattr(c, "fusable", False) or not isinstance(c, ConcatenationBasedConditioning):
+
+def _concatenates(cond):
+    """Behavioural probe: does ``cond.impose`` concatenate along dim 1?  (True for every subclass of the reference's
+    ConcatenationBasedConditioning, whatever package it was imported from.)"""
+    import torch
+    try:
+        out = cond.impose(torch.zeros(2, 3), torch.ones(2, 2))
+    except Exception:   # noqa: BLE001
+        return False
+    return torch.is_tensor(out) and tuple(out.shape) == (2, 5) and bool((out[:, :3] == 0).all()) and \
+        bool((out[:, 3:] == 1).all())
+
+
+class CondAdapter(object):
+    """Feeds a ConditionList-like object to the engine (see the module docstring)."""
+
+    def __init__(self, conditions):
+        self.conditions = conditions
+        self.members = list(conditions.values())
+        self.names = list(conditions.keys())
+        self.kinds = []
+        for name, c in zip(self.names, self.members):
+            rowlike = bool(getattr(c, "fusable", False)) or type(c).__name__ in ROW_CONDITION_CLASS_NAMES
+            if rowlike:
+                self.kinds.append("rows")
+            elif _concatenates(c):
+                self.kinds.append("generic")
+            else:
                 raise NotImplementedError(
-                    "condition %r (%s) is outside the accelerated envelope: only concatenation conditions whose "
-                    "encode() is a float-matrix lookup are fused; no CPU fallback" % (name, type(c).__name__))
-        enc = self.encode(condition_inputs)
-        return enc[0] if len(enc) == 1 else np.concatenate(enc, axis=1)
+                    "condition %r (%s) does not concatenate on the code: conditional biasing/scaling would need the "
+                    "fused encoder->decoder kernel split at the code; outside the accelerated envelope (no CPU "
+                    "fallback)" % (name, type(c).__name__))
+        self.all_rows = all(k == "rows" for k in self.kinds)
+        self.size = int(conditions.size_increment())
+
+    @staticmethod
+    def _rows(encoded):
+        try:
+            import torch
+            if torch.is_tensor(encoded):
+                encoded = encoded.detach().cpu().numpy()
+        except ImportError:   # pragma: no cover
+            pass
+        if hasattr(encoded, "toarray"):
+            encoded = encoded.toarray()
+        out = np.ascontiguousarray(np.asarray(encoded), dtype=np.float32)
+        assert out.ndim == 2, "encoded condition must be [n, dim]"
+        return out
+
+    def encode_all_rows(self, condition_data):
+        """Row conditions only: the whole [n, size_increment] float32 matrix, encoded once."""
+        assert self.all_rows
+        parts = [self._rows(c.encode(d)) for c, d in zip(self.members, condition_data)]
+        out = parts[0] if len(parts) == 1 else np.concatenate(parts, axis=1)
+        assert out.shape[1] == self.size, "size_increment() disagrees with the encoded condition width"
+        return out
+
+    @staticmethod
+    def take(container, rows):
+        """``container[rows]`` for the per-row containers conditions hand out (ndarray, scipy sparse, list)."""
+        if isinstance(container, (list, tuple)):
+            return [container[int(i)] for i in rows]
+        return container[rows]
+
+    def encode_batch(self, cond_batch, device, want_grad):
+        """Generic path, one batch: returns (rows float32 [B, size] on ``device`` (detached), leaves) where leaves
+        are the encoded tensors that require grad (to be given the kernels' gradient after the step)."""
+        import torch
+        outs, leaves, col = [], [], 0
+        for c, d in zip(self.members, cond_batch):
+            e = c.encode(d)
+            if not torch.is_tensor(e):
+                e = torch.as_tensor(self._rows(e))
+            w = int(e.shape[1])
+            if want_grad and e.requires_grad:
+                leaves.append((e, col, col + w))
+            outs.append(e.detach().to(device=device, dtype=torch.float32))
+            col += w
+        assert col == self.size, "size_increment() disagrees with the encoded condition width"
+        rows = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+        return rows.contiguous(), leaves
+
+    def backward_and_step(self, leaves, grad_rows):
+        """The reference's ``loss.backward()`` restricted to the conditions, then ``conditions.step()``
+        (aae.py:703-709); ``conditions.zero_grad()`` ran before the batch was encoded."""
+        import torch
+        if leaves:
+            tensors = [e for e, _, _ in leaves]
+            grads = [grad_rows[:, a:b].to(device=e.device, dtype=e.dtype) for e, a, b in leaves]
+            torch.autograd.backward(tensors, grads)
+        self.conditions.step()

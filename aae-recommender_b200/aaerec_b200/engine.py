@@ -46,6 +46,20 @@ def disc_block_sizes(H, C_):
             ("disc.lin2.bias", H), ("disc.lin3.weight", H), ("disc.lin3.bias", 1)]
 
 
+def _on_device(fn):
+    """Run an engine entry point with the engine's GPU as the CUDA current device: the C ABI launches on the current
+    device, so ``device='cuda:1'`` must not depend on the caller having called ``torch.cuda.set_device``."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if torch.cuda.current_device() == self.dev.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class _Branch(object):
     """Fork of the current stream onto ``engine.side2`` (see AAEEngine._branch)."""
 
@@ -80,6 +94,15 @@ class AAEEngine(object):
                  use_graph=True, overlap_sweep=True, adversarial=True, exchange="auto"):
         N.require_device(0 if device is None else (torch.device(device).index or 0))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.dev):
+            self._construct(n_items, n_hidden, n_code, cond_dim, gen_lr, reg_lr, dropout, prior_scale,
+                            normalize_inputs, rank, world, group, impl, seed, max_batch, max_nnz, use_graph,
+                            overlap_sweep, adversarial, exchange)
+
+    def _construct(self, n_items, n_hidden, n_code, cond_dim, gen_lr, reg_lr, dropout, prior_scale, normalize_inputs,
+                   rank, world, group, impl, seed, max_batch, max_nnz, use_graph, overlap_sweep, adversarial, exchange):
         self.V, self.H, self.C, self.D = int(n_items), int(n_hidden), int(n_code), int(cond_dim)
         self.Cp = self.C + self.D
         self.gen_lr, self.reg_lr = float(gen_lr), float(reg_lr)
@@ -105,6 +128,9 @@ class AAEEngine(object):
         self.impl = self._pick_impl(impl)
         self.steps_done = 0
         self._launches_per_step = 0
+        self._phase_cursor = 0
+        self._phase_ctx_live = None
+        self._epoch = None
         f32 = dict(dtype=torch.float32, device=self.dev)
         H, Cc, Cp, Vl = self.H, self.C, self.Cp, max(self.Vloc, 1)
         z = lambda *s: torch.zeros(*s, **f32)
@@ -217,9 +243,18 @@ class AAEEngine(object):
     def _ensure_ws(self, B, nnz):
         if B <= self._ws_B and nnz <= self._ws_nnz:
             return
-        B = max(B, self._ws_B)
-        nnz = max(nnz, self._ws_nnz, 1)
+        # grow geometrically: every growth synchronises, drops the captured graphs and re-pins the staging slots
+        if self._ws_B:
+            B = max(self._ws_B, B if B <= self._ws_B else max(B, int(1.5 * self._ws_B)))
+            nnz = max(self._ws_nnz, nnz if nnz <= self._ws_nnz else max(nnz, int(1.5 * self._ws_nnz)))
+        nnz = max(nnz, 1)
         torch.cuda.synchronize(self.dev)
+        if self.peer is not None and B * self.H > self.peer.n_max:
+            # the exchange buffers are sized for the largest [B,H] message: re-create them (collective: every rank
+            # sees the same batch sizes) instead of silently issuing NCCL calls inside a graph capture
+            from .dist import PeerExchange
+            self.peer.close()
+            self.peer = PeerExchange(self.rank, self.world, self.group, max(B, 128) * self.H, self.dev)
         self._graphs.clear()
         f32 = dict(dtype=torch.float32, device=self.dev)
         i32 = dict(dtype=torch.int32, device=self.dev)
@@ -265,6 +300,7 @@ class AAEEngine(object):
         self._ws_B, self._ws_nnz = B, nnz
 
     # ------------------------------------------------------------------ parameters
+    @_on_device
     def load_params(self, params):
         """``params``: torch-layout state dict (keys ``enc.lin1.weight`` ... as in the reference's
         modules, aae.py:104-213); values numpy arrays or tensors (full, unsharded)."""
@@ -296,20 +332,37 @@ class AAEEngine(object):
         self._init_state()
         self.steps_done = 0
 
+    INIT_BLOCK = 65536      # items per generator block of init_uniform
+
+    @_on_device
     def init_uniform(self, seed=42):
         """Random-init weights of the reference architecture directly in HBM (nn.Linear's law: U(-1/sqrt(fan_in),
-        1/sqrt(fan_in)) for weight and bias), without building the full [V,H] matrices on the host: the item-sharded
-        layers are drawn per shard, the replicated small layers identically on every rank.  For synthetic benchmarks
-        at vocabulary sizes where a host-side state dict is impractical (MPD shape, 2M items)."""
+        1/sqrt(fan_in)) for weight and bias), without building the full [V,H] matrices on the host -- for synthetic
+        benchmarks at vocabulary sizes where a host-side state dict is impractical (MPD shape, 2M items).  The
+        item-sharded layers are drawn in blocks of INIT_BLOCK items, each block from its own generator seeded by
+        (seed, tensor, block index): the full matrices are therefore the SAME for every world size, and a rank fills
+        exactly the rows of its item range (so an N-GPU run can be checked against a 1-GPU run).  The replicated small
+        layers are drawn identically on every rank."""
         gs = torch.Generator(device=self.dev).manual_seed(int(seed))                      # same on every rank
-        gl = torch.Generator(device=self.dev).manual_seed(int(seed) * 1000003 + 17 + self.rank)
 
         def fill(t, fan_in, g):
             bound = 1.0 / float(np.sqrt(fan_in))
             t.uniform_(-bound, bound, generator=g)
-        fill(self.W1t, self.V, gl)
-        fill(self.Wd3, self.H, gl)
-        fill(self.bd3, self.H, gl)
+
+        def fill_items(t, fan_in, tensor_id):
+            bound = 1.0 / float(np.sqrt(fan_in))
+            blk = self.INIT_BLOCK
+            width = (self.H,) if t.dim() == 2 else ()
+            for b in range(self.v_begin // blk, (max(self.v_end, 1) - 1) // blk + 1):
+                g = torch.Generator(device=self.dev).manual_seed(int(seed) * 1000003 + tensor_id * 7919 + b * 31 + 17)
+                full = torch.empty((blk,) + width, dtype=torch.float32, device=self.dev)
+                full.uniform_(-bound, bound, generator=g)
+                lo, hi = max(self.v_begin, b * blk), min(self.v_end, (b + 1) * blk)
+                if hi > lo:
+                    t[lo - self.v_begin: hi - self.v_begin].copy_(full[lo - b * blk: hi - b * blk])
+        fill_items(self.W1t, self.V, 1)
+        fill_items(self.Wd3, self.H, 2)
+        fill_items(self.bd3, self.H, 3)
         fan = {"enc.lin1.bias": self.V, "enc.lin2": self.H, "enc.lin3": self.H, "dec.lin1": self.Cp, "dec.lin2": self.H,
                "disc.lin1": self.C, "disc.lin2": self.H, "disc.lin3": self.H}
         for blk, sizes in ((self.enc, enc_block_sizes(self.H, self.C)), (self.dec, dec_block_sizes(self.H, self.Cp)),
@@ -329,10 +382,12 @@ class AAEEngine(object):
         """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export / dense predict)."""
         return gather_item_shards(local[: self.Vloc], self.V, self.world, self.group)
 
+    @_on_device
     def state_dict(self):
         """Weights in the reference's torch layout (full, gathered over shards), on the host."""
         self.flush_w1()
         torch.cuda.synchronize(self.dev)
+        self.check_exchange()
         out = {}
         out["enc.lin1.weight"] = self._gather_items(self.W1t[: self.Vloc]).t().contiguous().cpu()
         out["dec.lin3.weight"] = self._gather_items(self.Wd3[: self.Vloc]).contiguous().cpu()
@@ -350,7 +405,46 @@ class AAEEngine(object):
                 off += sz
         return out
 
+    def optim_state(self, which):
+        """Adam moments of one of the reference's four optimizers (aae.py:798-804) in torch's parameter names and
+        layouts: {name: (exp_avg, exp_avg_sq)} host tensors, gathered over item shards."""
+        self.flush_w1()
+        torch.cuda.synchronize(self.dev)
+        shapes = {"enc.lin2.weight": (self.H, self.H), "enc.lin3.weight": (self.C, self.H),
+                  "dec.lin1.weight": (self.H, self.Cp), "dec.lin2.weight": (self.H, self.H),
+                  "disc.lin1.weight": (self.H, self.C), "disc.lin2.weight": (self.H, self.H),
+                  "disc.lin3.weight": (1, self.H)}
+
+        def block(m, v, sizes):
+            out, off = {}, 0
+            for name, sz in sizes:
+                a, b = m[off:off + sz].cpu(), v[off:off + sz].cpu()
+                if name in shapes:
+                    a, b = a.reshape(shapes[name]), b.reshape(shapes[name])
+                out[name] = (a, b)
+                off += sz
+            return out
+
+        def items(t, transpose=False):
+            g = self._gather_items(t[: self.Vloc])
+            return (g.t().contiguous() if transpose else g.contiguous()).cpu()
+        if which in ("enc", "gen"):
+            m, v = (self.enc_m1, self.enc_v1) if which == "enc" else (self.enc_m2, self.enc_v2)
+            wm, wv = (self.W1_m1, self.W1_v1) if which == "enc" else (self.W1_m2, self.W1_v2)
+            out = {"enc.lin1.weight": (items(wm, True), items(wv, True))}
+            out.update(block(m, v, enc_block_sizes(self.H, self.C)))
+            return out
+        if which == "dec":
+            out = block(self.dec_m, self.dec_v, dec_block_sizes(self.H, self.Cp))
+            out["dec.lin3.weight"] = (items(self.Wd3_m), items(self.Wd3_v))
+            out["dec.lin3.bias"] = (items(self.bd3_m), items(self.bd3_v))
+            return out
+        if which == "disc":
+            return block(self.disc_m, self.disc_v, disc_block_sizes(self.H, self.C))
+        raise KeyError(which)
+
     # ------------------------------------------------------------------ batch staging
+    @_on_device
     def upload_csr(self, indptr_np, indices_np, cond_np=None):
         """Host CSR rows (int32, row-relative indptr starting at 0) -> device batch buffers,
         through pinned staging; returns (B, nnz).  This is the H2D leg of the end-to-end path."""
@@ -365,7 +459,7 @@ class AAEEngine(object):
         slot["indices"][:nnz].numpy()[:] = indices_np[:nnz]
         call("aae_upload_batch", ptr(slot["indptr"]), ptr(slot["indices"]), B, nnz, ptr(self.indptr),
              ptr(self.indices), self._stream())
-        if self.D:
+        if self.D and cond_np is not None:
             slot["cond"][:B].numpy()[:] = cond_np
             self.cond[:B].copy_(slot["cond"][:B], non_blocking=True)
         ev = torch.cuda.Event()
@@ -373,6 +467,7 @@ class AAEEngine(object):
         slot["ev"] = ev
         return B, nnz
 
+    @_on_device
     def set_batch_device(self, indptr_dev, indices_dev, cond_dev=None):
         """Batch already resident in HBM (bench 'value' leg): device-to-device into the fixed buffers."""
         B = indptr_dev.numel() - 1
@@ -385,6 +480,78 @@ class AAEEngine(object):
             self.cond[:B].copy_(cond_dev, non_blocking=True)
         return B, nnz
 
+    @_on_device
+    def set_epoch_data(self, indptr, indices, cond=None):
+        """Device-side epoch feed: keep the whole training (or query) matrix in HBM -- CSR with sorted unique
+        columns -- and, optionally, the float32 condition matrix [n, D]; batches are then built on the device by
+        ``gather_batch`` from a row permutation (aae.py:815-823 without the host round trip)."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        ep = dict(n=int(indptr.shape[0]) - 1,
+                  indptr=torch.from_numpy(indptr).to(self.dev),
+                  indices=torch.from_numpy(indices if indices.size else np.zeros(1, np.int32)).to(self.dev),
+                  lens=np.diff(indptr), cond=None, perm=None)
+        if cond is not None:
+            cond = np.ascontiguousarray(cond, dtype=np.float32)
+            assert cond.shape == (ep["n"], self.D), (cond.shape, ep["n"], self.D)
+            ep["cond"] = torch.from_numpy(cond).to(self.dev)
+        self._epoch = ep
+        return ep
+
+    @_on_device
+    def set_epoch_perm(self, perm):
+        """Row order of the coming epoch (host permutation, e.g. the reference's np.random shuffle); None = identity.
+        Returns the nnz of every batch boundary prefix (int64 cumulative lengths in that order)."""
+        ep = self._epoch
+        if perm is None:
+            ep["perm"] = None
+            lens = ep["lens"]
+        else:
+            perm = np.ascontiguousarray(perm, dtype=np.int32)
+            assert perm.shape[0] == ep["n"]
+            ep["perm"] = torch.from_numpy(perm).to(self.dev)
+            lens = ep["lens"][perm]
+        csum = np.zeros(ep["n"] + 1, dtype=np.int64)
+        np.cumsum(lens, out=csum[1:])
+        ep["csum"] = csum
+        return csum
+
+    @_on_device
+    def gather_batch(self, row0, B):
+        """Build the batch of rows perm[row0 : row0+B) of the resident matrix in the device batch buffers."""
+        ep = self._epoch
+        nnz = int(ep["csum"][row0 + B] - ep["csum"][row0])
+        self._ensure_ws(B, nnz)
+        call("aae_batch_gather", ptr(ep["indptr"]), ptr(ep["indices"]), ptr(ep["perm"]), C.c_int64(row0), B,
+             ptr(self.indptr), ptr(self.indices), ptr(ep["cond"]) if ep["cond"] is not None else None, self.D,
+             ptr(self.cond) if ep["cond"] is not None else None, self._stream())
+        return B, nnz
+
+    @_on_device
+    def set_cond_rows(self, rows_dev, B):
+        """Condition rows of the batch (generic conditions, encoded through their Python protocol): device float32
+        [B, D] into the step's fixed condition buffer."""
+        self._ensure_ws(B, 0)
+        self.cond[:B].copy_(rows_dev, non_blocking=True)
+
+    @_on_device
+    def snapshot_dec_lin1(self):
+        """dec.lin1.weight [H, C+D] as it is before the step (the backward of the step uses it; the step's own Adam
+        update overwrites it) -- needed only to hand generic trainable conditions their gradient."""
+        n = self.H * self.Cp
+        if getattr(self, "_wd1_snap", None) is None:
+            self._wd1_snap = torch.empty(n, dtype=torch.float32, device=self.dev)
+        self._wd1_snap.copy_(self.dec[:n])
+
+    @_on_device
+    def cond_grad(self, B):
+        """dL/d(condition rows) [B, D] of the reconstruction phase just run: g_d1 (gradient at dec.lin1's output, written
+        by aae_ae_bwd) times the condition columns of the pre-step dec.lin1.weight.  The one torch op on this path; it
+        exists only for conditions that train their own parameters (aae.py:703-709)."""
+        Wd1 = self._wd1_snap.view(self.H, self.Cp)
+        return self.g_d1[:B] @ Wd1[:, self.C:]
+
+    @_on_device
     def set_rng_draws(self, B, draws):
         """Oracle-RNG mode: inject the 12 dropout masks and z_real drawn by torch in the reference's
         order (``oracle.aae_oracle.draw_step_rng``)."""
@@ -428,7 +595,10 @@ class AAEEngine(object):
         2 (disc/gen-phase h1pre), 3 (predict)."""
         if self.world == 1:
             return
-        if self.peer is not None and t.numel() <= self.peer.n_max:
+        if self.peer is not None:
+            if t.numel() > self.peer.n_max:
+                raise RuntimeError("exchange message of %d floats exceeds the peer buffers (%d): _ensure_ws must "
+                                   "have regrown them" % (t.numel(), self.peer.n_max))
             self.peer.allreduce(t, exchange, extra)
             N.count_launch(1)
             return
@@ -436,6 +606,28 @@ class AAEEngine(object):
         dist.all_reduce(t, group=self.group)
         if extra is not None:
             dist.all_reduce(extra, group=self.group)
+
+    def check_exchange(self):
+        """Raise if a peer-memory exchange timed out (its result was poisoned with NaN on the device): called at the
+        host's synchronisation points (losses, state export, predict)."""
+        if self.peer is not None and self.peer.error():
+            raise RuntimeError("aaerec_b200: a peer-memory exchange timed out (a rank died or the ranks diverged); "
+                               "the step's results are invalid")
+
+    def close(self):
+        """Release the peer-exchange mappings and buffer (item-sharded engines)."""
+        if self.peer is not None:
+            try:
+                torch.cuda.synchronize(self.dev)
+                self.peer.close()
+            finally:
+                self.peer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001 -- interpreter shutdown
+            pass
 
     def launches_per_step(self):
         """Kernels of ours launched by one train_step (counted while enqueueing; a graph replay
@@ -452,16 +644,34 @@ class AAEEngine(object):
         [ae_fwd+gather] -> K3 -> ae_bwd -> w1_rows_update || ae_wgrad -> [disc_phase+gather] -> disc_wgrad ->
         [gen_phase+gather] -> w1_rows_update || gen_wgrad -> step_finish, with batch_prepare -> W1 sweep on a side
         branch under the decoder kernel.  Item-sharded runs gather separately (the partial sums are all-reduced)."""
+        ctx = self._phase_ctx(B, injected)
+        self._enqueue_ae(ctx)
+        if self.adversarial:
+            self._enqueue_adversarial(B, ctx["dims"], ctx["bag"], ctx["dr"], ctx["fused"], ctx["cap"], injected)
+        self._enqueue_finish(ctx)
+
+    def _phase_ctx(self, B, injected):
+        fused = self.world == 1
+        lo, hi = self.v_begin, self.v_end
+        return dict(B=B, injected=injected, dims=AaeDims(B, self.H, self.C, self.D), dr=self._drops(B, injected),
+                    fused=fused, cap=self.uniq.numel(), n_total=float(B) * float(self.V),
+                    bag=N.bag(self.indptr, self.indices, self.W1t, self.normalize, lo, hi) if fused else N.bag())
+
+    def _sweep(self):
+        call("aae_w1_sweep_blocked", ptr(self.slot_of), self.Vloc, self.H, ptr(self.W1t), ptr(self.W1_m1),
+             ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), ptr(self.state), ptr(self.ktab),
+             self.w1_groups, 0, self.sweep_ctas if self.overlap_sweep else 0, self._stream())
+
+    def _enqueue_ae(self, ctx):
+        """ae_step (aae.py:676-711): reconstruction forward, fused decoder output layer, backward, enc_optim and
+        dec_optim."""
         s = self._stream
-        H, dims = self.H, AaeDims(B, self.H, self.C, self.D)
-        dr = self._drops(B, injected)
+        B, dims, dr, bag, fused, cap = ctx["B"], ctx["dims"], ctx["dr"], ctx["bag"], ctx["fused"], ctx["cap"]
+        H = self.H
         st = ptr(self.state)
         lo, hi = self.v_begin, self.v_end
-        n_total = float(B) * float(self.V)
-        cap = self.uniq.numel()
+        n_total = ctx["n_total"]
         cur = torch.cuda.current_stream(self.dev)
-        fused = self.world == 1
-        bag = N.bag(self.indptr, self.indices, self.W1t, self.normalize, lo, hi) if fused else N.bag()
         # ---- side branch: slots + transposed batch view, then the zero-gradient Adam decay of every row that is
         # not in the batch (both optimizer states, one pass)
         self._ev_fork.record(cur)
@@ -470,16 +680,10 @@ class AAEEngine(object):
             call("aae_batch_prepare", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.slot_of), ptr(self.uniq),
                  ptr(self.n_uniq), ptr(self.csc_cnt), ptr(self.csc_pos), ptr(self.csc_off), ptr(self.csc_row), cap, s())
             self._ev_prep.record(self.side)
-
-        def sweep():
-            call("aae_w1_sweep_blocked", ptr(self.slot_of), self.Vloc, H, ptr(self.W1t), ptr(self.W1_m1),
-                 ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), st, ptr(self.ktab),
-                 self.w1_groups, 0, self.sweep_ctas if self.overlap_sweep else 0, s())
         # rows of this batch: pending zero-gradient steps applied before the encoder reads them
         call("aae_w1_catchup", ptr(self.indptr), ptr(self.indices), B, lo, hi, ptr(self.w1_claim), ptr(self.W1t),
              ptr(self.W1_m1), ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), H, st,
              ptr(self.ktab), s())
-        # ---- ae_step (aae.py:676-711)
         if not fused:
             call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
                  lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
@@ -487,16 +691,14 @@ class AAEEngine(object):
         call("aae_ae_fwd_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
              dr["ae_e2"], dr["ae_d1"], dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1),
              ptr(self.h2), ptr(self.dh2), s())
-        call("aae_dec_out_train", ptr(self.h2), B, H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m), ptr(self.Wd3_v),
-             ptr(self.bd3_m), ptr(self.bd3_v), lo, self.Vloc, ptr(self.indptr), ptr(self.indices), n_total, st,
-             ptr(self.dh2), ptr(self.loss_sums), self.impl_for(B), s())
+        self._dec_out_train(B, n_total)
         if self.overlap_sweep:
             # the decoder kernel owns the SMs and starves beside a bandwidth-bound neighbour (measured: 190 -> 375 us),
             # so the sweep runs under the latency-bound tail of the step instead, sized to leave the SMs open
             self._ev_k3.record(cur)
             self.side.wait_event(self._ev_k3)
             with torch.cuda.stream(self.side):
-                sweep()
+                self._sweep()
         if self.world > 1:
             self._allreduce(self.dh2[:B], 1, self.loss_sums[:1])
         call("aae_ae_bwd", dims, ptr(self.dh2), ptr(self.enc), ptr(self.dec), dr["ae_e1"], dr["ae_e2"], dr["ae_d1"],
@@ -514,23 +716,36 @@ class AAEEngine(object):
              ptr(self.indptr), self.normalize, ptr(self.g_h1), ptr(self.W1t), ptr(self.W1_m1), ptr(self.W1_v1), H, st,
              0, None if self.adversarial else ptr(self.w1_last), s())
         self._join()
-        if self.adversarial:
-            self._enqueue_adversarial(B, dims, bag, dr, fused, cap, injected)
+
+    def _dec_out_train(self, B, n_total):
+        """The n_items-wide decoder output layer, fused forward + BCE + backward + dec_optim (K3)."""
+        call("aae_dec_out_train", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m),
+             ptr(self.Wd3_v), ptr(self.bd3_m), ptr(self.bd3_v), self.v_begin, self.Vloc, ptr(self.indptr),
+             ptr(self.indices), n_total, ptr(self.state), ptr(self.dh2), ptr(self.loss_sums), self.impl_for(B),
+             self._stream())
+
+    def _enqueue_finish(self, ctx):
+        cur = torch.cuda.current_stream(self.dev)
         if self.overlap_sweep:
             self._ev_join.record(self.side)
             cur.wait_event(self._ev_join)
         else:
             cur.wait_event(self._ev_prep)
-            sweep()
-        call("aae_step_finish", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), cap, ptr(self.loss_sums), 3,
-             n_total, B, ptr(self.losses), st, ptr(self.ktab), s())
+            self._sweep()
+        call("aae_step_finish", ptr(self.slot_of), ptr(self.uniq), ptr(self.n_uniq), ctx["cap"], ptr(self.loss_sums), 3,
+             ctx["n_total"], ctx["B"], ptr(self.losses), ptr(self.state), ptr(self.ktab), self._stream())
 
     def _enqueue_adversarial(self, B, dims, bag, dr, fused, cap, injected):
         """disc_step (aae.py:713-732) and gen_step (aae.py:734-743) of one partial_fit."""
+        self._enqueue_disc(B, dims, bag, dr, fused, injected)
+        self._enqueue_gen(B, dims, bag, dr, cap)
+
+    def _enqueue_disc(self, B, dims, bag, dr, fused, injected):
+        """disc_step (aae.py:713-732): eval-mode encoder on the batch, prior sample, discriminator loss, disc_optim.
+        Also computes the pre-dropout first encoder layer that gen_step shares (identical weights and input)."""
         s = self._stream
         H, st = self.H, ptr(self.state)
         lo, hi = self.v_begin, self.v_end
-        # ---- disc_step (aae.py:713-732) and gen_step (734-743)
         if not fused:
             call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
                  lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
@@ -540,6 +755,11 @@ class AAEEngine(object):
              dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
         call("aae_disc_wgrad", dims, ptr(self.disc_acts), ptr(self.disc_grads), None,
              N.adam_block(self.disc, self.disc_m, self.disc_v, 1), st, s())
+
+    def _enqueue_gen(self, B, dims, bag, dr, cap):
+        """gen_step (aae.py:734-743): train-mode encoder against the updated discriminator, gen_optim."""
+        s = self._stream
+        H, st = self.H, ptr(self.state)
         call("aae_gen_phase_bag", dims, bag, ptr(self.h1pre2), ptr(self.enc), ptr(self.disc), dr["gen_e1"],
              dr["gen_e2"], dr["gen_q1"], dr["gen_q2"], st, ptr(self.ga1), ptr(self.ga2), ptr(self.gg_z), ptr(self.gg_e2),
              ptr(self.gg_h1), ptr(self.loss_sums[2:]), s())
@@ -550,6 +770,40 @@ class AAEEngine(object):
              ptr(self.indptr), self.normalize, ptr(self.gg_h1), ptr(self.W1t), ptr(self.W1_m2), ptr(self.W1_v2), H, st,
              1, ptr(self.w1_last), s())
         self._join()
+
+    # ------------------------------------------------------------------ the three phases as separate calls
+    @_on_device
+    def phase_step(self, phase, B, injected=False):
+        """ae_step / disc_step / gen_step of the reference (aae.py:676-743) as separate, eager calls on the batch in the
+        device buffers.  The four Adam optimizers share one step counter (they all step once per partial_fit,
+        aae.py:745-766), so the phases must be called in the reference's order ae -> disc -> gen; the counter advances
+        after gen (after ae for the plain AutoEncoder).  Returns the phase's loss (synchronises)."""
+        order = ("ae", "disc", "gen") if self.adversarial else ("ae",)
+        want = order[self._phase_cursor]
+        if phase != want:
+            raise RuntimeError("phase %r called out of order (expected %r): the optimizers share one Adam step "
+                               "counter, so ae_step, disc_step, gen_step run in partial_fit's order" % (phase, want))
+        if phase == "ae":
+            self._phase_ctx_live = self._phase_ctx(B, injected)
+        ctx = self._phase_ctx_live
+        if ctx is None or ctx["B"] != B:
+            raise RuntimeError("phase %r: batch differs from the one ae_step saw" % (phase,))
+        idx = order.index(phase)
+        if phase == "ae":
+            self._enqueue_ae(ctx)
+        elif phase == "disc":
+            self._enqueue_disc(B, ctx["dims"], ctx["bag"], ctx["dr"], ctx["fused"], injected)
+        else:
+            self._enqueue_gen(B, ctx["dims"], ctx["bag"], ctx["dr"], ctx["cap"])
+        denom = ctx["n_total"] if phase == "ae" else float(B)
+        loss = float(self.loss_sums[idx].item()) / denom
+        self._phase_cursor = (self._phase_cursor + 1) % len(order)
+        if self._phase_cursor == 0:
+            self._enqueue_finish(ctx)
+            self._phase_ctx_live = None
+            self.steps_done += 1
+            self._w1_dirty = True
+        return loss
 
     def _run(self, key, enqueue):
         """Enqueue ``enqueue()`` eagerly, or (graph mode) capture it once per ``key`` and replay the graph."""
@@ -578,6 +832,7 @@ class AAEEngine(object):
             self._graphs[key] = g
         g.replay()
 
+    @_on_device
     def train_step(self, B, injected=False):
         """Enqueue one partial_fit on the batch currently in the device batch buffers.  Losses
         (R, D, G) land in ``self.losses`` (device float32[3])."""
@@ -587,7 +842,9 @@ class AAEEngine(object):
         self.steps_done += 1
         self._w1_dirty = True
 
-    def train_step_host(self, indptr_np, indices_np, cond_np=None, injected=False, rng_draws=None):
+    @_on_device
+    def train_step_host(self, indptr_np, indices_np, cond_np=None, injected=False, rng_draws=None,
+                        cond_on_device=False):
         """One partial_fit straight from host CSR rows (int32, row-relative indptr): the end-to-end entry.  The batch
         is written into one of two pinned slots and moved with one H2D copy; the step's CUDA graph itself pushes the
         three losses back into the slot's pinned ``losses`` (``aae_copy_words_sel``) -- no D2H hop behind the step.  Returns the slot: ``slot['losses']`` is valid once ``slot['ev']`` has completed;
@@ -607,7 +864,8 @@ class AAEEngine(object):
         pk = slot["packed"].numpy()
         pk[: B + 1] = indptr_np
         pk[off: off + nnz] = indices_np[:nnz]
-        if self.D:
+        host_cond = bool(self.D) and not cond_on_device     # else: set_cond_rows already filled the condition buffer
+        if host_cond:
             slot["cond"][:B].numpy()[:] = cond_np
         if rng_draws is not None:
             self.set_rng_draws(B, rng_draws)
@@ -617,7 +875,7 @@ class AAEEngine(object):
         # at ~100 MB/s: +120 us per 8 KB batch); losses out: written into the slot's pinned memory by the graph itself
         call("aae_upload_batch", ptr(slot["packed"]), ptr(slot["packed"][off:]), B, nnz, ptr(self.indptr),
              ptr(self.indices), self._stream())
-        if self.D:
+        if host_cond:
             self.cond[:B].copy_(slot["cond"][:B], non_blocking=True)
 
         def enqueue():
@@ -632,6 +890,7 @@ class AAEEngine(object):
         self._w1_dirty = True
         return slot
 
+    @_on_device
     def flush_w1(self):
         """Apply every pending zero-gradient Adam step to W1t (time-blocked policy): after this the weights are
         exactly those of dense Adam after ``steps_done`` steps.  Needed before reading rows outside a training
@@ -656,6 +915,7 @@ class AAEEngine(object):
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------ predict
+    @_on_device
     def predict_h2(self, B):
         """eval-mode encoder + condition + decoder head for the batch in the device buffers."""
         self.flush_w1()
@@ -671,6 +931,7 @@ class AAEEngine(object):
              ptr(self.h2), self._stream())
         return self.h2[:B]
 
+    @_on_device
     def scores(self, B, out, apply_sigmoid=True):
         """out[B, >=Vloc] <- sigmoid probabilities (reference predict) or logits of the local items."""
         self.predict_h2(B)
@@ -678,6 +939,38 @@ class AAEEngine(object):
              1 if apply_sigmoid else 0, ptr(out), out.stride(0), self.impl_for_scores(), self._stream())
         return out
 
+    @_on_device
+    def gold_ranks(self, B, gold_indptr, gold_indices, scratch=None, mask_known=True):
+        """Ranks (1-based) of the gold items of the batch in the device buffers, in the descending order of
+        remove_non_missing(predict(X), X) (known items at the bottom; ties by lower item id): int64 host array aligned
+        with ``gold_indices``.  ``gold_indptr`` [B+1] / ``gold_indices``: CSR of the held-out items (global ids).
+        The [B, V] score matrix lives in HBM only (never on the host)."""
+        n_gold = int(gold_indptr[-1])
+        if n_gold == 0:
+            return np.zeros(0, dtype=np.int64)
+        if scratch is None or scratch.shape[0] < B or scratch.shape[1] < self.Vloc:
+            scratch = torch.empty(B, self.Vloc, dtype=torch.float32, device=self.dev)
+        gp = torch.from_numpy(np.ascontiguousarray(gold_indptr, dtype=np.int32)).to(self.dev)
+        gi = torch.from_numpy(np.ascontiguousarray(gold_indices, dtype=np.int32)).to(self.dev)
+        zg = torch.empty(n_gold, dtype=torch.float32, device=self.dev)
+        cnt = torch.zeros(n_gold, dtype=torch.int32, device=self.dev)
+        self.scores(B, scratch, apply_sigmoid=False)
+
+        def run(given):
+            call("aae_rank_counts", ptr(scratch), scratch.stride(0), B, self.Vloc, self.v_begin,
+                 ptr(self.indptr) if (mask_known and not given) else None,
+                 ptr(self.indices) if (mask_known and not given) else None, ptr(gp), ptr(gi), n_gold, ptr(zg),
+                 1 if given else 0, ptr(cnt), self._stream())
+        run(False)
+        if self.world > 1:
+            import torch.distributed as dist
+            zg.copy_(torch.nan_to_num(zg, nan=0.0))
+            dist.all_reduce(zg, group=self.group)
+            run(True)
+            dist.all_reduce(cnt, group=self.group)
+        return cnt.cpu().numpy().astype(np.int64) + 1
+
+    @_on_device
     def topk(self, B, k, scratch=None, mask_known=True, fused=None):
         """Masked top-k of the batch in the device buffers: returns (idx int32 [B,k] global item ids,
         val float32 [B,k] logits), descending.  Item-sharded: local top-k + all-gather + merge.

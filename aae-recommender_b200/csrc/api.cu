@@ -24,12 +24,16 @@ int check_launch(const char* what) {
 }
 
 int sm_count() {
-  static int n = 0;
+  // cached per device: a process may drive several GPUs (one engine each)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }

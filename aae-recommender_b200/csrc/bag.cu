@@ -768,6 +768,91 @@ int aae_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, cons
   adam_dense_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, st, which);
   return check_launch("adam_dense");
 }
+} // extern "C"
+namespace aae {
+// ---------------------------------------------------------------------------------------------
+// Device-side epoch feed (aae.py:815-823 replaces sklearn.utils.shuffle + X_shuf[s:e].toarray()): the whole CSR
+// matrix (and the condition matrix) stays in HBM, the host uploads one permutation per epoch, and every batch's
+// packed CSR rows are built here from perm[row0 .. row0+B).
+//   kernel 1 (one block): row lengths -> exclusive scan -> out_indptr[0..B]
+//   kernel 2 (warp per row): column indices of the row, and its condition row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) batch_gather_scan_kernel(const int64_t* __restrict__ indptr_all,
+                                                                 const int32_t* __restrict__ perm, int64_t row0, int B,
+                                                                 int32_t* __restrict__ out_indptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int r = base + tid;
+    int len = 0;
+    if (r < B) {
+      const int64_t src = perm ? (int64_t)perm[row0 + r] : row0 + r;
+      len = (int)(indptr_all[src + 1] - indptr_all[src]);
+    }
+    int x = len;                         // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;                // inclusive totals of the warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (warp ? warp_tot[warp - 1] : 0) + x - len;
+    if (r < B) out_indptr[r] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) out_indptr[B] = carry_s;
+}
+__global__ void __launch_bounds__(256) batch_gather_copy_kernel(const int64_t* __restrict__ indptr_all,
+                                                                const int32_t* __restrict__ indices_all,
+                                                                const int32_t* __restrict__ perm, int64_t row0, int B,
+                                                                const int32_t* __restrict__ out_indptr,
+                                                                int32_t* __restrict__ out_indices,
+                                                                const float* __restrict__ cond_all, int D,
+                                                                float* __restrict__ out_cond) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    const int64_t src = perm ? (int64_t)perm[row0 + r] : row0 + r;
+    const int64_t p0 = indptr_all[src];
+    const int len = (int)(indptr_all[src + 1] - p0);
+    const int o0 = out_indptr[r];
+    for (int j = lane; j < len; j += 32) out_indices[o0 + j] = indices_all[p0 + j];
+    if (cond_all)
+      for (int j = lane; j < D; j += 32) out_cond[(size_t)r * D + j] = cond_all[(size_t)src * D + j];
+  }
+}
+
+}  // namespace aae
+extern "C" {
+int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, const int32_t* perm, int64_t row0, int B,
+                     int32_t* out_indptr, int32_t* out_indices, const float* cond_all, int D, float* out_cond,
+                     void* stream) {
+  AAE_REQUIRE(indptr_all && indices_all && out_indptr && out_indices, "null pointer");
+  AAE_REQUIRE(B > 0 && row0 >= 0 && D >= 0, "bad size");
+  AAE_REQUIRE(!cond_all || (out_cond && D > 0), "condition rows without an output buffer");
+  batch_gather_scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(indptr_all, perm, row0, B, out_indptr);
+  const int blocks = std::min(4 * sm_count(), std::max(1, cdiv(B, 8)));
+  batch_gather_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(indptr_all, indices_all, perm, row0, B, out_indptr,
+                                                                out_indices, cond_all, D, out_cond);
+  return check_launch("batch_gather");
+}
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream) {
   AAE_REQUIRE(indptr_host && indices_host && indptr && indices, "null pointer");

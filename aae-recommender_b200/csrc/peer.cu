@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
     for (int u = u0 + tid; u < u1; u += blockDim.x) mine[u] = data[u];
   }
   if (b == 0 && tid < n_extra) mine_x[tid] = extra[tid];
+  __shared__ int timed_out;
+  if (tid == 0) timed_out = 0;
   __threadfence_system();
   __syncthreads();
   // 2. signal, 3. wait (one thread per peer)
@@ -96,12 +98,17 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
     while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
       if (clock64() - t0 > spin_cycles) {   // a peer died or diverged: report, do not hang the box
         my->err = 1u;
+        timed_out = 1;
         break;
       }
       __nanosleep(20);
     }
   }
   __syncthreads();
+  // A timed-out wait is fatal for the step: the peers' slots may be stale, so the result is poisoned with NaN
+  // (losses and weights turn NaN at once) instead of being summed from incomplete data; the host raises at its
+  // next synchronisation point (AAEEngine.check_exchange).
+  const float poison = timed_out ? __int_as_float(0x7fc00000) : 0.f;
   // 4. reduce in rank order
   if (vec) {
     for (int u = u0 + tid; u < u1; u += blockDim.x) {
@@ -112,6 +119,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
         if (r == 0) acc = x;
         else { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
       }
+      if (timed_out) acc = make_float4(poison, poison, poison, poison);
       reinterpret_cast<float4*>(data)[u] = acc;
     }
   } else {
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
         const float x = (r == P.rank) ? *src : ld_volatile_f(src);
         acc = (r == 0) ? x : acc + x;
       }
-      data[u] = acc;
+      data[u] = timed_out ? poison : acc;
     }
   }
   if (b == 0 && tid < n_extra) {
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
       const double x = (r == P.rank) ? *src : ld_volatile_d(src);
       acc = (r == 0) ? x : acc + x;
     }
-    extra[tid] = acc;
+    extra[tid] = timed_out ? (double)poison : acc;
   }
   // 5. the last block to finish advances the sequence number (every block has read it by then)
   __syncthreads();
@@ -226,9 +234,9 @@ int aae_peer_allreduce(aae_peers peers, int exchange, float* data, int n, double
   for (int r = 0; r < peers.world; ++r) AAE_REQUIRE(peers.base[r], "peer buffer not mapped");
   if (peers.world == 1) return AAE_OK;
   const int blocks = std::max(1, std::min(PX_MAX_BLOCKS, cdiv((n + 3) >> 2, 256)));
-  // ~2 s at 1.9 GHz: far beyond any legitimate skew between the ranks of one box
+  // ~20 s at 1.9 GHz: beyond any legitimate skew between the ranks of one box (graph capture, workspace growth)
   peer_allreduce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(peers, exchange, data, n, extra, n_extra, n_max,
-                                                            4000000000LL);
+                                                            40000000000LL);
   return check_launch("peer_allreduce");
 }
 

@@ -389,6 +389,75 @@ static TopkPlan make_plan(int B, int Vloc, int k) {
 }
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+
+// ---------------------------------------------------------------------------------------------
+// Rank of the gold items (evaluation.py:70-164, 202-240 need, per test row, the positions of the
+// held-out items in the descending ranking of remove_non_missing(predict(X), X)): rank - 1 = number of unknown
+// items scored strictly higher (+ equal-score items with a lower id: the deterministic tie order of the top-k
+// kernels).  Known items are -FLT_MAX in `scores` (mask_known_kernel) = the bottom of the ranking, where the
+// reference's min-max scaling + zeroing puts them.
+//   gold_scores_kernel : zg[p] = scores[row(p), gold[p]]  (NaN when the item belongs to another shard)
+//   rank_count_kernel  : grid (column chunks, rows); each CTA counts, for up to RC_G gold items of its row at a
+//                        time, the entries of its column chunk that rank before them; one atomicAdd per CTA and gold.
+// ---------------------------------------------------------------------------------------------
+__global__ void gold_scores_kernel(const float* __restrict__ scores, int64_t lds, int B, int Vloc, int v_begin,
+                                   const int32_t* __restrict__ gold_indptr, const int32_t* __restrict__ gold_indices,
+                                   float* __restrict__ zg) {
+  const int n = gold_indptr[B];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int lo = 0, hi = B;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (gold_indptr[mid + 1] <= e) lo = mid + 1; else hi = mid;
+    }
+    const int i = gold_indices[e] - v_begin;
+    zg[e] = (i >= 0 && i < Vloc) ? scores[(size_t)lo * lds + i] : __int_as_float(0x7fc00000);
+  }
+}
+constexpr int RC_THREADS = 256, RC_G = 8, RC_CHUNK = 16384;
+__global__ void __launch_bounds__(RC_THREADS) rank_count_kernel(const float* __restrict__ scores, int64_t lds, int Vloc,
+                                                                int v_begin,
+                                                                const int32_t* __restrict__ gold_indptr,
+                                                                const int32_t* __restrict__ gold_indices,
+                                                                const float* __restrict__ zg,
+                                                                int32_t* __restrict__ cnt) {
+  __shared__ int red[RC_THREADS / 32][RC_G];
+  const int row = blockIdx.y;
+  const int c0 = blockIdx.x * RC_CHUNK, c1 = min(Vloc, c0 + RC_CHUNK);
+  const int p0 = gold_indptr[row], p1 = gold_indptr[row + 1];
+  const float* r = scores + (size_t)row * lds;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g0 = p0; g0 < p1; g0 += RC_G) {
+    float z[RC_G];
+    int id[RC_G], c[RC_G];
+#pragma unroll
+    for (int j = 0; j < RC_G; ++j) {
+      const bool ok = g0 + j < p1;
+      z[j] = ok ? zg[g0 + j] : __int_as_float(0x7fc00000);      // NaN compares false: counts stay 0
+      id[j] = ok ? gold_indices[g0 + j] - v_begin : -1;
+      c[j] = 0;
+    }
+    for (int v = c0 + threadIdx.x; v < c1; v += RC_THREADS) {
+      const float x = r[v];
+#pragma unroll
+      for (int j = 0; j < RC_G; ++j) c[j] += (x > z[j] || (x == z[j] && v < id[j])) ? 1 : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < RC_G; ++j) {
+      int t = c[j];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) red[warp][j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < RC_G && g0 + threadIdx.x < p1) {
+      int t = 0;
+      for (int w = 0; w < RC_THREADS / 32; ++w) t += red[w][threadIdx.x];
+      if (t) atomicAdd(cnt + g0 + threadIdx.x, t);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace aae
 
 using namespace aae;
@@ -423,6 +492,29 @@ int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, co
     if (rc) return rc;
   }
   return launch_row_topk(scores, lds, B, Vloc, k, v_begin, nullptr, idx_out, val_out, as_stream(stream));
+}
+
+int aae_rank_counts(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
+                    const int32_t* indices, const int32_t* gold_indptr, const int32_t* gold_indices, int n_gold,
+                    float* gold_scores, int gold_scores_given, int32_t* counts, void* stream) {
+  AAE_REQUIRE(scores && gold_indptr && gold_indices && gold_scores && counts, "null pointer");
+  AAE_REQUIRE(B > 0 && Vloc > 0 && n_gold >= 0 && lds >= Vloc, "bad size");
+  cudaStream_t s = as_stream(stream);
+  if (indptr && indices) {
+    mask_known_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv((int64_t)B * 32, 256))), 256, 0, s>>>(
+        scores, lds, B, Vloc, v_begin, indptr, indices);
+    int rc = check_launch("mask_known");
+    if (rc) return rc;
+  }
+  if (n_gold == 0) return AAE_OK;
+  cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_gold, s);
+  if (!gold_scores_given)
+    gold_scores_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(n_gold, 256))), 256, 0, s>>>(
+        scores, lds, B, Vloc, v_begin, gold_indptr, gold_indices, gold_scores);
+  dim3 grid((unsigned)cdiv(Vloc, RC_CHUNK), (unsigned)B);
+  rank_count_kernel<<<grid, RC_THREADS, 0, s>>>(scores, lds, Vloc, v_begin, gold_indptr, gold_indices, gold_scores,
+                                                counts);
+  return check_launch("rank_count");
 }
 
 int64_t aae_predict_topk_work_bytes(int B, int Vloc, int k) {

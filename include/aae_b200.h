@@ -331,6 +331,32 @@ int aae_peer_error(const void* base, int* err_host);
  * mode 3: D[128,32] = A[128,104]^T.Bm[128,32] (rows >= 104 undefined).  split = 3 (3xTF32) or 1. */
 int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int split, void* stream);
 
+/* ---- GPU-side ranking metrics -----------------------------------------------------
+ * Replaces the dense D2H + host argsort behind the harness' metrics (evaluation.py:70-164 RankingMetric / MRR /
+ * MAP / P, evaluate 202-240 on remove_non_missing(predict(X), X)): for every held-out ("gold") item of every
+ * query row, counts[p] = number of items of the local shard that rank before it -- unknown items with a strictly
+ * higher score, or an equal score and a lower id (the tie order of the top-k kernels); known items of the row
+ * (CSR indptr/indices, may be NULL) are pushed to the bottom first, as the reference's zeroing after min-max
+ * scaling does.  rank = 1 + counts (summed over item shards).  scores [B, >=Vloc] (row pitch lds) are the logits
+ * from aae_dec_out_scores and are modified (known entries := -FLT_MAX).  gold_indptr [B+1] / gold_indices [n_gold]:
+ * CSR of the gold items (global ids); gold_scores [n_gold]: gold_scores_given == 0: receives their logits (NaN when
+ * the item lies in another shard -- item-sharded callers replace NaN by 0, sum over the shards and call again with
+ * gold_scores_given != 0, then sum the counts). */
+int aae_rank_counts(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
+                    const int32_t* indices, const int32_t* gold_indptr, const int32_t* gold_indices, int n_gold,
+                    float* gold_scores, int gold_scores_given, int32_t* counts, void* stream);
+
+/* ---- device-side epoch feed --------------------------------------------------------------------
+ * Replaces sklearn.utils.shuffle(X, *condition_data) + X_shuf[start:end].toarray() (aae.py:815-823) and the
+ * condition slices c[start:end] (aae.py:828): the training matrix (CSR: int64 indptr_all, int32 indices_all, sorted
+ * unique columns) and the float32 condition matrix cond_all [n,D] stay resident in HBM; the host uploads one
+ * permutation per epoch (the same np.random permutation the reference draws) and this call builds the packed CSR rows
+ * (and condition rows) of the batch perm[row0 .. row0+B) in the step's fixed batch buffers.  perm == NULL: identity
+ * (predict).  cond_all may be NULL.  out_indices must hold the batch's nnz (the caller knows the row lengths). */
+int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, const int32_t* perm, int64_t row0, int B,
+                     int32_t* out_indptr, int32_t* out_indices, const float* cond_all, int D, float* out_cond,
+                     void* stream);
+
 /* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);

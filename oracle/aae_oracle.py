@@ -377,3 +377,46 @@ def argtopk(X, k):
 def rank_topk(Y_pred, X_test, k):
     """The consumer chain evaluation.py:375 -> 388 / make_submission.py:36-53."""
     return argtopk(remove_non_missing(Y_pred, X_test), k)[1]
+
+
+# ---- ranking metrics (evaluation.py:70-164, 202-240; rank_metrics_with_std.py:13-40, 108-154) ----------------
+def relevance_in_rank_order(y_true, y_pred, k):
+    """RankingMetric.__call__ (evaluation.py:81-92): gold flags looked up in the top-k order of the prediction."""
+    ind = argtopk(np.asarray(y_pred), k)
+    return np.asarray(y_true)[ind]
+
+
+def _reciprocal_rank(r):
+    z = np.asarray(r).nonzero()[0]
+    return 1.0 / (z[0] + 1) if z.size else 0.0
+
+
+def _average_precision(r):
+    r = np.asarray(r) != 0
+    out = [np.mean(r[:i + 1]) for i in range(r.size) if r[i]]
+    return float(np.mean(out)) if out else 0.0
+
+
+def metric_per_row(name, y_true, y_pred):
+    """One metric of evaluation.py:166-180 ('mrr@5', 'map', 'P@1' ...) per row of a dense (gold, prediction) pair."""
+    name = name.lower()
+    kind, _, kk = name.partition("@")
+    k = int(kk) if kk else None
+    rs = relevance_in_rank_order(y_true, y_pred, k)
+    if kind == "mrr":
+        return np.array([_reciprocal_rank(r) for r in rs])
+    if kind == "map":
+        return np.array([_average_precision(r) for r in rs])
+    if kind == "p":
+        return (rs > 0).mean(axis=1)
+    raise KeyError(name)
+
+
+def evaluate(y_true, y_pred, metrics):
+    """evaluation.py:202-240 (batch_size=None): [(mean, std)] per metric."""
+    y_true = y_true.toarray() if hasattr(y_true, "toarray") else np.asarray(y_true)
+    out = []
+    for m in metrics:
+        v = metric_per_row(m, y_true, y_pred)
+        out.append((float(v.mean()), float(v.std())))
+    return out

@@ -1,12 +1,14 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference package.
 
-Imports ``aaerec`` from ``/root/reference`` (read-only, exists only in the
-authoring container, never on the GPU box) so that ``oracle/make_golden.py``
-can (a) pin the restatement in ``oracle/aae_oracle.py`` against the real
-reference and (b) dump golden vectors into ``tests/golden/``.
+Imports ``aaerec`` from ``/root/reference`` (read-only, authoring container) or
+from the unmodified copy ``oracle/_ref`` that ``oracle/build_ref.py`` makes
+(git-ignored, ships to the GPU box) so that (a) ``oracle/make_golden.py`` can
+pin the restatement in ``oracle/aae_oracle.py`` against the real reference and
+dump golden vectors into ``tests/golden/``, (b) ``bench.py --impl reference`` /
+the ``gpu_baseline`` leg can time the reference's own code, (c) the harness
+parity test can run the reference's ``Evaluation`` on both recommenders.
 
-Nothing in the product package, in ``-m gpu`` tests, in ``smoke()`` or in
-``bench.py`` may import this module.
+Nothing in the product package may import this module.
 
 Shims (none of them touches the hot path):
   * ``gensim.models.keyedvectors.KeyedVectors`` -- imported at
@@ -20,7 +22,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("AAE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _pick_root():
+    """The reference tree: AAE_REFERENCE_ROOT, else /root/reference (authoring container), else the unmodified copy
+    that oracle/build_ref.py made under oracle/_ref (the GPU box)."""
+    for cand in (os.environ.get("AAE_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "aaerec")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
