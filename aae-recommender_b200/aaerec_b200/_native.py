@@ -82,6 +82,8 @@ _SIGS = {
     "aae_disc_wgrad": (I, [AaeDims, P, P, P, AdamBlock, P, P]),
     "aae_gen_wgrad": (I, [AaeDims, P, P, P, P, P, P, AdamBlock, P, P]),
     "aae_dec_out_train": (I, [P, I, I, P, P, P, P, P, P, I, I, P, P, D, P, P, P, I, P]),
+    "aae_dec_out_train_ws": (I, [P, I, I, P, P, P, P, P, P, I, I, P, P, D, P, P, P, I, P, I64, P]),
+    "aae_dec_out_train_work_floats": (I64, [I, I, I, I]),
     "aae_predict_tail": (I, [AaeDims, P, P, P, P, P, P]),
     "aae_dec_out_scores": (I, [P, I, I, P, P, I, I, P, I64, I, P]),
     "aae_topk_work_bytes": (I64, [I, I]),

@@ -354,7 +354,9 @@ class AdversarialAutoEncoder(object):
             eng.upload_csr(indptr, indices, rows)
             self._phase_B = B
             draws = self._draws(B)
-            self._phase_injected = draws is not None and eng.set_rng_draws(B, draws)
+            if draws is not None:
+                eng.set_rng_draws(B, draws)
+            self._phase_injected = draws is not None
             loss = eng.phase_step("ae", B, self._phase_injected)
             self._cond_end(leaves, B)
             return loss
@@ -423,8 +425,9 @@ class AdversarialAutoEncoder(object):
                     _, leaves = self._cond_begin([ad.take(c, rows) for c in condition_data], B)
                 eng.gather_batch(start, B)
                 draws = self._draws(B)
-                injected = draws is not None and eng.set_rng_draws(B, draws)
-                eng.train_step(B, injected)
+                if draws is not None:
+                    eng.set_rng_draws(B, draws)      # oracle RNG: masks (none when p == 0) and the prior sample
+                eng.train_step(B, draws is not None)
                 self._cond_end(leaves, B)
                 if self.verbose or self.record_losses:
                     cur = self.losses()

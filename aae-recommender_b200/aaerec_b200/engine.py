@@ -131,6 +131,7 @@ class AAEEngine(object):
         self._phase_cursor = 0
         self._phase_ctx_live = None
         self._epoch = None
+        self._gwork = None
         f32 = dict(dtype=torch.float32, device=self.dev)
         H, Cc, Cp, Vl = self.H, self.C, self.Cp, max(self.Vloc, 1)
         z = lambda *s: torch.zeros(*s, **f32)
@@ -225,12 +226,15 @@ class AAEEngine(object):
         return names[impl]
 
     def impl_for(self, B):
-        """Decoder-output kernel for a batch of B rows: 1 = tcgen05 3xTF32 (n_hidden % 4 == 0, n_hidden <= 124;
-        training additionally needs B <= 128), 0 = fp32 CUDA cores (any shape up to n_hidden 512)."""
+        """Decoder-output kernel for a batch of B rows: 1 = tcgen05 3xTF32 (n_hidden % 4 == 0, n_hidden <= 124; any
+        batch size: batches beyond one row chunk are walked chunk by chunk, aae_dec_out_train_ws), 0 = fp32 CUDA cores
+        (any shape up to n_hidden 512)."""
         if self.impl >= 0:
             return self.impl
         ok = self.H % 4 == 0 and self.H <= 124
-        return 1 if (ok and B <= 128) else 0
+        if ok and B > 128 and int(N.load().aae_dec_out_train_work_floats(B, self.H, max(self.Vloc, 1), 1)) == 0:
+            ok = False      # n_hidden outside the pipelined kernel's envelope: no chunked path
+        return 1 if ok else 0
 
     def impl_for_scores(self):
         if self.impl >= 0:
@@ -719,10 +723,18 @@ class AAEEngine(object):
 
     def _dec_out_train(self, B, n_total):
         """The n_items-wide decoder output layer, fused forward + BCE + backward + dec_optim (K3)."""
-        call("aae_dec_out_train", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m),
+        impl = self.impl_for(B)
+        need = int(N.load().aae_dec_out_train_work_floats(B, self.H, self.Vloc, impl))
+        if need and (self._gwork is None or self._gwork.numel() < need):
+            # gradient scratch of the chunked tensor-core path (allocated outside any graph capture: _run warms up
+            # eagerly first)
+            self._gwork = torch.empty(need, dtype=torch.float32, device=self.dev)
+        call("aae_dec_out_train_ws", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), ptr(self.Wd3_m),
              ptr(self.Wd3_v), ptr(self.bd3_m), ptr(self.bd3_v), self.v_begin, self.Vloc, ptr(self.indptr),
-             ptr(self.indices), n_total, ptr(self.state), ptr(self.dh2), ptr(self.loss_sums), self.impl_for(B),
-             self._stream())
+             ptr(self.indices), n_total, ptr(self.state), ptr(self.dh2), ptr(self.loss_sums), impl,
+             ptr(self._gwork) if need else None, C.c_int64(need), self._stream())
+        if need:
+            N.count_launch((B + 103) // 104 - 1)
 
     def _enqueue_finish(self, ctx):
         cur = torch.cuda.current_stream(self.dev)

@@ -45,7 +45,9 @@ int dec_out_scores_simt(const float* h2, int B, int H, const float* Wd3, const f
                         float* out, int64_t ldo, cudaStream_t s);
 int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
                      int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
-                     const aae_step_state* st, float* dh2, double* loss_sum, int split, bool pipelined, cudaStream_t s);
+                     const aae_step_state* st, float* dh2, double* loss_sum, int split, bool pipelined, float* gwork,
+                     cudaStream_t s);
+int tc2_max_rows(int H);
 int dec_out_scores_tc(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,
                       float* out, int64_t ldo, int split, cudaStream_t s);
 
@@ -92,19 +94,39 @@ int aae_trace_set(uint64_t* buf) {
 }
 int aae_trace_slots(void) { return 2 * (int)TR_N; }
 
-int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
-                      float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
-                      const aae_step_state* st, float* dh2, double* loss_sum, int impl, void* stream) {
+int64_t aae_dec_out_train_work_floats(int B, int H, int Vloc, int impl) {
+  if (impl != 1 || B <= 0 || H <= 0 || Vloc <= 0) return 0;
+  const int rows = tc2_max_rows(H);
+  if (rows <= 0 || B <= rows) return 0;
+  return (int64_t)Vloc * H + Vloc;
+}
+
+int aae_dec_out_train_ws(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                         float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices,
+                         double n_total, const aae_step_state* st, float* dh2, double* loss_sum, int impl, float* work,
+                         int64_t work_floats, void* stream) {
   AAE_REQUIRE(h2 && Wd3 && bd3 && mW && vW && mb && vb && indptr && indices && st && dh2 && loss_sum, "null pointer");
   AAE_REQUIRE(B > 0 && H > 0 && Vloc > 0 && n_total > 0, "bad size");
   if (impl == 0)
     return dec_out_train_simt(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
                               loss_sum, as_stream(stream));
-  if (impl >= 1 && impl <= 4)   // 1/2: pipelined when the shape allows it; 3/4: the non-pipelined kernel
+  if (impl >= 1 && impl <= 4) {   // 1/2: pipelined when the shape allows it; 3/4: the non-pipelined kernel
+    if (work && work_floats < aae_dec_out_train_work_floats(B, H, Vloc, impl)) {
+      set_error("dec_out_train: gradient scratch of %lld floats is too small", (long long)work_floats);
+      return AAE_E_ARG;
+    }
     return dec_out_train_tc(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
-                            loss_sum, (impl & 1) ? 3 : 1, impl <= 2, as_stream(stream));
+                            loss_sum, (impl & 1) ? 3 : 1, impl <= 2, work, as_stream(stream));
+  }
   set_error("dec_out_train: unknown impl %d", impl);
   return AAE_E_ARG;
+}
+
+int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                      float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                      const aae_step_state* st, float* dh2, double* loss_sum, int impl, void* stream) {
+  return aae_dec_out_train_ws(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2,
+                              loss_sum, impl, nullptr, 0, stream);
 }
 
 int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc, int apply_sigmoid,

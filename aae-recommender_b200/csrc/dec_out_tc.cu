@@ -822,12 +822,18 @@ template <int CWT> struct Tc2Cfg {
   static constexpr int NTT = 32 * NWE + 32;       // + the MMA / TMA warp
   static constexpr int WCHT = 32 / NWE;           // W' chunks per thread
 };
-template <int SPLIT, int HC, int CWT>
+// MODE (batches larger than one row chunk are walked chunk by chunk, one launch each; the weight gradient of the
+// chunks is summed in a global scratch [Vloc,H] + [Vloc] before the one Adam update):
+//   0  single chunk: gradient -> Adam                     1  first chunk:  gW  = dW'   (no Adam, no W/m/v stage)
+//   2  middle chunk: gW += dW'                            3  last chunk:   Adam with gW + dW'
+template <int SPLIT, int HC, int CWT, int MODE>
 __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     const float* __restrict__ h2, int B, int Hrt, float* __restrict__ Wd3, float* __restrict__ bd3,
     float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
     int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
-    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum, int smem_total) {
+    const aae_step_state* __restrict__ st, float* __restrict__ dh2, double* __restrict__ loss_sum, int smem_total,
+    float* __restrict__ gW, float* __restrict__ gB) {
+  constexpr bool kAdam = (MODE == 0 || MODE == 3);     // this launch applies dec_optim
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_g1, bar_g23;   // completion of G1(i) / of G3(i-1)+G2(i-1)
   __shared__ uint64_t bar_stage;         // E2 stage (W/m/v rows of one tile) filled by TMA
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     // tile j of this CTA -> E2 stage (a ragged last tile is read from global memory by E2 instead)
     auto stage_copy = [&](int j) {
       const int v0 = ((int)blockIdx.x + j * G) * TN;
-      if (Vloc - v0 >= TN) {
+      if (kAdam && Vloc - v0 >= TN) {
         const uint32_t wbytes = (uint32_t)(TN * H) * 4u, bbytes = TN * 4u;
         mbar_arrive_expect_tx(&bar_stage, 3u * wbytes + 3u * bbytes);
         bulk_g2s(sW, Wd3 + (size_t)v0 * H, wbytes, &bar_stage);
@@ -924,6 +930,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       const int nv = min(TN, Vloc - v0);
       const uint32_t wbytes = (uint32_t)nv * (uint32_t)H * 4u;
       if (j >= 2) prefetch_l2_bulk(Wd3 + (size_t)v0 * H, wbytes);
+      if (!kAdam) return;
 #if K3_PF_MV
       prefetch_l2_bulk(mW + (size_t)v0 * H, wbytes);
       prefetch_l2_bulk(vW + (size_t)v0 * H, wbytes);
@@ -1068,25 +1075,34 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       float* pW = eW + eoff;
       float* pM = eM + eoff;
       float* pV = eV + eoff;
-      float pw[CWT], pm[CWT], pv[CWT];
+      float* pG = (MODE != 0) ? ((is_bias ? gB : gW) + eoff) : nullptr;
+      float pw[CWT], pm[CWT], pv[CWT], pg[CWT];
+#pragma unroll
+      for (int j = 0; j < CWT; ++j) pw[j] = pm[j] = pv[j] = 0.f;
+      if (MODE == 2 || MODE == 3) {                      // gradient of the earlier chunks (coalesced over the lanes)
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pg[j] = (j < ecnt) ? pG[(size_t)j * H] : 0.f;
+      }
       mbar_wait(&bar_stage, phase_e);
       phase_e ^= 1;
-      if (nv == TN) {
+      if (kAdam) {
+        if (nv == TN) {
 #pragma unroll
-        for (int j = 0; j < CWT; ++j) {
-          if (j < ecnt_full) {
-            pw[j] = sWp[j * H];
-            pm[j] = sMp[j * H];
-            pv[j] = sVp[j * H];
+          for (int j = 0; j < CWT; ++j) {
+            if (j < ecnt_full) {
+              pw[j] = sWp[j * H];
+              pm[j] = sMp[j * H];
+              pv[j] = sVp[j * H];
+            }
           }
-        }
-      } else {
+        } else {
 #pragma unroll
-        for (int j = 0; j < CWT; ++j) {
-          if (j < ecnt) {
-            pw[j] = pW[(size_t)j * H];
-            pm[j] = pM[(size_t)j * H];
-            pv[j] = pV[(size_t)j * H];
+          for (int j = 0; j < CWT; ++j) {
+            if (j < ecnt) {
+              pw[j] = pW[(size_t)j * H];
+              pm[j] = pM[(size_t)j * H];
+              pv[j] = pV[(size_t)j * H];
+            }
           }
         }
       }
@@ -1104,15 +1120,38 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         }
         if (is_bias) gw[0] = gb;
       }
+      if (MODE == 2 || MODE == 3) {
 #pragma unroll
-      for (int j = 0; j < CWT; ++j) {
-        if (j < ecnt) {
-          float p = pw[j], m = pm[j], vv = pv[j];
-          adam_update(ak, gw[j], p, m, vv);
-          pW[(size_t)j * H] = p;
-          __stcs(pM + (size_t)j * H, m);
-          __stcs(pV + (size_t)j * H, vv);
+        for (int j = 0; j < CWT; ++j) gw[j] += pg[j];
+      }
+      if (kAdam) {
+        // Adam (common.cuh adam_update, same operations in the same order per element), written stage by stage over the
+        // CWT independent elements: the per-element chain is ~10 dependent instructions incl. two MUFU, and with four
+        // warps per scheduler the element-after-element form left the issue slots idle (ncu: 11 stall samples per
+        // instruction in this block).
+        float dn[CWT];
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pm[j] = fmaf(ak.w1, gw[j] - pm[j], pm[j]);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pv[j] = fmaf(ak.w2 * gw[j], gw[j], pv[j] * ak.beta2);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) dn[j] = fmaf(sqrt_approx(pv[j]), ak.inv_bc2_sqrt, ak.eps);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) dn[j] = pm[j] * rcp_approx(dn[j]);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pw[j] = fmaf(-ak.step_size, dn[j], pw[j]);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) {
+          if (j < ecnt) {
+            pW[(size_t)j * H] = pw[j];
+            __stcs(pM + (size_t)j * H, pm[j]);
+            __stcs(pV + (size_t)j * H, pv[j]);
+          }
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CWT; ++j)
+          if (j < ecnt) pG[(size_t)j * H] = gw[j];
       }
     };
 
@@ -1159,15 +1198,29 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
 #pragma unroll
         for (int j = 0; j < CWT; ++j) zmax = fmaxf(zmax, fabsf(z[j]));
         if (tb == 0u && vm >= CWT && zmax < 16.0f) {
+          // All-negative-target columns with moderate logits (nearly every element).  sigmoid(z) = 1/(1+e^-z) and
+          // -log(1-sigmoid(z)) = z + log(1+e^-z) need no branch on the sign of z for |z| < 16 (e^16 is far inside
+          // fp32); the logarithms of four elements are taken as ONE lg2 of the product of their (1+e^-z) <= 8.9e6
+          // (product < 6.3e27): 7 FP32 + 2 MUFU instructions per element instead of 11 + 3.
+          float sz = 0.f;
+          float pr[CWT / 4];
+#pragma unroll
+          for (int q = 0; q < CWT / 4; ++q) pr[q] = 1.0f;
 #pragma unroll
           for (int j = 0; j < CWT; ++j) {
-            float d;
-            float l = bce_neg_fast(z[j], inv_n_row, d);
-            loss_local = fmaf(l, rvf, loss_local);
-            float h = tf32_hi(d);
+            const float u = ex2_approx(-1.4426950408889634f * z[j]);
+            const float t = 1.0f + u;
+            const float d = rcp_approx(t) * inv_n_row;
+            sz += z[j];
+            pr[j >> 2] *= t;
+            const float h = tf32_hi(d);
             dzh[j] = h;
             dzl[j] = d - h;
           }
+          float lg = 0.f;
+#pragma unroll
+          for (int q = 0; q < CWT / 4; ++q) lg += lg2_approx(pr[q]);
+          loss_local = fmaf(rvf, fmaf(lg, 0.6931471805599453f, sz), loss_local);
         } else {
 #pragma unroll
           for (int j = 0; j < CWT; ++j) {
@@ -1788,37 +1841,83 @@ static bool tc2_supported(int B, int H) {
   return tc2_smem_bytes(g, B) <= 227 * 1024 - 256;
 }
 
+// largest row chunk the pipelined kernel takes for this n_hidden (multiple of 8; 0: shape outside its envelope)
+int tc2_max_rows(int H) {
+  if ((H & 3) != 0 || H + 1 > 128) return 0;
+  for (int b = tc::BM; b >= 8; b -= 8)
+    if (tc2_supported(b, H)) return b;
+  return 0;
+}
+
+template <int MODE>
+static int launch_tc2(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
+                      int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
+                      const aae_step_state* st, float* dh2, double* loss_sum, int split, float* gW, float* gB,
+                      cudaStream_t s) {
+  tc::Geom g = tc::make_geom(H);
+  int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
+  int grid = std::min(n_tiles, sm_count());
+  size_t smem = tc2_smem_bytes(g, B);
+  void (*kern)(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
+               const int32_t*, float, const aae_step_state*, float*, double*, int, float*, float*);
+  if (MODE == 0 && split != 3)
+    kern = (H == 100) ? tc::dec_out_train_tc2_kernel<1, 100, TC2_CW, 0> : tc::dec_out_train_tc2_kernel<1, 0, TC2_CW, 0>;
+  else
+    kern = (H == 100) ? tc::dec_out_train_tc2_kernel<3, 100, TC2_CW, MODE> : tc::dec_out_train_tc2_kernel<3, 0, TC2_CW, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
+    return AAE_E_CUDA;
+  }
+  kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+                                                   (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem, gW, gB);
+  return check_launch("dec_out_train(tc2)");
+}
+
 int dec_out_train_tc(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb, float* vb,
                      int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices, double n_total,
                      const aae_step_state* st, float* dh2, double* loss_sum, int split, bool pipelined,
-                     cudaStream_t s) {
+                     float* gwork, cudaStream_t s) {
   if (!tc_supported(B, H, "dec_out_train")) return AAE_E_UNSUPPORTED;
-  if (B > tc::BM) {
-    set_error("dec_out_train: tensor-core kernel handles batch <= %d (got %d); use impl=simt", tc::BM, B);
-    return AAE_E_UNSUPPORTED;
-  }
   tc::Geom g = tc::make_geom(H);
   int n_tiles = (Vloc + tc::TN - 1) / tc::TN;
   int grid = std::min(n_tiles, sm_count());
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(Wd3) | reinterpret_cast<uintptr_t>(mW) |
                            reinterpret_cast<uintptr_t>(vW) | reinterpret_cast<uintptr_t>(bd3) |
                            reinterpret_cast<uintptr_t>(mb) | reinterpret_cast<uintptr_t>(vb)) & 15) == 0;   // TMA bulk copies
-  if (pipelined && aligned16 && tc2_supported(B, H)) {
-    size_t smem = tc2_smem_bytes(g, B);
-    void (*kern)(const float*, int, int, float*, float*, float*, float*, float*, float*, int, int, const int32_t*,
-                 const int32_t*, float, const aae_step_state*, float*, double*, int);
-    if (H == 100)
-      kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 100, TC2_CW> : tc::dec_out_train_tc2_kernel<1, 100, TC2_CW>;
-    else
-      kern = (split == 3) ? tc::dec_out_train_tc2_kernel<3, 0, TC2_CW> : tc::dec_out_train_tc2_kernel<1, 0, TC2_CW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
-      return AAE_E_CUDA;
+  if (pipelined && aligned16 && tc2_supported(B, H))
+    return launch_tc2<0>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices, n_total, st, dh2, loss_sum,
+                         split, nullptr, nullptr, s);
+  const int rows = (pipelined && aligned16) ? tc2_max_rows(H) : 0;
+  if (B > tc::BM || (rows > 0 && B > rows && gwork && split == 3)) {
+    // Batches beyond one row chunk (the reference's scripts use 500, 1000, 10000: main.py:76, mpd.py:75-76,
+    // aminer.py:62): one launch of the pipelined kernel per chunk of <= `rows` rows with the W' tile walk unchanged;
+    // the chunks' weight gradients are summed in `gwork` ([Vloc,H] + [Vloc] floats) and the last chunk applies Adam
+    // once with the total, exactly as the reference's single backward over the whole batch does.
+    if (!(pipelined && aligned16 && rows > 0 && gwork && split == 3)) {
+      set_error("dec_out_train: batch %d needs the chunked tensor-core path (3xTF32, gradient scratch, 16-byte aligned "
+                "tensors, n_hidden inside the pipelined kernel's envelope); use impl=simt", B);
+      return AAE_E_UNSUPPORTED;
     }
-    kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
-                                     (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem);
-    return check_launch("dec_out_train(tc2)");
+    const int n_chunks = (B + rows - 1) / rows;
+    int per = (B + n_chunks - 1) / n_chunks;
+    per = std::min(rows, (per + 7) & ~7);
+    float* gW = gwork;
+    float* gB = gwork + (size_t)Vloc * H;
+    for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+      const int nb = std::min(per, B - b0);
+      const bool first = (b0 == 0), last = (b0 + nb >= B);
+      int rc;
+#define TC2_CHUNK(M)                                                                                                    \
+  launch_tc2<M>(h2 + (size_t)b0 * H, nb, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr + b0, indices, n_total, st, \
+                dh2 + (size_t)b0 * H, loss_sum, 3, gW, gB, s)
+      if (first) rc = TC2_CHUNK(1);
+      else if (last) rc = TC2_CHUNK(3);
+      else rc = TC2_CHUNK(2);
+#undef TC2_CHUNK
+      if (rc) return rc;
+    }
+    return AAE_OK;
   }
   size_t smem = tc::smem_bytes(g);
   auto kern = (split == 3) ? tc::dec_out_train_tc_kernel<3> : tc::dec_out_train_tc_kernel<1>;

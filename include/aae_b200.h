@@ -265,6 +265,18 @@ int aae_dec_out_train(const float* h2, int B, int H, float* Wd3, float* bd3, flo
                       float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices,
                       double n_total, const aae_step_state* st, float* dh2, double* loss_sum, int impl,
                       void* stream);
+/* The same call for ANY batch size on the tensor-core path (the reference's scripts train with batches of 500, 1000
+ * and 10000: main.py:76, eval/mpd/mpd.py:75-76, eval/aminer.py:62).  A batch beyond one row chunk of the pipelined
+ * kernel (n_hidden 100: 104 rows) is walked chunk by chunk -- one pass over Wd3 per chunk with the forward, BCE and both
+ * backward GEMMs of that chunk -- while the chunks' weight gradients are summed in `work` ([Vloc,H] + [Vloc] floats,
+ * caller-owned; aae_dec_out_train_work_floats gives the size, 0 when the batch fits one chunk) and the last chunk
+ * applies dec_optim's Adam once with the total gradient, as the reference's single backward does (aae.py:703-707).
+ * work == NULL: batches beyond one chunk are only served by impl 0. */
+int64_t aae_dec_out_train_work_floats(int B, int H, int Vloc, int impl);
+int aae_dec_out_train_ws(const float* h2, int B, int H, float* Wd3, float* bd3, float* mW, float* vW, float* mb,
+                         float* vb, int v_begin, int Vloc, const int32_t* indptr, const int32_t* indices,
+                         double n_total, const aae_step_state* st, float* dh2, double* loss_sum, int impl, float* work,
+                         int64_t work_floats, void* stream);
 
 /* ---- predict (aae.py:840-870) --------------------------------------------------------------- */
 /* eval-mode forward tail: h1pre -> h2 (no dropout). */

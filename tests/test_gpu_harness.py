@@ -153,12 +153,12 @@ def test_phase_methods_equal_partial_fit():
         torch.manual_seed(100 + s)
         dense = torch.FloatTensor(xb.toarray())            # the reference hands the phases a dense tensor (aae.py:751)
         lb = (b.ae_step(dense), b.disc_step(dense), b.gen_step(dense))
-        np.testing.assert_allclose(lb, la, rtol=1e-6)
+        np.testing.assert_allclose(lb, la, rtol=1e-5)
     with pytest.raises(RuntimeError):
         b.disc_step(dense)
     sa, sb = a.state_dict(), b.state_dict()
-    for k in sa:
-        np.testing.assert_allclose(sb[k].numpy(), sa[k].numpy(), rtol=1e-6, atol=1e-9, err_msg=k)
+    for k in sa:     # the decoder kernel reduces dh2 over its CTAs with floating-point atomics: equal to fp32 noise, not bitwise
+        np.testing.assert_allclose(sb[k].numpy(), sa[k].numpy(), rtol=1e-5, atol=2e-7, err_msg=k)
     st = a.enc_optim.state_dict()["state"]
     assert st["enc.lin1.weight"]["exp_avg"].shape == (H, V) and st["enc.lin2.weight"]["step"] == 3
     assert a.gen_optim.param_groups[0]["lr"] == 0.001
