@@ -132,6 +132,9 @@ class AAEEngine(object):
         self._phase_ctx_live = None
         self._epoch = None
         self._gwork = None
+        self._wp = None             # padded [Vloc,104] copy of the output layer for the TMA-fed predict filter
+        self._wp_dirty = True
+        self._topk_out = None
         f32 = dict(dtype=torch.float32, device=self.dev)
         H, Cc, Cp, Vl = self.H, self.C, self.Cp, max(self.Vloc, 1)
         z = lambda *s: torch.zeros(*s, **f32)
@@ -335,6 +338,7 @@ class AAEEngine(object):
             m.zero_()
         self._init_state()
         self.steps_done = 0
+        self._wp_dirty = True
 
     INIT_BLOCK = 65536      # items per generator block of init_uniform
 
@@ -381,6 +385,7 @@ class AAEEngine(object):
             m.zero_()
         self._init_state()
         self.steps_done = 0
+        self._wp_dirty = True
 
     def _gather_items(self, local):
         """All-gather an item-sharded [Vloc, ...] tensor into [V, ...] (state export / dense predict)."""
@@ -815,6 +820,7 @@ class AAEEngine(object):
             self._phase_ctx_live = None
             self.steps_done += 1
             self._w1_dirty = True
+        self._wp_dirty = True
         return loss
 
     def _run(self, key, enqueue):
@@ -853,6 +859,7 @@ class AAEEngine(object):
         self._run((B, bool(injected)), lambda: self._enqueue_step(B, injected))
         self.steps_done += 1
         self._w1_dirty = True
+        self._wp_dirty = True
 
     @_on_device
     def train_step_host(self, indptr_np, indices_np, cond_np=None, injected=False, rng_draws=None,
@@ -900,6 +907,7 @@ class AAEEngine(object):
         slot["ev"] = ev
         self.steps_done += 1
         self._w1_dirty = True
+        self._wp_dirty = True
         return slot
 
     @_on_device
@@ -982,32 +990,76 @@ class AAEEngine(object):
             dist.all_reduce(cnt, group=self.group)
         return cnt.cpu().numpy().astype(np.int64) + 1
 
+    def _padded_weights(self):
+        """Wp = [Wd3 | bd3 | 0 0 0] as [Vloc, 104] (+ its largest row norm): the TMA-described operand of the v2 predict
+        filter, rebuilt only after the weights changed (one streaming pass, amortised over all query batches)."""
+        n = int(N.load().aae_pad_weights_floats(self.Vloc, self.H))
+        if n == 0:
+            return None, None
+        if self._wp is None or self._wp.numel() < n:
+            self._wp = torch.empty(n, dtype=torch.float32, device=self.dev)
+            self._wp_dirty = True
+        wmax = self._wp[n - 64:]
+        if self._wp_dirty:
+            call("aae_pad_weights", ptr(self.Wd3), ptr(self.bd3), self.Vloc, self.H, ptr(self._wp), ptr(wmax),
+                 self._stream())
+            self._wp_dirty = False
+        return self._wp, wmax
+
     @_on_device
-    def topk(self, B, k, scratch=None, mask_known=True, fused=None):
+    def topk(self, B, k, scratch=None, mask_known=True, fused=None, check=True):
         """Masked top-k of the batch in the device buffers: returns (idx int32 [B,k] global item ids,
         val float32 [B,k] logits), descending.  Item-sharded: local top-k + all-gather + merge.
 
-        Large shards take the fused path (``aae_predict_topk``: candidates selected in the GEMM epilogue, no
-        [B, Vloc] score matrix); its per-batch status word is read back (one 4-byte synchronising copy) and a
-        batch it could not rank exactly is redone through the dense path.  ``fused=False`` forces the dense path."""
+        Large shards take the fused path: candidates selected in the GEMM epilogue, no [B, Vloc] score matrix.
+        ``aae_predict_topk2`` (TMA-multicast single-pass TF32 filter + exact fp32 re-scoring of the survivors) when
+        the shape is inside its envelope, else ``aae_predict_topk`` (3xTF32 throughout).  The per-batch status word is
+        read back (one 4-byte synchronising copy) and a batch the fused path could not rank exactly is redone through
+        the dense path; ``check=False`` skips that read (the caller inspects ``topk_status()`` later -- pipelined
+        callers and the device-timed benchmark loop).  ``fused=False`` forces the dense path."""
         kl = min(k, self.Vloc)
-        idx = torch.empty(B, kl, dtype=torch.int32, device=self.dev)
-        val = torch.empty(B, kl, dtype=torch.float32, device=self.dev)
+        # results land in a ring of four preallocated buffers (no allocation in the query loop); a result stays valid
+        # for the next three topk calls
+        if self._topk_out is None or self._topk_out[0][0].shape[0] < B or self._topk_out[0][0].shape[1] != kl:
+            self._topk_out = [(torch.empty(max(B, 1), kl, dtype=torch.int32, device=self.dev),
+                               torch.empty(max(B, 1), kl, dtype=torch.float32, device=self.dev)) for _ in range(4)]
+            self._topk_i = 0
+        self._topk_i = (self._topk_i + 1) % 4
+        idx, val = self._topk_out[self._topk_i][0][:B], self._topk_out[self._topk_i][1][:B]
         impl = self.impl_for_scores()
-        need = 0
-        if fused is not False and impl in (1, 2) and os.environ.get("AAE_B200_TOPK", "") != "dense":
-            need = int(N.load().aae_predict_topk_work_bytes(B, self.Vloc, kl))
+        lib = N.load()
+        mode, need = None, 0
+        want = os.environ.get("AAE_B200_TOPK", "")
+        if fused is not False and impl in (1, 2) and want != "dense":
+            if impl == 1 and want != "v1":
+                need = int(lib.aae_predict_topk2_work_bytes(B, self.Vloc, kl, self.H))
+                mode = "v2" if need > 0 else None
+            if mode is None:
+                need = int(lib.aae_predict_topk_work_bytes(B, self.Vloc, kl))
+                mode = "v1" if need > 0 else None
         done = False
-        if need > 0:
+        if mode is not None:
             if self._topk_work is None or self._topk_work.numel() < need:
                 self._topk_work = torch.empty(need, dtype=torch.uint8, device=self.dev)
             self.predict_h2(B)
-            call("aae_predict_topk", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), self.Vloc, self.v_begin,
-                 ptr(self.indptr) if mask_known else None, ptr(self.indices) if mask_known else None, kl, impl,
-                 ptr(self._topk_work), need, ptr(idx), ptr(val), ptr(self._n_bad), self._stream())
-            done = int(self._n_bad.item()) == 0
-            self.topk_fallbacks += 0 if done else 1
+            ip = ptr(self.indptr) if mask_known else None
+            ii = ptr(self.indices) if mask_known else None
+            if mode == "v2":
+                wp, wmax = self._padded_weights()
+                call("aae_predict_topk2", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), ptr(wp), ptr(wmax),
+                     self.Vloc, self.v_begin, ip, ii, kl, ptr(self._topk_work), need, ptr(idx), ptr(val),
+                     ptr(self._n_bad), self._stream())
+            else:
+                call("aae_predict_topk", ptr(self.h2), B, self.H, ptr(self.Wd3), ptr(self.bd3), self.Vloc, self.v_begin,
+                     ip, ii, kl, impl, ptr(self._topk_work), need, ptr(idx), ptr(val), ptr(self._n_bad), self._stream())
+            self.topk_mode = mode
+            if check:
+                done = int(self._n_bad.item()) == 0
+                self.topk_fallbacks += 0 if done else 1
+            else:
+                done = True
         if not done:
+            self.topk_mode = "dense"
             if scratch is None or scratch.shape[0] < B or scratch.shape[1] < self.Vloc:
                 scratch = torch.empty(B, self.Vloc, dtype=torch.float32, device=self.dev)
             self.scores(B, scratch, apply_sigmoid=False)
@@ -1023,3 +1075,7 @@ class AAEEngine(object):
         ov = torch.empty(B, kk, dtype=torch.float32, device=self.dev)
         call("aae_topk_merge", ptr(cv), ptr(ci), B, cv.shape[1], kk, ptr(oi), ptr(ov), self._stream())
         return oi, ov
+
+    def topk_status(self):
+        """Rows the last fused ``topk(check=False)`` could not rank exactly (0 = the result is exact); synchronises."""
+        return int(self._n_bad.item())

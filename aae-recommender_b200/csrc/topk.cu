@@ -204,15 +204,23 @@ __global__ void __launch_bounds__(TK_THREADS, 1) row_topk_kernel(const float* __
 // the bottom.  Rows with an overflowed sub-list, more than cap_out candidates or fewer than k unknown ones are counted
 // in n_bad (the caller then re-ranks the batch through the dense path -- exactness never depends on the threshold
 // estimate).  One CTA per row.
+// RESCORE (K5 v2): the sub-lists hold item ids only (they passed an approximate single-pass TF32 filter); every unknown
+// candidate is scored here exactly in fp32 -- one warp per candidate: z = h2'[b,:] . Wd3[item,:] + bd3[item], lanes over
+// the float4 columns, fixed reduction order -- so the final ranking never sees an approximate value.
+struct RescoreArgs {
+  const float* h2; const float* Wd3; const float* bd3; int H; int v_begin;
+};
 constexpr int FIN_THREADS = 256;
+template <bool RESCORE>
 __global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* __restrict__ cand_val,
                                                                   const int32_t* __restrict__ cand_idx,
                                                                   const int32_t* __restrict__ cnt, int nsub, int cap_sub,
                                                                   float* __restrict__ out_val, int32_t* __restrict__ out_idx,
                                                                   int cap_out, int32_t* __restrict__ tot, int B, int k,
                                                                   const int32_t* __restrict__ indptr,
-                                                                  const int32_t* __restrict__ indices, int32_t* n_bad) {
-  extern __shared__ int off_s[];                 // [nsub + 1] exclusive prefix of the sub-list counts
+                                                                  const int32_t* __restrict__ indices, int32_t* n_bad,
+                                                                  RescoreArgs ra) {
+  extern __shared__ int off_s[];                 // [nsub + 1] exclusive prefix of the sub-list counts (+ h2 row if RESCORE)
   __shared__ int warp_s[FIN_THREADS / 32];
   __shared__ int valid_s, over_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* _
         if (sl >= off_s[sidx + 1] - o0) continue;
         const size_t src = ((size_t)row * nsub + sidx) * cap_sub + sl;
         const int id = cand_idx[src];
-        float v = cand_val[src];
+        float v = RESCORE ? 0.f : cand_val[src];
         int lo = p0, hi = p1;
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
@@ -275,13 +283,75 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* _
     }
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
     if (lane == 0 && valid) atomicAdd(&valid_s, valid);
+    if (RESCORE) {
+      float* hrow = reinterpret_cast<float*>(off_s + ((nsub + 4) & ~3));     // 16-byte aligned behind the prefix
+      for (int c = tid; c < ra.H; c += FIN_THREADS) hrow[c] = ra.h2[(size_t)row * ra.H + c];
+    }
     __syncthreads();
+    if (RESCORE && fits) {
+      // one THREAD per candidate: the 25 float4 loads of its W row are independent (memory-level parallelism; a warp
+      // per candidate was latency-bound: 514 us for 1000 rows), the h2 row is a shared-memory broadcast, the sum runs
+      // in ascending k (deterministic)
+      const float* hrow = reinterpret_cast<const float*>(off_s + ((nsub + 4) & ~3));
+      const int H4 = ra.H >> 2;
+      for (int c = tid; c < total; c += FIN_THREADS) {
+        const size_t o = (size_t)row * cap_out + c;
+        if (out_val[o] == -FLT_MAX) continue;                       // a known item: stays at the bottom
+        const int item = out_idx[o] - ra.v_begin;
+        const float4* wrow = reinterpret_cast<const float4*>(ra.Wd3 + (size_t)item * ra.H);
+        float a0 = 0.f, a1 = 0.f;
+        int c4 = 0;
+        for (; c4 + 1 < H4; c4 += 2) {
+          const float4 w0 = __ldg(wrow + c4), w1 = __ldg(wrow + c4 + 1);
+          const float4 h0 = reinterpret_cast<const float4*>(hrow)[c4], h1 = reinterpret_cast<const float4*>(hrow)[c4 + 1];
+          a0 = fmaf(w0.x, h0.x, a0); a0 = fmaf(w0.y, h0.y, a0); a0 = fmaf(w0.z, h0.z, a0); a0 = fmaf(w0.w, h0.w, a0);
+          a1 = fmaf(w1.x, h1.x, a1); a1 = fmaf(w1.y, h1.y, a1); a1 = fmaf(w1.z, h1.z, a1); a1 = fmaf(w1.w, h1.w, a1);
+        }
+        if (c4 < H4) {
+          const float4 w0 = __ldg(wrow + c4);
+          const float4 h0 = reinterpret_cast<const float4*>(hrow)[c4];
+          a0 = fmaf(w0.x, h0.x, a0); a0 = fmaf(w0.y, h0.y, a0); a0 = fmaf(w0.z, h0.z, a0); a0 = fmaf(w0.w, h0.w, a0);
+        }
+        out_val[o] = (a0 + a1) + __ldg(ra.bd3 + item);
+      }
+    }
     if (tid == 0) {
       tot[row] = fits ? total : 0;
       if (over_s || !fits || valid_s < k) atomicAdd(n_bad, 1);
     }
     __syncthreads();
   }
+}
+
+// K5 v2: filter threshold of row b = tau_b - (bound of the single-pass TF32 error of the row's logits).
+// Both operands are truncated to tf32 (10 explicit mantissa bits: relative error < 2^-10 each), so
+// |z_tf32 - z| <= (2^-9 + 2^-20) * sum_k |h'_k w'_k| + accumulation error <= 2.1 * 2^-10 * ||h'_b|| * max_v ||w'_v||
+// (Cauchy-Schwarz; h' = [h2 | 1], w' = [Wd3 | bd3]).  One warp per row.
+__global__ void __launch_bounds__(256) tau_margin_kernel(const float* __restrict__ thr, int thr_stride,
+                                                         const float* __restrict__ h2, int B, int H,
+                                                         const float* __restrict__ wmax, float* __restrict__ tau_f) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= B) return;
+  float ss = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float x = h2[(size_t)row * H + c];
+    ss = fmaf(x, x, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) {
+    const float margin = 2.1f * 0.0009765625f * sqrtf(ss + 1.0f) * (*wmax);
+    tau_f[row] = thr[(size_t)row * thr_stride] - margin;
+  }
+}
+// The ranking is exact iff every item whose exact score reaches the k-th exact score passed the filter.  An item with
+// exact score z has a TF32 score >= z - margin, and the filter kept everything above tau - margin: rows whose k-th exact
+// score does not clear tau are reported (the caller re-ranks them through the exact dense path).
+__global__ void check_kth_kernel(const float* __restrict__ val, int k, const float* __restrict__ thr, int thr_stride,
+                                 const int32_t* __restrict__ tot, int B, int32_t* n_bad) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B || tot[row] == 0) return;                 // tot == 0: already counted by cand_finish
+  if (!(val[(size_t)row * k + (k - 1)] > thr[(size_t)row * thr_stride])) atomicAdd(n_bad, 1);
 }
 
 // Final ranking of a short candidate list (the common case of the fused predict path: ~1.4 k live candidates per row):
@@ -366,7 +436,13 @@ struct TopkPlan {
   int nsub, cap_sub;       // private candidate sub-lists per row (one per CTA column and 16-column tile part)
   bool ok;
 };
-static TopkPlan make_plan(int B, int Vloc, int k) {
+void dec_out_select2_grid(int B, int n_sel, int* gx, int* gy);
+int dec_out_select2(const float* h2, int B, int H, const float* Wp, int Vloc, int v_begin, int tile_stride, int n_sel,
+                    int filter, float* out, int64_t ldo, int out_by_visit, const float* tau, int32_t* cnt,
+                    int32_t* cand_idx, int cap_sub, cudaStream_t s);
+bool select2_supported(int H);
+
+static TopkPlan make_plan(int B, int Vloc, int k, bool v2 = false) {
   TopkPlan p;
   p.n_tiles = (Vloc + 127) / 128;
   p.n_samp = std::min(512, p.n_tiles / 8);
@@ -377,7 +453,8 @@ static TopkPlan make_plan(int B, int Vloc, int k) {
   p.cap = TK_CAP;
   p.J = p.ok ? std::max(8, (int)(((int64_t)p.T * p.S + Vloc - 1) / Vloc)) : 8;
   int gx = 1, gy = 1;
-  dec_out_select_grid(B, p.n_tiles, &gx, &gy);
+  if (v2) dec_out_select2_grid(B, p.n_tiles, &gx, &gy);
+  else dec_out_select_grid(B, p.n_tiles, &gx, &gy);
   p.nsub = 4 * gx;
   // expected T / nsub candidates per sub-list; room for 8 sigma of a Poisson count, and for the worst clustering of
   // twice T candidates in consecutive items (32 per visited tile part)
@@ -573,15 +650,88 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
                          kth_fast ? thr_val : thr_val + (p.J - 1), kth_fast ? 1 : p.J, cnt, sub_val, sub_idx, p.cap_sub,
                          split, s);
   if (rc) return rc;
-  cand_finish_kernel<<<std::min(B, 8 * sm_count()), FIN_THREADS, (p.nsub + 1) * sizeof(int), s>>>(
+  cand_finish_kernel<false><<<std::min(B, 8 * sm_count()), FIN_THREADS, (p.nsub + 1) * sizeof(int), s>>>(
       sub_val, sub_idx, cnt, p.nsub, p.cap_sub, cand_val, cand_idx, p.cap, tot, B, std::min(k, Vloc), indptr, indices,
-      n_bad);
+      n_bad, RescoreArgs{nullptr, nullptr, nullptr, 0, 0});
   rc = check_launch("cand_finish");
   if (rc) return rc;
   cand_sort_small_kernel<<<B, CS_THREADS, 0, s>>>(cand_val, cand_idx, p.cap, tot, k, idx_out, val_out);
   rc = check_launch("cand_sort_small");
   if (rc) return rc;
   return launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, val_out, s, tot, CS_CAP);
+}
+
+int64_t aae_predict_topk2_work_bytes(int B, int Vloc, int k, int H) {
+  if (B <= 0 || Vloc <= 0 || k <= 0 || !select2_supported(H)) return 0;
+  TopkPlan p = make_plan(B, Vloc, k, true);
+  if (!p.ok) return 0;
+  return (int64_t)(al256((size_t)B * p.S * 4) + 2 * al256((size_t)B * p.J * 4) + al256((size_t)B * p.nsub * 4) +
+                   2 * al256((size_t)B * 4) + al256((size_t)B * p.nsub * p.cap_sub * 4) +
+                   2 * al256((size_t)B * p.cap * 4) + al256((size_t)B * k * 4));
+}
+
+int aae_predict_topk2(const float* h2, int B, int H, const float* Wd3, const float* bd3, const float* Wp,
+                      const float* wmax, int Vloc, int v_begin, const int32_t* indptr, const int32_t* indices, int k,
+                      void* work, int64_t work_bytes, int32_t* idx_out, float* val_out, int32_t* n_bad, void* stream) {
+  AAE_REQUIRE(h2 && Wd3 && bd3 && Wp && wmax && idx_out && n_bad && work, "null pointer");
+  AAE_REQUIRE(B > 0 && H > 0 && Vloc > 0 && k > 0, "bad size");
+  AAE_REQUIRE((indptr == nullptr) == (indices == nullptr), "indptr and indices go together");
+  AAE_REQUIRE(select2_supported(H), "n_hidden outside the TMA-fed filter's envelope");
+  const TopkPlan p = make_plan(B, Vloc, k, true);
+  if (!p.ok) {
+    set_error("aae_predict_topk2: shard of %d items / k = %d is outside the fused envelope (use the dense path)", Vloc, k);
+    return AAE_E_UNSUPPORTED;
+  }
+  AAE_REQUIRE(work_bytes >= aae_predict_topk2_work_bytes(B, Vloc, k, H), "workspace too small");
+  cudaStream_t s = as_stream(stream);
+  unsigned char* w = reinterpret_cast<unsigned char*>(work);
+  float* samp = reinterpret_cast<float*>(w);        w += al256((size_t)B * p.S * 4);
+  float* thr_val = reinterpret_cast<float*>(w);     w += al256((size_t)B * p.J * 4);
+  int32_t* thr_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.J * 4);
+  int32_t* cnt = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * p.nsub * 4);
+  int32_t* tot = reinterpret_cast<int32_t*>(w);     w += al256((size_t)B * 4);
+  float* tau_f = reinterpret_cast<float*>(w);       w += al256((size_t)B * 4);
+  int32_t* sub_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.nsub * p.cap_sub * 4);
+  float* cand_val = reinterpret_cast<float*>(w);    w += al256((size_t)B * p.cap * 4);
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * p.cap * 4);
+  float* val_tmp = reinterpret_cast<float*>(w);
+  float* vout = val_out ? val_out : val_tmp;
+  const int kk = std::min(k, Vloc);
+  // (1) approximate (single-pass TF32) scores of a strided sample of the tiles -> (2) per-row threshold tau = J-th
+  // largest sample score -> filter threshold tau - margin (rigorous TF32 error bound of the row) -> (3) full
+  // TMA-multicast pass, item ids of the logits above the filter threshold appended from the GEMM epilogue -> (4) known
+  // items masked, survivors re-scored EXACTLY in fp32, sorted, first k emitted -> (5) rows whose k-th exact score does
+  // not clear tau are reported in n_bad
+  int rc = dec_out_select2(h2, B, H, Wp, Vloc, v_begin, p.stride, p.n_samp, 0, samp, p.S, 1, nullptr, nullptr, nullptr, 0, s);
+  if (rc) return rc;
+  const bool kth_fast = p.J <= 256;
+  if (kth_fast) {
+    row_kth_approx_kernel<<<B, KTH_THREADS, 0, s>>>(samp, p.S, p.S, p.J, thr_val);
+    rc = check_launch("row_kth_approx");
+  } else {
+    rc = launch_row_topk(samp, p.S, B, p.S, p.J, 0, nullptr, thr_idx, thr_val, s);
+  }
+  if (rc) return rc;
+  const float* thr = kth_fast ? thr_val : thr_val + (p.J - 1);
+  const int thr_stride = kth_fast ? 1 : p.J;
+  tau_margin_kernel<<<cdiv((int64_t)B * 32, 256), 256, 0, s>>>(thr, thr_stride, h2, B, H, wmax, tau_f);
+  rc = check_launch("tau_margin");
+  if (rc) return rc;
+  cudaMemsetAsync(n_bad, 0, 4, s);
+  rc = dec_out_select2(h2, B, H, Wp, Vloc, v_begin, 1, p.n_tiles, 1, nullptr, 0, 0, tau_f, cnt, sub_idx, p.cap_sub, s);
+  if (rc) return rc;
+  cand_finish_kernel<true><<<std::min(B, 8 * sm_count()), FIN_THREADS, ((p.nsub + 4) & ~3) * sizeof(int) + H * sizeof(float) + 16,
+                             s>>>(nullptr, sub_idx, cnt, p.nsub, p.cap_sub, cand_val, cand_idx, p.cap, tot, B, kk, indptr,
+                                  indices, n_bad, RescoreArgs{h2, Wd3, bd3, H, v_begin});
+  rc = check_launch("cand_finish(rescore)");
+  if (rc) return rc;
+  cand_sort_small_kernel<<<B, CS_THREADS, 0, s>>>(cand_val, cand_idx, p.cap, tot, k, idx_out, vout);
+  rc = check_launch("cand_sort_small");
+  if (rc) return rc;
+  rc = launch_row_topk(cand_val, p.cap, B, p.cap, k, 0, cand_idx, idx_out, vout, s, tot, CS_CAP);
+  if (rc) return rc;
+  check_kth_kernel<<<cdiv(B, 256), 256, 0, s>>>(vout, k, thr, thr_stride, tot, B, n_bad);
+  return check_launch("check_kth");
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,

@@ -343,6 +343,21 @@ int aae_peer_error(const void* base, int* err_host);
  * mode 3: D[128,32] = A[128,104]^T.Bm[128,32] (rows >= 104 undefined).  split = 3 (3xTF32) or 1. */
 int aae_tc_selftest(int mode, const float* A, const float* Bm, float* D, int split, void* stream);
 
+/* ---- K5 v2: TMA-fed, cluster-multicast candidate filter + exact re-scoring -------------------------
+ * Same contract as aae_predict_topk (top-k of remove_non_missing(predict(X), X), evaluation.py:183-199, 20-58, exact
+ * outside score ties; n_bad[0] counts rows the caller must re-rank through the dense path).  The filter pass computes
+ * single-pass TF32 logits straight from a padded copy of the output layer, Wp [Vloc, 104] = [Wd3 | bd3 | 0 0 0]
+ * (aae_pad_weights; rebuilt by the caller whenever the weights change), streamed by TMA tensor loads that are multicast
+ * across a thread-block cluster of up to 8 row-chunk CTAs; the filter threshold is lowered by a rigorous bound of the
+ * TF32 error (wmax[0] = largest row norm of Wp, written by aae_pad_weights), the survivors (~1.4 k per row) are
+ * re-scored exactly in fp32 from Wd3/bd3 and ranked.  n_hidden % 4 == 0, n_hidden <= 100. */
+int64_t aae_pad_weights_floats(int Vloc, int H);
+int aae_pad_weights(const float* Wd3, const float* bd3, int Vloc, int H, float* Wp, float* wmax, void* stream);
+int64_t aae_predict_topk2_work_bytes(int B, int Vloc, int k, int H);
+int aae_predict_topk2(const float* h2, int B, int H, const float* Wd3, const float* bd3, const float* Wp,
+                      const float* wmax, int Vloc, int v_begin, const int32_t* indptr, const int32_t* indices, int k,
+                      void* work, int64_t work_bytes, int32_t* idx_out, float* val_out, int32_t* n_bad, void* stream);
+
 /* ---- GPU-side ranking metrics -----------------------------------------------------
  * Replaces the dense D2H + host argsort behind the harness' metrics (evaluation.py:70-164 RankingMetric / MRR /
  * MAP / P, evaluate 202-240 on remove_non_missing(predict(X), X)): for every held-out ("gold") item of every

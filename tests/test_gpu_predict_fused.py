@@ -27,21 +27,35 @@ def _oracle_logits(eng, X):
     return O.OracleAAE(sd, n_code=eng.C).logits(X.toarray())
 
 
-@pytest.mark.parametrize("V,B,k", [(40000, 70, 100), (150001, 200, 20), (70000, 130, 500)])
-def test_fused_topk_matches_oracle_and_dense_path(V, B, k):
+@pytest.mark.parametrize("mode", ["v2", "v1"])
+@pytest.mark.parametrize("V,B,k", [(40000, 70, 100), (150001, 200, 20), (70000, 130, 500), (300000, 1100, 100)])
+def test_fused_topk_matches_oracle_and_dense_path(V, B, k, mode, monkeypatch):
+    """mode v2: TMA-multicast single-pass TF32 filter + exact fp32 re-scoring of the survivors (aae_predict_topk2; a
+    cluster of 1, 2 or 8 row-chunk CTAs for these batch sizes); mode v1: the 3xTF32 filter (aae_predict_topk)."""
     from aaerec_b200.synth import synth_sets
     from oracle import aae_oracle as O
-    eng = _engine(V)
+    if mode == "v1":
+        monkeypatch.setenv("AAE_B200_TOPK", "v1")
+    eng = _engine(V, B=B)
     X = synth_sets(B, V, 20, seed=V % 89)
     _upload(eng, X)
     assert eng.impl_for_scores() == 1
     assert int(__import__("aaerec_b200")._native.load().aae_predict_topk_work_bytes(B, V, k)) > 0
     fi, fv = eng.topk(B, k)
     assert eng.topk_fallbacks == 0, "threshold estimate failed on benign scores"
+    assert eng.topk_mode == mode
     di, dv = eng.topk(B, k, fused=False)
     fi, fv, di, dv = fi.cpu().numpy(), fv.cpu().numpy(), di.cpu().numpy(), dv.cpu().numpy()
-    np.testing.assert_array_equal(fv, dv)          # same kernel arithmetic -> identical logits
-    np.testing.assert_array_equal(fi, di)
+    if mode == "v1":
+        np.testing.assert_array_equal(fv, dv)          # same kernel arithmetic -> identical logits
+        np.testing.assert_array_equal(fi, di)
+    else:
+        # exact fp32 FMA re-scoring vs the dense path's 3xTF32 logits: equal to fp32 rounding; the rankings may differ
+        # only where two logits are within that rounding of each other
+        np.testing.assert_allclose(fv, dv, rtol=3e-6, atol=3e-6)
+        md = fi != di
+        assert md.mean() < 0.01
+        assert np.all(np.abs(fv[md] - dv[md]) <= 3e-6 * np.maximum(1.0, np.abs(dv[md])))
     # against the reference chain on the oracle's logits (sigmoid + min-max scaling are monotone): indices agree
     # except where fp32 logits are within rounding of each other
     Z = _oracle_logits(eng, X)
@@ -51,6 +65,24 @@ def test_fused_topk_matches_oracle_and_dense_path(V, B, k):
     assert mism.mean() < 0.02
     assert np.all(np.abs(Z[rows, fi][mism] - Z[rows, ref][mism]) <= 2e-5 * np.maximum(1.0, np.abs(Z[rows, ref][mism])))
     assert not X.toarray()[rows, fi].any(), "a known item was recommended"
+
+
+def test_fused_topk_v2_margin_guards_exactness():
+    """The v2 filter runs on single-pass TF32 logits: with an output layer scaled so that the TF32 error is far larger
+    than the gaps between neighbouring scores, the ranking must still equal the exact dense ranking (margin + exact
+    re-scoring), or the batch must be reported and redone -- never a silently wrong list."""
+    from aaerec_b200.synth import synth_sets
+    V, B, k = 60000, 64, 100
+    eng = _engine(V, B=B)
+    eng.Wd3.mul_(6.0)                    # |logits| up to ~50: TF32 absolute error ~5e-2
+    X = synth_sets(B, V, 20, seed=4)
+    _upload(eng, X)
+    fi, fv = eng.topk(B, k)
+    di, dv = eng.topk(B, k, fused=False)
+    fi, fv, di, dv = fi.cpu().numpy(), fv.cpu().numpy(), di.cpu().numpy(), dv.cpu().numpy()
+    np.testing.assert_allclose(fv, dv, rtol=3e-6, atol=3e-5)
+    md = fi != di
+    assert np.all(np.abs(fv[md] - dv[md]) <= 3e-6 * np.maximum(1.0, np.abs(dv[md])))
 
 
 def test_fused_topk_degenerate_scores_fall_back_exactly():
@@ -95,32 +127,46 @@ def test_pipelined_scores_kernel_matches_oracle(V, B):
     np.testing.assert_allclose(tc.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6)
 
 
-def test_sharded_fused_topk_offsets():
-    """v_begin / Vloc handling of the fused path: two engines owning the halves of the vocabulary (as two ranks
+@pytest.mark.parametrize("mode", ["v2", "v1"])
+def test_sharded_fused_topk_offsets(mode, monkeypatch):
+    """v_begin / Vloc handling of the fused paths: two engines owning the halves of the vocabulary (as two ranks
     would), candidates merged with aae_topk_merge == the single-shard result."""
     from aaerec_b200.synth import synth_sets
     from aaerec_b200._native import call, ptr
-    from aaerec_b200.engine import AAEEngine
+    lib = __import__("aaerec_b200")._native.load()
+    if mode == "v1":
+        monkeypatch.setenv("AAE_B200_TOPK", "v1")
     V, B, k, H, C = 90000, 64, 100, 100, 50
     full = _engine(V)
     sd = full.state_dict()
     X = synth_sets(B, V, 20, seed=21)
     _upload(full, X)
     fi, fv = full.topk(B, k)
+    assert full.topk_mode == mode
     cv, ci = [], []
     for r in range(2):
         # emulate rank r of 2 without a process group: shard the weights by hand, feed the full h2
         lo, hi = (0, V // 2) if r == 0 else (V // 2, V)
         Wd3 = sd["dec.lin3.weight"][lo:hi].contiguous().cuda()
         bd3 = sd["dec.lin3.bias"][lo:hi].contiguous().cuda()
-        need = int(__import__("aaerec_b200")._native.load().aae_predict_topk_work_bytes(B, hi - lo, k))
-        assert need > 0
-        work = torch.empty(need, dtype=torch.uint8, device="cuda")
         idx = torch.empty(B, k, dtype=torch.int32, device="cuda")
         val = torch.empty(B, k, dtype=torch.float32, device="cuda")
         n_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
-        call("aae_predict_topk", ptr(full.h2), B, H, ptr(Wd3), ptr(bd3), hi - lo, lo, ptr(full.indptr), ptr(full.indices),
-             k, 1, ptr(work), need, ptr(idx), ptr(val), ptr(n_bad), None)
+        if mode == "v1":
+            need = int(lib.aae_predict_topk_work_bytes(B, hi - lo, k))
+            assert need > 0
+            work = torch.empty(need, dtype=torch.uint8, device="cuda")
+            call("aae_predict_topk", ptr(full.h2), B, H, ptr(Wd3), ptr(bd3), hi - lo, lo, ptr(full.indptr),
+                 ptr(full.indices), k, 1, ptr(work), need, ptr(idx), ptr(val), ptr(n_bad), None)
+        else:
+            need = int(lib.aae_predict_topk2_work_bytes(B, hi - lo, k, H))
+            nwp = int(lib.aae_pad_weights_floats(hi - lo, H))
+            assert need > 0 and nwp > 0
+            work = torch.empty(need, dtype=torch.uint8, device="cuda")
+            wp = torch.empty(nwp, dtype=torch.float32, device="cuda")
+            call("aae_pad_weights", ptr(Wd3), ptr(bd3), hi - lo, H, ptr(wp), ptr(wp[nwp - 64:]), None)
+            call("aae_predict_topk2", ptr(full.h2), B, H, ptr(Wd3), ptr(bd3), ptr(wp), ptr(wp[nwp - 64:]), hi - lo, lo,
+                 ptr(full.indptr), ptr(full.indices), k, ptr(work), need, ptr(idx), ptr(val), ptr(n_bad), None)
         assert int(n_bad.item()) == 0
         cv.append(val)
         ci.append(idx)
