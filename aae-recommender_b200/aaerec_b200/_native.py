@@ -54,20 +54,8 @@ _SIGS = {
     "aae_step_state_init": (I, [P, F, F, C.c_uint64, P]),
     "aae_step_tick": (I, [P, P]),
     "aae_bag_fwd": (I, [P, P, I, P, P, I, I, I, I, I, P, P]),
-    "aae_step_begin": (I, [P, P, I, P, P, I64, P, P, P, I, I, P]),
-    "aae_step_end": (I, [P, P, P, I, P, D, I, P, P]),
-    "aae_batch_slots": (I, [P, P, I, I, I, P, P, P, I, P]),
-    "aae_batch_slots_reset": (I, [P, P, P, I, P]),
-    "aae_bag_bwd": (I, [P, P, I, P, I, I, P, I, I, P, P]),
-    "aae_zero_rows": (I, [P, P, I, I, P]),
-    "aae_rows_adam": (I, [P, P, I, P, P, P, P, I, P, I, P]),
     "aae_w1_sweep_untouched": (I, [P, I, I, I, P, P, P, P, P, P, P]),
-    "aae_w1_sweep_untouched_slim": (I, [P, I, I, I, P, P, P, P, P, P, I, P]),
-    "aae_adam_dense": (I, [P, P, P, P, I64, P, I, P]),
-    "aae_ae_fwd": (I, [AaeDims, P, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P]),
     "aae_ae_bwd": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P, P, P, P]),
-    "aae_disc_phase": (I, [AaeDims, P, P, F, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P]),
-    "aae_gen_phase": (I, [AaeDims, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
     "aae_ae_fwd_bag": (I, [AaeDims, AaeBag, P, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
     "aae_disc_phase_bag": (I, [AaeDims, AaeBag, P, P, F, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P]),
     "aae_gen_phase_bag": (I, [AaeDims, AaeBag, P, P, P, AaeDrop, AaeDrop, AaeDrop, AaeDrop, P, P, P, P, P, P, P, P]),
@@ -84,11 +72,10 @@ _SIGS = {
     "aae_dec_out_train": (I, [P, I, I, P, P, P, P, P, P, I, I, P, P, D, P, P, P, I, P]),
     "aae_dec_out_train_ws": (I, [P, I, I, P, P, P, P, P, P, I, I, P, P, D, P, P, P, I, P, I64, P]),
     "aae_dec_out_train_work_floats": (I64, [I, I, I, I]),
-    "aae_predict_tail": (I, [AaeDims, P, P, P, P, P, P]),
     "aae_dec_out_scores": (I, [P, I, I, P, P, I, I, P, I64, I, P]),
-    "aae_topk_work_bytes": (I64, [I, I]),
     "aae_masked_topk": (I, [P, I64, I, I, I, P, P, I, P, P, P, P]),
     "aae_topk_merge": (I, [P, P, I, I, I, P, P, P]),
+    "aae_topk_merge_seg": (I, [P, P, I, I, I, I, P, P, P]),
     "aae_rank_counts": (I, [P, I64, I, I, I, P, P, P, P, I, P, I, P, P]),
     "aae_predict_topk_work_bytes": (I64, [I, I, I]),
     "aae_predict_topk": (I, [P, I, I, P, P, I, I, P, P, I, I, P, I64, P, P, P, P]),
@@ -99,8 +86,6 @@ _SIGS = {
     "aae_tc_selftest": (I, [I, P, P, P, I, P]),
     "aae_upload_batch": (I, [P, P, I, I, P, P, P]),
     "aae_batch_gather": (I, [P, P, P, I64, I, P, P, P, I, P, P]),
-    "aae_finish_losses": (I, [P, D, I, P, P]),
-    "aae_copy_words": (I, [P, P, I64, P]),
     "aae_copy_words_sel": (I, [P, P, P, P, I64, P, I, P]),
     "aae_peer_buffer_bytes": (I64, [I64]),
     "aae_peer_alloc": (I, [I64, C.POINTER(P), C.c_char_p]),

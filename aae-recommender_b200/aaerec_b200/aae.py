@@ -483,9 +483,15 @@ class AdversarialAutoEncoder(object):
         eng.check_exchange()
         return out
 
-    def predict_topk(self, X, k, condition_data=None, mask_known=True, return_scores=False):
+    def predict_topk(self, X, k, condition_data=None, mask_known=True, return_scores=False, shard="items"):
         """Top-k unknown items per row = argtopk(remove_non_missing(predict(X), X), k)[1]
-        (evaluation.py:183-199, 20-58) without materialising [n, n_items] on the host."""
+        (evaluation.py:183-199, 20-58) without materialising [n, n_items] on the host.
+
+        Multi-GPU: ``shard='items'`` ranks every query against the local item shard and merges the per-shard lists
+        (one all-gather per batch); ``shard='sets'`` gives every rank a full-weight replica (built once) and its own
+        slice of the query rows -- no communication in the query loop; the slices are exchanged at the end."""
+        if shard == "sets" and self.engine.world > 1:
+            return self._predict_topk_set_sharded(X, k, condition_data, mask_known, return_scores)
         eng = self.engine
         n = X.shape[0]
         kk = min(k, eng.V)
@@ -503,6 +509,33 @@ class AdversarialAutoEncoder(object):
         return (idx, val) if return_scores else idx
 
 
+
+    def _predict_topk_set_sharded(self, X, k, condition_data, mask_known, return_scores):
+        import torch.distributed as dist
+        eng = self.engine
+        if getattr(self, "_replica", None) is None or self._replica_step != eng.steps_done:
+            self._replica = eng.make_replica(max_batch=max(self.batch_size, self.predict_batch_size))   # collective
+            self._replica_step = eng.steps_done
+        n = X.shape[0]
+        per = (n + eng.world - 1) // eng.world
+        lo, hi = min(n, eng.rank * per), min(n, (eng.rank + 1) * per)
+        Xl = _canonical_csr(X, "query matrix")[lo:hi]
+        cl = None
+        if condition_data is not None:
+            ad = self._cond_adapter()
+            cl = [ad.take(c, np.arange(lo, hi)) for c in condition_data]
+        main, self.engine = self.engine, self._replica
+        try:
+            out = self.predict_topk(Xl, k, condition_data=cl, mask_known=mask_known, return_scores=return_scores) \
+                if hi > lo else ((np.zeros((0, min(k, eng.V)), np.int64), np.zeros((0, min(k, eng.V)), np.float32))
+                                 if return_scores else np.zeros((0, min(k, eng.V)), np.int64))
+        finally:
+            self.engine = main
+        parts = [None] * eng.world
+        dist.all_gather_object(parts, out, group=eng.group)
+        if return_scores:
+            return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        return np.concatenate(parts)
 
     def gold_ranks(self, X, Y, condition_data=None, batch_size=256):
         """Rank (1-based) of every held-out item of ``Y`` (scipy sparse [n, n_items], the harness' ``y_test``) in the

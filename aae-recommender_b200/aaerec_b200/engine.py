@@ -91,7 +91,8 @@ class AAEEngine(object):
     def __init__(self, n_items, n_hidden=100, n_code=50, cond_dim=0, gen_lr=1e-3, reg_lr=1e-3,
                  dropout=(.2, .2), prior_scale=None, normalize_inputs=True, device=None,
                  rank=0, world=1, group=None, impl="auto", seed=0, max_batch=128, max_nnz=None,
-                 use_graph=True, overlap_sweep=True, adversarial=True, exchange="auto"):
+                 use_graph=True, overlap_sweep=True, adversarial=True, exchange="auto", inference_only=False):
+        self.inference_only = bool(inference_only)
         N.require_device(0 if device is None else (torch.device(device).index or 0))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.dev.index is None:
@@ -138,9 +139,14 @@ class AAEEngine(object):
         f32 = dict(dtype=torch.float32, device=self.dev)
         H, Cc, Cp, Vl = self.H, self.C, self.Cp, max(self.Vloc, 1)
         z = lambda *s: torch.zeros(*s, **f32)
-        self.W1t, self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2 = (z(Vl, H) for _ in range(5))
-        self.Wd3, self.Wd3_m, self.Wd3_v = (z(Vl, H) for _ in range(3))
-        self.bd3, self.bd3_m, self.bd3_v = (z(Vl) for _ in range(3))
+        # inference-only engines (set-sharded predict replicas) carry the weights without the six [V,H] Adam tensors
+        zm = (lambda *s: torch.zeros(*((1,) + tuple(s[1:])), **f32)) if self.inference_only else z
+        self.W1t = z(Vl, H)
+        self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2 = (zm(Vl, H) for _ in range(4))
+        self.Wd3 = z(Vl, H)
+        self.Wd3_m, self.Wd3_v = (zm(Vl, H) for _ in range(2))
+        self.bd3 = z(Vl)
+        self.bd3_m, self.bd3_v = (zm(Vl) for _ in range(2))
         self.n_enc = sum(s for _, s in enc_block_sizes(H, Cc))
         self.n_dec = sum(s for _, s in dec_block_sizes(H, Cp))
         self.n_disc = sum(s for _, s in disc_block_sizes(H, Cc))
@@ -413,6 +419,27 @@ class AAEEngine(object):
                 out[name] = v.reshape(shapes[name]) if name in shapes else v.clone()
                 off += sz
         return out
+
+    @_on_device
+    def make_replica(self, max_batch=1024):
+        """Set-sharded predict (SURVEY 8(e) 'Predict: ... or set-sharded replicas'): a single-rank, inference-only engine
+        on this GPU holding the FULL weights (item shards all-gathered once, collective), so that every rank can rank
+        its own slice of the query rows with zero communication.  Query sets are independent; the weights (1.6 GB at the
+        MPD shape) fit every GPU."""
+        self.flush_w1()
+        rep = AAEEngine(self.V, self.H, self.C, cond_dim=self.D, dropout=self.dropout, prior_scale=self.prior_scale,
+                        normalize_inputs=bool(self.normalize), device=self.dev, rank=0, world=1,
+                        impl={-1: "auto"}.get(self.impl, self.impl), seed=self.seed, max_batch=max_batch,
+                        use_graph=False, adversarial=self.adversarial, inference_only=True)
+        rep.W1t.copy_(self._gather_items(self.W1t[: self.Vloc]))
+        rep.Wd3.copy_(self._gather_items(self.Wd3[: self.Vloc]))
+        rep.bd3.copy_(self._gather_items(self.bd3[: self.Vloc]))
+        rep.enc.copy_(self.enc)
+        rep.dec.copy_(self.dec)
+        rep.disc.copy_(self.disc)
+        rep._w1_dirty = False
+        rep._wp_dirty = True
+        return rep
 
     def optim_state(self, which):
         """Adam moments of one of the reference's four optimizers (aae.py:798-804) in torch's parameter names and
@@ -856,6 +883,8 @@ class AAEEngine(object):
         (R, D, G) land in ``self.losses`` (device float32[3])."""
         if B <= 0:
             return
+        if self.inference_only:
+            raise RuntimeError("this engine was built inference_only (a predict replica): it cannot train")
         self._run((B, bool(injected)), lambda: self._enqueue_step(B, injected))
         self.steps_done += 1
         self._w1_dirty = True
@@ -872,6 +901,8 @@ class AAEEngine(object):
         nnz = int(indptr_np[-1])
         if B <= 0:
             return None
+        if self.inference_only:
+            raise RuntimeError("this engine was built inference_only (a predict replica): it cannot train")
         self._ensure_ws(B, nnz)
         si = self.steps_done & 1          # the graph's copy kernels pick the slot from the device step counter: t = steps_done + 1
         slot = self._zc[si]
@@ -1068,12 +1099,43 @@ class AAEEngine(object):
                  ptr(val), None, self._stream())
         if self.world == 1:
             return idx, val
+        return self._merge_shards(B, k, idx, val)
+
+    def _merge_shards(self, B, k, idx, val):
+        """Item shards -> global top-k: all-gather of the [B, kpad] per-shard lists into preallocated [world, B, kpad]
+        buffers, then one merge kernel that reads that layout directly (no torch repacking in the query loop)."""
+        import torch.distributed as dist
         kmax = min(k, (self.V + self.world - 1) // self.world)
-        cv, ci = gather_topk_candidates(val, idx, kmax, self.world, self.group)
         kk = min(k, self.V)
-        oi = torch.empty(B, kk, dtype=torch.int32, device=self.dev)
-        ov = torch.empty(B, kk, dtype=torch.float32, device=self.dev)
-        call("aae_topk_merge", ptr(cv), ptr(ci), B, cv.shape[1], kk, ptr(oi), ptr(ov), self._stream())
+        kl = idx.shape[1]
+        key = (B, kmax, kk)
+        mb = getattr(self, "_merge_bufs", None)
+        if mb is None or mb["key"] != key:
+            mb = dict(key=key,
+                      pv=torch.full((B, kmax), -3.0e38, dtype=torch.float32, device=self.dev),
+                      pi=torch.full((B, kmax), -1, dtype=torch.int32, device=self.dev),
+                      gv=torch.empty(self.world, B, kmax, dtype=torch.float32, device=self.dev),
+                      gi=torch.empty(self.world, B, kmax, dtype=torch.int32, device=self.dev),
+                      out=[(torch.empty(B, kk, dtype=torch.int32, device=self.dev),
+                            torch.empty(B, kk, dtype=torch.float32, device=self.dev)) for _ in range(4)], i=0)
+            self._merge_bufs = mb
+        if kl == kmax:
+            pv, pi = val.contiguous(), idx.contiguous()
+        else:                                   # a last shard smaller than k: pad its list
+            mb["pv"][:, :kl].copy_(val)
+            mb["pi"][:, :kl].copy_(idx)
+            pv, pi = mb["pv"], mb["pi"]
+        dist.all_gather_into_tensor(mb["gv"], pv, group=self.group)
+        dist.all_gather_into_tensor(mb["gi"], pi, group=self.group)
+        mb["i"] = (mb["i"] + 1) % 4
+        oi, ov = mb["out"][mb["i"]]
+        if self.world * kmax <= 2048:
+            call("aae_topk_merge_seg", ptr(mb["gv"]), ptr(mb["gi"]), self.world, B, kmax, kk, ptr(oi), ptr(ov),
+                 self._stream())
+        else:
+            cv = mb["gv"].permute(1, 0, 2).reshape(B, -1).contiguous()
+            ci = mb["gi"].permute(1, 0, 2).reshape(B, -1).contiguous()
+            call("aae_topk_merge", ptr(cv), ptr(ci), B, cv.shape[1], kk, ptr(oi), ptr(ov), self._stream())
         return oi, ov
 
     def topk_status(self):

@@ -38,46 +38,6 @@ __global__ void step_tick_kernel(aae_step_state* st) {
   st->bc2_sqrt = (float)sqrt(bc2);
 }
 
-// Start of one partial_fit in a single launch: Adam step counter / bias corrections, loss accumulators,
-// the touched-row counter, and the zero fill of the accumulation buffers (dh2 and the two compact
-// first-layer gradient buffers, nnz*H floats each).
-__global__ void __launch_bounds__(256) step_begin_kernel(aae_step_state* st, double* sums, int n_sums, int32_t* counter,
-                                                         float* z0, int64_t n0, float* z1, float* z2,
-                                                         const int32_t* __restrict__ indptr, int B, int H) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int t = st->t + 1;
-    st->t = t;
-    st->rng_step += 1;
-    double bc1 = 1.0 - pow(0.9, (double)t);
-    double bc2 = 1.0 - pow(0.999, (double)t);
-    st->step_size_gen = (float)((double)st->gen_lr / bc1);
-    st->step_size_reg = (float)((double)st->reg_lr / bc1);
-    st->bc2_sqrt = (float)sqrt(bc2);
-    for (int i = 0; i < n_sums; ++i) sums[i] = 0.0;
-    if (counter) *counter = 0;
-  }
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = tid; i < n0; i += nth) z0[i] = 0.f;
-  if (z1 || z2) {
-    const int64_t n = (int64_t)indptr[B] * H;
-    for (int64_t i = tid; i < n; i += nth) {
-      if (z1) z1[i] = 0.f;
-      if (z2) z2[i] = 0.f;
-    }
-  }
-}
-// End of one partial_fit: release the touched-row slots and finalise the three losses.
-__global__ void __launch_bounds__(256) step_end_kernel(int32_t* slot_of, const int32_t* __restrict__ uniq,
-                                                       const int32_t* __restrict__ n_uniq, int cap, const double* sums,
-                                                       double n_total, int B, float* out) {
-  int n = min(*n_uniq, cap);
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) slot_of[uniq[s]] = -1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    out[0] = (float)(sums[0] / n_total);
-    out[1] = (float)(sums[1] / (double)B);
-    out[2] = (float)(sums[2] / (double)B);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // K1: one warp per set, lanes stride over the float4 columns of each gathered row.
@@ -147,88 +107,10 @@ __global__ void __launch_bounds__(256) bag_fwd_kernel(const int32_t* __restrict_
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// touched-row slots
-// ---------------------------------------------------------------------------------------------
-__global__ void batch_slots_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int B,
-                                   int v_begin, int v_end, int32_t* slot_of, int32_t* uniq, int32_t* n_uniq) {
-  int nnz = indptr[B];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x) {
-    int i = indices[e];
-    if (i < v_begin || i >= v_end) continue;
-    i -= v_begin;
-    if (atomicCAS(&slot_of[i], -1, -2) == -1) {
-      int s = atomicAdd(n_uniq, 1);
-      uniq[s] = i;
-      slot_of[i] = s;  // nobody reads slot_of before the next kernel
-    }
-  }
-}
-__global__ void batch_slots_reset_kernel(int32_t* slot_of, const int32_t* __restrict__ uniq, int32_t* n_uniq,
-                                         int cap) {
-  int n = min(*n_uniq, cap);
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) slot_of[uniq[s]] = -1;
-}
 __global__ void zero_counter_kernel(int32_t* n_uniq) { *n_uniq = 0; }
 
-__global__ void zero_rows_kernel(float* G, const int32_t* __restrict__ indptr, int B, int H) {
-  size_t n = (size_t)indptr[B] * H;
-  size_t n4 = n >> 2;
-  float4* G4 = reinterpret_cast<float4*>(G);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-    G4[i] = make_float4(0, 0, 0, 0);
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) G[(n4 << 2) + threadIdx.x] = 0.f;
-}
 
-// ---------------------------------------------------------------------------------------------
-// K2: scatter-add of the first layer's weight gradient into the compact touched-row buffer.
-// One warp per (set, item) pair (the set of a CSR entry is found by bisection of indptr); lanes over the
-// hidden units, red.global.add.f32 (rows of popular items are shared by several sets).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bag_bwd_kernel(const int32_t* __restrict__ indptr,
-                                                      const int32_t* __restrict__ indices, int B,
-                                                      const float* __restrict__ dh1, int H, int normalize,
-                                                      const int32_t* __restrict__ slot_of, int v_begin, int v_end,
-                                                      float* __restrict__ G) {
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int nnz = indptr[B];
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nnz; e += warps) {
-    const int i = indices[e];
-    if (i < v_begin || i >= v_end) continue;
-    int lo = 0, hi = B;                       // largest b with indptr[b] <= e
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (indptr[mid] <= e) lo = mid; else hi = mid;
-    }
-    const int b = lo;
-    const float scale = normalize ? 1.0f / fmaxf((float)(indptr[b + 1] - indptr[b]), 1e-12f) : 1.0f;
-    float* grow = G + (size_t)slot_of[i - v_begin] * H;
-    const float* drow = dh1 + (size_t)b * H;
-    for (int c = lane; c < H; c += 32) atomicAdd(grow + c, drow[c] * scale);
-  }
-}
 
-__global__ void __launch_bounds__(256) rows_adam_kernel(const int32_t* __restrict__ uniq,
-                                                        const int32_t* __restrict__ n_uniq, int cap,
-                                                        const float* __restrict__ G, float* __restrict__ W,
-                                                        float* __restrict__ m, float* __restrict__ v, int H,
-                                                        const aae_step_state* __restrict__ st, int which) {
-  AdamK k = adam_load(st, which);
-  int n = min(*n_uniq, cap);
-  int lane = threadIdx.x & 31;
-  int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
-    size_t row = (size_t)uniq[s] * H;
-    for (int c = lane; c < H; c += 32) {
-      float p = W[row + c], mm = m[row + c], vv = v[row + c];
-      adam_update(k, G[(size_t)s * H + c], p, mm, vv);
-      W[row + c] = p;
-      m[row + c] = mm;
-      v[row + c] = vv;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Fused-step bookkeeping: ONE single-CTA launch builds the touched-row slots and the transposed (item ->
@@ -526,59 +408,6 @@ __global__ void __launch_bounds__(256) w1_sweep_untouched_kernel(const int32_t* 
   }
   trace_mark(TR_SWEEP, 1);
 }
-// Co-resident variant: the decoder-output kernel owns every SM (one 544-thread CTA, 221 KB of shared memory,
-// 52k registers), so a sweep launched as 8x256-thread CTAs per SM would simply keep it off the machine until
-// the sweep is done.  This variant is sized to fit BESIDE it: 64-thread CTAs of <= 96 registers (two of them
-// fit into the 13k registers the decoder kernel leaves free), each thread keeping U float4 positions of all five
-// tensors in flight (U*80 bytes) so that few threads still cover the HBM latency.
-template <int T, int U>
-__global__ void __launch_bounds__(T) w1_sweep_untouched_slim_kernel(const int32_t* __restrict__ slot_of, int r_begin,
-                                                                     int r_end, int H, float* __restrict__ W,
-                                                                     float* __restrict__ m1, float* __restrict__ v1,
-                                                                     float* __restrict__ m2, float* __restrict__ v2,
-                                                                     const aae_step_state* __restrict__ st) {
-  const AdamK k1 = adam_load(st, 0), k2 = adam_load(st, 1);
-  trace_mark(TR_SWEEP, 0);
-  const int H4 = H >> 2;
-  const size_t begin = (size_t)r_begin * H4, end = (size_t)r_end * H4;
-  const size_t nth = (size_t)gridDim.x * blockDim.x;
-  for (size_t q0 = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q0 < end; q0 += nth * U) {
-    float4 p[U], a[U], b[U], c[U], d[U];
-    bool live[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t q = q0 + (size_t)u * nth;
-      live[u] = q < end && __ldg(slot_of + (int)(q / H4)) < 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t q = q0 + (size_t)u * nth;
-      if (live[u]) {
-        p[u] = __ldcs(reinterpret_cast<const float4*>(W) + q);
-        a[u] = __ldcs(reinterpret_cast<const float4*>(m1) + q);
-        b[u] = __ldcs(reinterpret_cast<const float4*>(v1) + q);
-        c[u] = __ldcs(reinterpret_cast<const float4*>(m2) + q);
-        d[u] = __ldcs(reinterpret_cast<const float4*>(v2) + q);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t q = q0 + (size_t)u * nth;
-      if (live[u]) {
-        adam_update_zero(k1, p[u].x, a[u].x, b[u].x); adam_update_zero(k2, p[u].x, c[u].x, d[u].x);
-        adam_update_zero(k1, p[u].y, a[u].y, b[u].y); adam_update_zero(k2, p[u].y, c[u].y, d[u].y);
-        adam_update_zero(k1, p[u].z, a[u].z, b[u].z); adam_update_zero(k2, p[u].z, c[u].z, d[u].z);
-        adam_update_zero(k1, p[u].w, a[u].w, b[u].w); adam_update_zero(k2, p[u].w, c[u].w, d[u].w);
-        __stcs(reinterpret_cast<float4*>(W) + q, p[u]);
-        __stcs(reinterpret_cast<float4*>(m1) + q, a[u]);
-        __stcs(reinterpret_cast<float4*>(v1) + q, b[u]);
-        __stcs(reinterpret_cast<float4*>(m2) + q, c[u]);
-        __stcs(reinterpret_cast<float4*>(v2) + q, d[u]);
-      }
-    }
-  }
-  trace_mark(TR_SWEEP, 1);
-}
 __global__ void __launch_bounds__(256) w1_sweep_untouched_scalar_kernel(const int32_t* __restrict__ slot_of,
                                                                         int r_begin, int r_end, int H, float* W,
                                                                         float* m1, float* v1, float* m2, float* v2,
@@ -595,22 +424,7 @@ __global__ void __launch_bounds__(256) w1_sweep_untouched_scalar_kernel(const in
   }
 }
 
-__global__ void __launch_bounds__(256) adam_dense_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                         const aae_step_state* __restrict__ st, int which) {
-  AdamK k = adam_load(st, which);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float pp = p[i], mm = m[i], vv = v[i];
-    adam_update(k, g[i], pp, mm, vv);
-    p[i] = pp; m[i] = mm; v[i] = vv;
-  }
-}
 
-__global__ void finish_losses_kernel(const double* sums, double n_total, int B, float* out) {
-  out[0] = (float)(sums[0] / n_total);
-  out[1] = (float)(sums[1] / (double)B);
-  out[2] = (float)(sums[2] / (double)B);
-}
 
 }  // namespace aae
 
@@ -629,21 +443,6 @@ int aae_step_tick(aae_step_state* st, void* stream) {
   return check_launch("step_tick");
 }
 
-int aae_step_begin(aae_step_state* st, double* loss_sums, int n_sums, int32_t* n_uniq, float* dh2, int64_t n_dh2,
-                   float* G1, float* G2, const int32_t* indptr, int B, int H, void* stream) {
-  AAE_REQUIRE(st && loss_sums && n_sums >= 0, "null pointer");
-  AAE_REQUIRE((!G1 && !G2) || indptr, "indptr missing");
-  step_begin_kernel<<<2 * sm_count(), 256, 0, as_stream(stream)>>>(st, loss_sums, n_sums, n_uniq, dh2, dh2 ? n_dh2 : 0,
-                                                                  G1, G2, indptr, B, H);
-  return check_launch("step_begin");
-}
-int aae_step_end(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, const double* sums,
-                 double n_total, int B, float* losses, void* stream) {
-  AAE_REQUIRE(slot_of && uniq && n_uniq && sums && losses, "null pointer");
-  step_end_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(cap, 256))), 256, 0, as_stream(stream)>>>(
-      slot_of, uniq, n_uniq, cap, sums, n_total, B, losses);
-  return check_launch("step_end");
-}
 
 int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const float* W1t, const float* b1, int H,
                 int normalize, int v_begin, int v_end, int add_bias, float* out, void* stream) {
@@ -659,40 +458,6 @@ int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const floa
   return check_launch("bag_fwd");
 }
 
-int aae_batch_slots(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end, int32_t* slot_of,
-                    int32_t* uniq, int32_t* n_uniq, int counter_is_zero, void* stream) {
-  AAE_REQUIRE(indptr && indices && slot_of && uniq && n_uniq, "null pointer");
-  if (!counter_is_zero) zero_counter_kernel<<<1, 1, 0, as_stream(stream)>>>(n_uniq);
-  batch_slots_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv((int64_t)B * 16, 256))), 256, 0, as_stream(stream)>>>(
-      indptr, indices, B, v_begin, v_end, slot_of, uniq, n_uniq);
-  return check_launch("batch_slots");
-}
-int aae_batch_slots_reset(int32_t* slot_of, const int32_t* uniq, int32_t* n_uniq, int cap, void* stream) {
-  AAE_REQUIRE(slot_of && uniq && n_uniq, "null pointer");
-  batch_slots_reset_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(cap, 256))), 256, 0, as_stream(stream)>>>(
-      slot_of, uniq, n_uniq, cap);
-  return check_launch("batch_slots_reset");
-}
-int aae_zero_rows(float* G, const int32_t* indptr, int B, int H, void* stream) {
-  AAE_REQUIRE(G && indptr, "null pointer");
-  zero_rows_kernel<<<2 * sm_count(), 256, 0, as_stream(stream)>>>(G, indptr, B, H);
-  return check_launch("zero_rows");
-}
-int aae_bag_bwd(const int32_t* indptr, const int32_t* indices, int B, const float* dh1, int H, int normalize,
-                const int32_t* slot_of, int v_begin, int v_end, float* G, void* stream) {
-  AAE_REQUIRE(indptr && indices && dh1 && slot_of && G, "null pointer");
-  int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)B * 16 * 32, 256)));   // ~one warp per entry
-  bag_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(indptr, indices, B, dh1, H, normalize, slot_of, v_begin,
-                                                       v_end, G);
-  return check_launch("bag_bwd");
-}
-int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const float* G, float* W, float* m, float* v,
-                  int H, const aae_step_state* st, int which, void* stream) {
-  AAE_REQUIRE(uniq && n_uniq && G && W && m && v && st, "null pointer");
-  int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)cap * 32, 256)));
-  rows_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, G, W, m, v, H, st, which);
-  return check_launch("rows_adam");
-}
 int aae_batch_prepare(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end, int32_t* slot_of,
                       int32_t* uniq, int32_t* n_uniq, int32_t* cnt, int32_t* pos, int32_t* csc_off, int32_t* csc_row,
                       int cap, void* stream) {
@@ -725,30 +490,6 @@ int aae_step_finish(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq
       slot_of, uniq, n_uniq, cap, sums, n_sums, n_total, B, losses, st, ktab);
   return check_launch("step_finish");
 }
-int aae_w1_sweep_untouched_slim(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
-                                float* m2, float* v2, const aae_step_state* st, int ctas_per_sm, void* stream) {
-  AAE_REQUIRE(slot_of && W && m1 && v1 && m2 && v2 && st, "null pointer");
-  AAE_REQUIRE((H & 3) == 0 && ctas_per_sm >= 1 && ctas_per_sm <= 8, "n_hidden must be a multiple of 4; 1..8 CTAs per SM");
-  if (r_end <= r_begin) return AAE_OK;
-  static int cfg = -1;   // experiment switch: AAE_B200_SWEEP_CFG = threads*10 + unroll
-  if (cfg < 0) {
-    const char* e = getenv("AAE_B200_SWEEP_CFG");
-    cfg = e ? atoi(e) : 644;
-  }
-  const int grid = ctas_per_sm * sm_count();
-  cudaStream_t s = as_stream(stream);
-#define SLIM(T, U) w1_sweep_untouched_slim_kernel<T, U><<<grid, T, 0, s>>>(slot_of, r_begin, r_end, H, W, m1, v1, m2, v2, st)
-  switch (cfg) {
-    case 642: SLIM(64, 2); break;
-    case 1282: SLIM(128, 2); break;
-    case 1284: SLIM(128, 4); break;
-    case 2562: SLIM(256, 2); break;
-    case 2561: SLIM(256, 1); break;
-    default: SLIM(64, 4); break;
-  }
-#undef SLIM
-  return check_launch("w1_sweep_untouched_slim");
-}
 int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
                            float* m2, float* v2, const aae_step_state* st, void* stream) {
   AAE_REQUIRE(slot_of && W && m1 && v1 && m2 && v2 && st, "null pointer");
@@ -760,13 +501,6 @@ int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H
     w1_sweep_untouched_scalar_kernel<<<blocks, 256, 0, as_stream(stream)>>>(slot_of, r_begin, r_end, H, W, m1, v1, m2,
                                                                            v2, st);
   return check_launch("w1_sweep_untouched");
-}
-int aae_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, const aae_step_state* st, int which,
-                   void* stream) {
-  AAE_REQUIRE(p && g && m && v && st, "null pointer");
-  int blocks = std::max(1, std::min(8 * sm_count(), cdiv(n, 256)));
-  adam_dense_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, st, which);
-  return check_launch("adam_dense");
 }
 } // extern "C"
 namespace aae {
@@ -876,21 +610,6 @@ int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, in
   }
   return AAE_OK;
 }
-// 4-byte words from src to dst; either side may be pinned (mapped) host memory -- used INSIDE the step's CUDA graph
-// instead of memcpy nodes: a kernel-to-kernel edge costs ~1.5 us, a copy-engine hop several.
-__global__ void __launch_bounds__(256) copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                         int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = src[i];
-}
-int aae_copy_words(const void* src, void* dst, int64_t n_words, void* stream) {
-  AAE_REQUIRE(src && dst && n_words >= 0, "bad argument");
-  if (n_words == 0) return AAE_OK;
-  int blocks = (int)std::min<int64_t>(2 * sm_count(), (n_words + 255) / 256);
-  copy_words_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(src),
-                                                           reinterpret_cast<uint32_t*>(dst), n_words);
-  return check_launch("copy_words");
-}
 
 // Same copy, with the pinned slot chosen ON THE DEVICE from the step counter: slot = (t + bias) & 1.  One captured
 // graph then serves both slots (alternating between two instantiated graphs costs ~100 us per launch).
@@ -915,10 +634,5 @@ int aae_copy_words_sel(const void* src0, const void* src1, void* dst0, void* dst
   return check_launch("copy_words_sel");
 }
 
-int aae_finish_losses(const double* sums, double n_total, int B, float* out, void* stream) {
-  AAE_REQUIRE(sums && out, "null pointer");
-  finish_losses_kernel<<<1, 1, 0, as_stream(stream)>>>(sums, n_total, B, out);
-  return check_launch("finish_losses");
-}
 
 }  // extern "C"

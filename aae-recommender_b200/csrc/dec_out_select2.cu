@@ -368,13 +368,28 @@ static int get_tensor_map(const float* Wp, int Vloc, int cy, CUtensorMap* out) {
   const cuuint64_t gstride[1] = {(cuuint64_t)s2::KP * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)s2::KBOX, (cuuint32_t)(s2::PN / cy)};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstride, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // The driver entry point is looked up through the runtime (cudaGetDriverEntryPoint), so the library has no link-time
+  // dependency on libcuda.so.1 and still loads on a machine without a driver (CPU-side ABI tests, the build check).
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ce != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(ce));
+      cudaGetLastError();
+      return AAE_E_CUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    const char* msg = nullptr;
-    cuGetErrorString(r, &msg);
-    set_error("cuTensorMapEncodeTiled: %s", msg ? msg : "error");
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return AAE_E_CUDA;
   }
   if (g_maps.size() > 64) g_maps.clear();

@@ -951,12 +951,20 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       tc_fence_after();
       if (elect_one()) {
         // logits of the next tile first: its epilogue math then overlaps the backward GEMMs of this tile
+        // K3X_* (here and below): timing experiments only (scripts/k3_experiments.sh); never defined in the product build
+#ifndef K3X_NO_G1
         if (it < n_my) issue_gemm<SPLIT>(tmem + T2_Z + (uint32_t)(it & 1) * 32u, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
+#endif
         mma_commit(&bar_g1);
         if (it > 0) {
           const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
+#ifndef K3X_NO_G3
           issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g1, 0u);
+#endif
+#ifndef K3X_NO_G2
           issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2, it > 1 ? 1u : 0u);
+#endif
+          (void)bo;
         }
         mma_commit(&bar_g23);
         prefetch_w(it + K3_PF_AHEAD);
@@ -1085,7 +1093,11 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       }
       mbar_wait(&bar_stage, phase_e);
       phase_e ^= 1;
+#ifdef K3X_NO_E2LD
+      if (false) {
+#else
       if (kAdam) {
+#endif
         if (nv == TN) {
 #pragma unroll
           for (int j = 0; j < CWT; ++j) {
@@ -1130,6 +1142,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         // warps per scheduler the element-after-element form left the issue slots idle (ncu: 11 stall samples per
         // instruction in this block).
         float dn[CWT];
+#ifndef K3X_NO_E2MATH
 #pragma unroll
         for (int j = 0; j < CWT; ++j) pm[j] = fmaf(ak.w1, gw[j] - pm[j], pm[j]);
 #pragma unroll
@@ -1140,6 +1153,11 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         for (int j = 0; j < CWT; ++j) dn[j] = pm[j] * rcp_approx(dn[j]);
 #pragma unroll
         for (int j = 0; j < CWT; ++j) pw[j] = fmaf(-ak.step_size, dn[j], pw[j]);
+#else
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) { dn[j] = gw[j]; pw[j] += dn[j]; }
+#endif
+#ifndef K3X_NO_E2ST
 #pragma unroll
         for (int j = 0; j < CWT; ++j) {
           if (j < ecnt) {
@@ -1148,6 +1166,9 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
             __stcs(pV + (size_t)j * H, pv[j]);
           }
         }
+#else
+        if (pw[0] + pm[1] + pv[2] == 1.2345e30f) pW[0] = pw[3];      // keep the values alive
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < CWT; ++j)
@@ -1208,9 +1229,14 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
           for (int q = 0; q < CWT / 4; ++q) pr[q] = 1.0f;
 #pragma unroll
           for (int j = 0; j < CWT; ++j) {
+#ifdef K3X_NO_E1MATH
+            const float u = z[j], t = 1.0f + u;
+            const float d = t * inv_n_row;
+#else
             const float u = ex2_approx(-1.4426950408889634f * z[j]);
             const float t = 1.0f + u;
             const float d = rcp_approx(t) * inv_n_row;
+#endif
             sz += z[j];
             pr[j >> 2] *= t;
             const float h = tf32_hi(d);
@@ -1244,7 +1270,9 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       }
       TmemIO<CWT>::st(lane_addr + T2_DZH + cpart * CWT, dzh);
       if (with_lo) TmemIO<CWT>::st(lane_addr + T2_DZL + cpart * CWT, dzl);
+#ifndef K3X_NO_WT
       store_wt_regs<WCHT>(wA, wc, wt_hi, wt_lo, with_lo);              // W'(i) transposed for G2(i)
+#endif
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();

@@ -796,11 +796,6 @@ int aae_ae_fwd_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* con
            dh2_zero, 1);
   return check_launch("ae_fwd");
 }
-int aae_ae_fwd(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, aae_drop e1,
-               aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st, float* a1, float* a2, float* zc,
-               float* dd1, float* h2, void* stream) {
-  return aae_ae_fwd_bag(d, NO_BAG, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2, nullptr, stream);
-}
 
 int aae_predict_tail_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* enc,
                          const float* dec, float* h2, void* stream) {
@@ -813,10 +808,6 @@ int aae_predict_tail_bag(aae_dims d, aae_bag bag, const float* h1pre, const floa
            (const aae_step_state*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, h2,
            (float*)nullptr, 0);
   return check_launch("predict_tail");
-}
-int aae_predict_tail(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec, float* h2,
-                     void* stream) {
-  return aae_predict_tail_bag(d, NO_BAG, h1pre, cond, enc, dec, h2, stream);
 }
 
 int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec, aae_drop e1, aae_drop e2, aae_drop d1,
@@ -850,12 +841,6 @@ int aae_disc_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float*
   }
   return check_launch("disc_phase");
 }
-int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float prior_scale, const float* enc,
-                   const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2, const aae_step_state* st,
-                   float* acts, float* grads, double* loss_sum, void* stream) {
-  return aae_disc_phase_bag(d, NO_BAG, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum,
-                            stream);
-}
 
 int aae_gen_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* enc, const float* disc, aae_drop e1,
                       aae_drop e2, aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
@@ -866,11 +851,6 @@ int aae_gen_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* 
   LAUNCH_R(gen_phase_kernel, d.B, 7 * ld + 2, stream, d, bag, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2,
            g_h1, loss_sum);
   return check_launch("gen_phase");
-}
-int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float* disc, aae_drop e1, aae_drop e2,
-                  aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z, float* g_e2,
-                  float* g_h1, double* loss_sum, void* stream) {
-  return aae_gen_phase_bag(d, NO_BAG, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2, g_h1, loss_sum, stream);
 }
 
 int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, const float* dd1, const float* g_d2,

@@ -387,6 +387,41 @@ __global__ void __launch_bounds__(CS_THREADS) cand_sort_small_kernel(const float
   }
 }
 
+// k-way merge of per-shard top-k lists that an all-gather left in [world][B][kpad] order (item-sharded predict): one
+// CTA per row gathers its world * kpad <= CS_CAP candidates from the segments and sorts them in shared memory.
+__global__ void __launch_bounds__(CS_THREADS) seg_merge_small_kernel(const float* __restrict__ val,
+                                                                     const int32_t* __restrict__ idx, int world, int B,
+                                                                     int kpad, int k, int32_t* __restrict__ idx_out,
+                                                                     float* __restrict__ val_out) {
+  __shared__ unsigned long long buf[CS_CAP];
+  const int rowi = blockIdx.x;
+  const int n = world * kpad;
+  int npow = 2;
+  while (npow < n) npow <<= 1;
+  for (int i = threadIdx.x; i < npow; i += CS_THREADS) {
+    unsigned long long c = 0ull;
+    if (i < n) {
+      const int r = i / kpad, j = i - r * kpad;
+      const size_t src = ((size_t)r * B + rowi) * kpad + j;
+      const int32_t id = idx[src];
+      c = (id >= 0) ? compose(f2key(val[src]), (uint32_t)id) : 0ull;
+    }
+    buf[i] = c;
+  }
+  bitonic_desc(buf, npow);
+  for (int i = threadIdx.x; i < k; i += CS_THREADS) {
+    const unsigned long long c = buf[i];
+    int32_t id = -1;
+    float v = -FLT_MAX;
+    if (c != 0ull) {
+      id = (int32_t)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull));
+      v = key2f((uint32_t)(c >> 32));
+    }
+    idx_out[(size_t)rowi * k + i] = id;
+    if (val_out) val_out[(size_t)rowi * k + i] = v;
+  }
+}
+
 // Threshold of the fused predict path: (approximately) the J-th largest of the row's S sample scores.  Every
 // thread keeps the 4 largest of its strided share in registers, the 256 x 4 survivors are sorted in shared memory
 // and the J-th is taken.  A thread that holds more than 4 of the row's top J makes the result slightly LOWER than
@@ -541,7 +576,6 @@ using namespace aae;
 
 extern "C" {
 
-int64_t aae_topk_work_bytes(int B, int k) { return 16; }
 
 static int launch_row_topk(const float* scores, int64_t lds, int B, int n, int k, int idx_offset,
                            const int32_t* idx_map, int32_t* idx_out, float* val_out, cudaStream_t s,
@@ -732,6 +766,16 @@ int aae_predict_topk2(const float* h2, int B, int H, const float* Wd3, const flo
   if (rc) return rc;
   check_kth_kernel<<<cdiv(B, 256), 256, 0, s>>>(vout, k, thr, thr_stride, tot, B, n_bad);
   return check_launch("check_kth");
+}
+
+int aae_topk_merge_seg(const float* cand_val, const int32_t* cand_idx, int world, int B, int kpad, int k,
+                       int32_t* idx_out, float* val_out, void* stream) {
+  AAE_REQUIRE(cand_val && cand_idx && idx_out, "null pointer");
+  AAE_REQUIRE(world >= 1 && B > 0 && kpad > 0 && k > 0 && k <= world * kpad, "bad size");
+  AAE_REQUIRE(world * kpad <= CS_CAP, "more than 2048 candidates per row: use aae_topk_merge");
+  seg_merge_small_kernel<<<B, CS_THREADS, 0, as_stream(stream)>>>(cand_val, cand_idx, world, B, kpad, k, idx_out,
+                                                                  val_out);
+  return check_launch("seg_merge_small");
 }
 
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,

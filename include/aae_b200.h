@@ -69,14 +69,6 @@ int aae_device_check(int dev);
 /* ---- step bookkeeping ------------------------------------------------------------------- */
 int aae_step_state_init(aae_step_state* st, float gen_lr, float reg_lr, uint64_t seed, void* stream);
 int aae_step_tick(aae_step_state* st, void* stream);
-/* One launch for the start of a partial_fit: aae_step_tick + zero of loss_sums[0..n_sums), of the
- * touched-row counter n_uniq (may be NULL), of dh2[0..n_dh2) and of the first indptr[B]*H floats of the
- * compact first-layer gradient buffers G1 / G2 (each may be NULL). */
-int aae_step_begin(aae_step_state* st, double* loss_sums, int n_sums, int32_t* n_uniq, float* dh2, int64_t n_dh2,
-                   float* G1, float* G2, const int32_t* indptr, int B, int H, void* stream);
-/* One launch for its end: aae_batch_slots_reset + aae_finish_losses. */
-int aae_step_end(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, const double* sums,
-                 double n_total, int B, float* losses, void* stream);
 
 /* ---- K1: encoder first layer on the sparse multi-hot input ---------------------------------
  * Replaces F.normalize(inp, 1) + Encoder.lin1 (aae.py:132-135): out[b,:] = b1 + sum_{i in set_b}
@@ -85,26 +77,8 @@ int aae_step_end(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, i
 int aae_bag_fwd(const int32_t* indptr, const int32_t* indices, int B, const float* W1t, const float* b1,
                 int H, int normalize, int v_begin, int v_end, int add_bias, float* out, void* stream);
 
-/* ---- touched-row bookkeeping for the sparse first layer -------------------------------------
- * slot_of[V] (all -1 between steps) maps an item of the current batch to a dense slot, uniq[]
- * lists the items, n_uniq[0] their count.  Only items in [v_begin, v_end) get slots.
- * counter_is_zero != 0: n_uniq[0] was already cleared (aae_step_begin), skip the clearing launch. */
-int aae_batch_slots(const int32_t* indptr, const int32_t* indices, int B, int v_begin, int v_end,
-                    int32_t* slot_of, int32_t* uniq, int32_t* n_uniq, int counter_is_zero, void* stream);
-int aae_batch_slots_reset(int32_t* slot_of, const int32_t* uniq, int32_t* n_uniq, int cap, void* stream);
 
-/* ---- K2: weight gradient of the sparse first layer ------------------------------------------
- * Replaces the dense dW1 = dh1^T . Xhat that autograd builds (aae.py:703, 741):
- * G[slot_of[i],:] += dh1[b,:] * (normalize ? 1/|set_b| : 1) for every i in set_b.  G must be zero
- * on entry for the first n_uniq rows (aae_zero_rows). */
-int aae_bag_bwd(const int32_t* indptr, const int32_t* indices, int B, const float* dh1, int H, int normalize,
-                const int32_t* slot_of, int v_begin, int v_end, float* G, void* stream);
-int aae_zero_rows(float* G, const int32_t* indptr, int B, int H, void* stream);
 
-/* Adam on the touched rows only (rows uniq[0..n_uniq)) with gradient G[slot,:]; which = 0 uses
- * step_size_gen (enc_optim), 1 uses step_size_reg (gen_optim). */
-int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const float* G, float* W, float* m,
-                  float* v, int H, const aae_step_state* st, int which, void* stream);
 
 /* Dense-Adam-equivalent sweep of W1t for rows NOT in the batch: torch's Adam moves every row every
  * step even when its gradient is zero (momentum decay), once per optimizer state, enc_optim first
@@ -113,12 +87,6 @@ int aae_rows_adam(const int32_t* uniq, const int32_t* n_uniq, int cap, const flo
 int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,
                            float* m2, float* v2, const aae_step_state* st, void* stream);
 
-/* Same update, sized to run BESIDE aae_dec_out_train (whose one CTA per SM leaves 13k registers and no shared
- * memory free): ctas_per_sm x 64-thread CTAs of <= 96 registers, four float4 positions of all five tensors in
- * flight per thread.  n_hidden % 4 == 0. */
-int aae_w1_sweep_untouched_slim(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1,
-                                float* v1, float* m2, float* v2, const aae_step_state* st, int ctas_per_sm,
-                                void* stream);
 
 /* ---- time-blocked dense Adam for W1t (the engine's default policy) ----------------------------------
  * The zero-gradient Adam update of a row that is not in the batch depends only on the row and on the step's
@@ -144,9 +112,6 @@ int aae_w1_sweep_blocked(const int32_t* slot_of, int Vloc, int H, float* W, floa
                          float* v2, int32_t* last, const aae_step_state* st, const float* ktab, int G, int flush,
                          int ctas_per_sm, void* stream);
 
-/* Elementwise Adam over a contiguous block of n parameters (the small replicated layers). */
-int aae_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, const aae_step_state* st,
-                   int which, void* stream);
 
 /* ---- K4: the small replicated layers ---------------------------------------------------------
  * All small weights of a module live in one contiguous block; the structs give their shapes.
@@ -158,11 +123,6 @@ typedef struct {
   int B, H, C, D;
 } aae_dims;
 
-/* ae_step forward tail (aae.py:136-146, 688-690, 168-174): from h1pre = Xhat.W1^T + b1 to the
- * decoder hidden h2.  Saves the post-activation values needed by the backward. */
-int aae_ae_fwd(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec,
-               aae_drop e1, aae_drop e2, aae_drop d1, aae_drop d2, const aae_step_state* st,
-               float* a1, float* a2, float* zc, float* dd1, float* h2, void* stream);
 /* ae_step backward tail: from dh2 = dL/dh2 to dL/dh1pre; writes the pre-activation gradients of
  * every small layer (g_d2, g_d1, g_z, g_e2, g_h1), consumed by aae_small_wgrad / aae_bag_bwd. */
 int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec, aae_drop e1, aae_drop e2,
@@ -170,20 +130,6 @@ int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec,
                const float* dd1, const float* h2, float* g_d2, float* g_d1, float* g_z, float* g_e2,
                float* g_h1, void* stream);
 
-/* disc_step (aae.py:713-732): encoder tail in eval mode, discriminator on z_real and z_fake,
- * loss, and the backward through the discriminator (the encoder backward the reference computes
- * and discards is skipped).  z_real == NULL -> sampled in-kernel (Philox normal * prior_scale).
- * Outputs: activations and pre-activation gradients for aae_disc_wgrad, loss_sum[0] += the summed
- * per-row loss terms (caller divides by B). */
-int aae_disc_phase(aae_dims d, const float* h1pre, const float* z_real, float prior_scale, const float* enc,
-                   const float* disc, aae_drop r1, aae_drop r2, aae_drop f1, aae_drop f2,
-                   const aae_step_state* st, float* acts /* [B, 2*(C+2H)] */, float* grads /* [B, 2*(2H+1)] */,
-                   double* loss_sum, void* stream);
-/* gen_step (aae.py:734-743): encoder tail in train mode, discriminator, loss, backward through
- * the discriminator into the encoder tail down to dL/dh1pre. */
-int aae_gen_phase(aae_dims d, const float* h1pre, const float* enc, const float* disc, aae_drop e1, aae_drop e2,
-                  aae_drop q1, aae_drop q2, const aae_step_state* st, float* a1, float* a2, float* g_z,
-                  float* g_e2, float* g_h1, double* loss_sum, void* stream);
 
 /* ---- fused step (the engine's default flow): the sparse first layer inside the row-local kernels ----
  * aae_bag describes the batch's CSR rows and W1t; a kernel given a bag with indptr != NULL computes its row
@@ -279,9 +225,6 @@ int aae_dec_out_train_ws(const float* h2, int B, int H, float* Wd3, float* bd3, 
                          int64_t work_floats, void* stream);
 
 /* ---- predict (aae.py:840-870) --------------------------------------------------------------- */
-/* eval-mode forward tail: h1pre -> h2 (no dropout). */
-int aae_predict_tail(aae_dims d, const float* h1pre, const float* cond, const float* enc, const float* dec,
-                     float* h2, void* stream);
 /* out[b, v] = logit or sigmoid(logit) for local items; ldo = row pitch of out in floats. */
 int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const float* bd3, int Vloc,
                        int apply_sigmoid, float* out, int64_t ldo, int impl, void* stream);
@@ -290,7 +233,6 @@ int aae_dec_out_scores(const float* h2, int B, int H, const float* Wd3, const fl
  * remaining local items per row are returned sorted by descending score (ties: lower id first).
  * scores is overwritten (known items are set to -FLT_MAX).  idx_out holds GLOBAL item ids.
  * work: caller-provided scratch of aae_topk_work_bytes(B,k) bytes. */
-int64_t aae_topk_work_bytes(int B, int k);
 int aae_masked_topk(float* scores, int64_t lds, int B, int Vloc, int v_begin, const int32_t* indptr,
                     const int32_t* indices, int k, int32_t* idx_out, float* val_out, void* work, void* stream);
 /* Fused predict + ranking for large vocabularies (K5): reconstruction logits and the masked top-k WITHOUT the
@@ -310,6 +252,10 @@ int aae_predict_topk(const float* h2, int B, int H, const float* Wd3, const floa
 /* k-way merge of per-shard results: cand_val/cand_idx [B, n_cand] -> top k (descending). */
 int aae_topk_merge(const float* cand_val, const int32_t* cand_idx, int B, int n_cand, int k, int32_t* idx_out,
                    float* val_out, void* stream);
+/* The same merge for lists an all-gather left in [world][B][kpad] order (no repacking pass): world * kpad <= 2048;
+ * entries with idx < 0 are padding. */
+int aae_topk_merge_seg(const float* cand_val, const int32_t* cand_idx, int world, int B, int kpad, int k,
+                       int32_t* idx_out, float* val_out, void* stream);
 
 /* ---- item-sharded exchange over NVLink peer memory (multi-GPU) -------------------------------------
  * What one device does inside a single dense GEMM in the reference (aae.py:132-135 X.W1^T, aae.py:176-177/703 the
@@ -388,10 +334,6 @@ int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, cons
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);
 
-/* Copy n 4-byte words with a kernel; src or dst may be pinned (mapped) host memory.  Lets the host-buffer entry live
- * INSIDE the step's CUDA graph (batch in, losses out) without copy-engine hops; the pinned source must stay
- * untouched until the launch that reads it has completed. */
-int aae_copy_words(const void* src, void* dst, int64_t n_words, void* stream);
 /* The same with two source / destination candidates, chosen on the device: index (st->t + bias) & 1.  One captured
  * graph then alternates between two pinned slots (batch in: bias -1 before the step; losses out: bias 0 after it). */
 int aae_copy_words_sel(const void* src0, const void* src1, void* dst0, void* dst1, int64_t n_words,
@@ -406,8 +348,6 @@ int aae_copy_words_sel(const void* src0, const void* src1, void* dst0, void* dst
 int aae_trace_set(uint64_t* buf);
 int aae_trace_slots(void);
 
-/* finalise the three losses on device: out[0]=R/(n_total), out[1]=D/B, out[2]=G/B (float32). */
-int aae_finish_losses(const double* sums, double n_total, int B, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -123,6 +123,26 @@ def check_training(rank, world, dev, exchange, use_graph):
     ref = O.rank_topk(oracle.predict(Xq.toarray()), Xq.toarray(), 10)
     agree = float((top == ref).mean())
     assert agree > 0.98, agree
+    # set-sharded replicas (every rank ranks its slice of the rows against full weights) == item-sharded
+    top2 = model.predict_topk(Xq, 10, shard="sets")
+    assert top2.shape == top.shape and float((top2 == top).mean()) > 0.99, float((top2 == top).mean())
+    # fused large-shard path + segment merge on a bigger vocabulary: item shards vs replicas
+    from aaerec_b200.engine import AAEEngine
+    big = AAEEngine(140000, H, C, rank=rank, world=world, max_batch=128, exchange=exchange)
+    big.init_uniform(5)
+    big.Wd3.mul_(8.0)
+    Xb = synth_sets(96, 140000, 15, seed=3)
+    big.upload_csr(Xb.indptr.astype(np.int32), Xb.indices.astype(np.int32))
+    bi, bv = big.topk(96, 100)
+    rep = big.make_replica(max_batch=128)
+    rep.upload_csr(Xb.indptr.astype(np.int32), Xb.indices.astype(np.int32))
+    ri, rv = rep.topk(96, 100)
+    torch.cuda.synchronize()
+    same = (bi == ri)
+    assert float(same.float().mean()) > 0.99, float(same.float().mean())
+    assert torch.allclose(bv[same], rv[same], rtol=1e-5, atol=1e-6)
+    big.close()
+    del big, rep
     if eng.peer is not None:
         assert eng.peer.error() == 0
     return True
