@@ -8,13 +8,17 @@ from .condition import (ConditionList, ConditionBase, ConcatenationBasedConditio
                         PrecomputedEmbeddingCondition, _check_conditions)
 
 __all__ = ["Recommender", "ConditionList", "ConditionBase", "ConcatenationBasedConditioning",
-           "PrecomputedEmbeddingCondition", "AAERecommender", "AdversarialAutoEncoder", "AutoEncoder", "AAEEngine"]
+           "PrecomputedEmbeddingCondition", "AAERecommender", "AdversarialAutoEncoder", "AutoEncoder", "AAEEngine",
+           "DAERecommender", "DenoisingAutoEncoder"]
 
 
 def __getattr__(name):
     if name in ("AAERecommender", "AdversarialAutoEncoder", "AutoEncoder"):
         from . import aae
         return getattr(aae, name)
+    if name in ("DAERecommender", "DenoisingAutoEncoder"):
+        from . import dae
+        return getattr(dae, name)
     if name == "AAEEngine":
         from .engine import AAEEngine
         return AAEEngine

@@ -424,11 +424,14 @@ class AdversarialAutoEncoder(object):
                     rows = perm[start:end]
                     _, leaves = self._cond_begin([ad.take(c, rows) for c in condition_data], B)
                 eng.gather_batch(start, B)
-                draws = self._draws(B)
-                if draws is not None:
-                    eng.set_rng_draws(B, draws)      # oracle RNG: masks (none when p == 0) and the prior sample
-                eng.train_step(B, draws is not None)
-                self._cond_end(leaves, B)
+                if getattr(self, "_fit_step", None) is not None:     # DenoisingAutoEncoder: corruption + step
+                    self._fit_step(B, leaves)
+                else:
+                    draws = self._draws(B)
+                    if draws is not None:
+                        eng.set_rng_draws(B, draws)      # oracle RNG: masks (none when p == 0) and the prior sample
+                    eng.train_step(B, draws is not None)
+                    self._cond_end(leaves, B)
                 if self.verbose or self.record_losses:
                     cur = self.losses()
                     if self.record_losses:

@@ -125,7 +125,9 @@ class AAEEngine(object):
         # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
         self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "2"))
         # W1t Adam policy: rows outside the batch are swept in G time-blocked groups (1 = dense sweep every step)
-        self.w1_groups = max(1, min(32, int(os.environ.get("AAE_B200_W1_GROUPS", "8"))))
+        # (measured at V=2M: 2.01 / 1.82 / 1.67 ms per step for G = 8 / 16 / 32 -- the group sweep runs exposed behind
+        # the decoder kernel; V=200k: no difference)
+        self.w1_groups = max(1, min(32, int(os.environ.get("AAE_B200_W1_GROUPS", "32"))))
         self.impl = self._pick_impl(impl)
         self.steps_done = 0
         self._launches_per_step = 0
@@ -562,6 +564,22 @@ class AAEEngine(object):
              ptr(self.indptr), ptr(self.indices), ptr(ep["cond"]) if ep["cond"] is not None else None, self.D,
              ptr(self.cond) if ep["cond"] is not None else None, self._stream())
         return B, nnz
+
+    @_on_device
+    def corrupt_batch(self, B, p, noise=None):
+        """Denoising-autoencoder corruption of the batch in the device buffers (dae.py:48-52): every entry is dropped
+        with probability ``p``; ``noise`` = the reference's [B,V] uniform draws (oracle-RNG mode) or None (Philox)."""
+        if getattr(self, "_tmp_batch", None) is None or self._tmp_batch.numel() != self._batch.numel():
+            self._tmp_batch = torch.empty_like(self._batch)
+        self._tmp_batch.copy_(self._batch, non_blocking=True)
+        off = self.indices.data_ptr() - self._batch.data_ptr()
+        nz = None
+        if noise is not None:
+            nz = torch.as_tensor(noise, dtype=torch.float32).to(self.dev).contiguous()
+            assert nz.shape == (B, self.V)
+        call("aae_batch_corrupt", ptr(self._tmp_batch), C.c_void_p(self._tmp_batch.data_ptr() + off), B, self.V,
+             C.c_float(p), ptr(nz), ptr(self.state), ptr(self.indptr), ptr(self.indices), self._stream())
+        self._keep_alive = nz
 
     @_on_device
     def set_cond_rows(self, rows_dev, B):

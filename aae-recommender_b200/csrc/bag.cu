@@ -575,6 +575,97 @@ __global__ void __launch_bounds__(256) batch_gather_copy_kernel(const int64_t* _
 
 }  // namespace aae
 extern "C" {
+} // extern "C"
+namespace aae {
+// ---------------------------------------------------------------------------------------------
+// Input corruption of the denoising autoencoder (dae.py:48-52 zeros_noise: mask = torch.rand(batch.size()) <
+// noise_factor; batch[mask] = 0 -- in place, so the BCE target of dae.py:198-200 is the corrupted batch too): every
+// entry of the batch's CSR rows is dropped with probability p.  noise != NULL: the reference's own [B,V] uniform draws
+// (oracle-RNG mode); NULL: Philox keyed by (seed, step, row, item).  Two kernels: kept-entry counts + scan, then a
+// per-row ballot compaction (column order is preserved).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool corrupt_keep(const float* __restrict__ noise, int V, const aae_step_state* st, int row,
+                                             int item, float p) {
+  if (noise) return !(noise[(size_t)row * V + item] < p);
+  uint4 r = philox4x32(make_uint4((uint32_t)item, st->rng_step, (uint32_t)row, 0xd0e5u),
+                       make_uint2((uint32_t)st->seed, (uint32_t)(st->seed >> 32)));
+  return !(u01(r.x) < p);
+}
+__global__ void __launch_bounds__(1024) batch_corrupt_scan_kernel(const int32_t* __restrict__ in_indptr,
+                                                                  const int32_t* __restrict__ in_indices, int B, int V,
+                                                                  float p, const float* __restrict__ noise,
+                                                                  const aae_step_state* __restrict__ st,
+                                                                  int32_t* __restrict__ out_indptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int r = base + tid;
+    int len = 0;
+    if (r < B)
+      for (int j = in_indptr[r]; j < in_indptr[r + 1]; ++j) len += corrupt_keep(noise, V, st, r, in_indices[j], p) ? 1 : 0;
+    int x = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (r < B) out_indptr[r] = carry + (warp ? warp_tot[warp - 1] : 0) + x - len;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) out_indptr[B] = carry_s;
+}
+__global__ void __launch_bounds__(256) batch_corrupt_copy_kernel(const int32_t* __restrict__ in_indptr,
+                                                                 const int32_t* __restrict__ in_indices, int B, int V,
+                                                                 float p, const float* __restrict__ noise,
+                                                                 const aae_step_state* __restrict__ st,
+                                                                 const int32_t* __restrict__ out_indptr,
+                                                                 int32_t* __restrict__ out_indices) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    const int p0 = in_indptr[r], p1 = in_indptr[r + 1];
+    int o = out_indptr[r];
+    for (int j0 = p0; j0 < p1; j0 += 32) {
+      const int j = j0 + lane;
+      const int item = (j < p1) ? in_indices[j] : 0;
+      const bool keep = (j < p1) && corrupt_keep(noise, V, st, r, item, p);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) out_indices[o + __popc(m & ((1u << lane) - 1u))] = item;
+      o += __popc(m);
+    }
+  }
+}
+}  // namespace aae
+extern "C" {
+int aae_batch_corrupt(const int32_t* in_indptr, const int32_t* in_indices, int B, int V, float p, const float* noise,
+                      const aae_step_state* st, int32_t* out_indptr, int32_t* out_indices, void* stream) {
+  AAE_REQUIRE(in_indptr && in_indices && st && out_indptr && out_indices, "null pointer");
+  AAE_REQUIRE(B > 0 && V > 0 && p >= 0.f && p <= 1.f, "bad argument");
+  AAE_REQUIRE(in_indices != out_indices && in_indptr != out_indptr, "in-place corruption is not supported");
+  batch_corrupt_scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(in_indptr, in_indices, B, V, p, noise, st, out_indptr);
+  const int blocks = std::min(4 * sm_count(), std::max(1, cdiv(B, 8)));
+  batch_corrupt_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in_indptr, in_indices, B, V, p, noise, st, out_indptr,
+                                                                  out_indices);
+  return check_launch("batch_corrupt");
+}
 int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, const int32_t* perm, int64_t row0, int B,
                      int32_t* out_indptr, int32_t* out_indices, const float* cond_all, int D, float* out_cond,
                      void* stream) {

@@ -330,6 +330,14 @@ int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, cons
                      int32_t* out_indptr, int32_t* out_indices, const float* cond_all, int D, float* out_cond,
                      void* stream);
 
+/* ---- denoising autoencoder input corruption ------------------------------------------
+ * Replaces zeros_noise (dae.py:48-52: `mask = torch.rand(batch.size()) < noise_factor; batch[mask] = 0`, in place,
+ * so the BCE target of dae.py:198-200 is the corrupted batch as well): every entry of the batch's CSR rows is dropped
+ * with probability p.  noise != NULL: the reference's own [B,V] uniform draws (oracle-RNG mode); NULL: in-kernel Philox
+ * keyed by (seed, step, row, item).  Column order is preserved; the output must not alias the input. */
+int aae_batch_corrupt(const int32_t* in_indptr, const int32_t* in_indices, int B, int V, float p, const float* noise,
+                      const aae_step_state* st, int32_t* out_indptr, int32_t* out_indices, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);

@@ -329,6 +329,29 @@ class OracleAE(OracleAAE):
         return (self.ae_step(X, cond, rng),)
 
 
+class OracleDAE(OracleAE):
+    """Denoising autoencoder (dae.py:144-314): the plain autoencoder step on a batch whose entries were zeroed IN PLACE
+    with probability noise_factor (dae.py:48-52, 191) -- input and BCE target are both the thinned batch
+    (dae.py:198-200).  ``rng['noise']`` holds the reference's ``torch.rand(batch.size())`` draw."""
+
+    def __init__(self, params, n_code=50, lr=0.001, normalize_inputs=True, noise_factor=0.2):
+        super().__init__(params, n_code=n_code, lr=lr, normalize_inputs=normalize_inputs)
+        self.noise_factor = noise_factor
+
+    def partial_fit(self, X, cond=None, rng=None):
+        X = torch.as_tensor(np.asarray(X), dtype=torch.float32).clone()
+        X[rng["noise"] < self.noise_factor] = 0
+        return super().partial_fit(X, cond, rng)
+
+
+def draw_dae_rng(B, V, n_hidden, n_code, dropout=(.2, .2)):
+    """DAE draws of one step in the reference's order: torch.rand(batch.size()) (dae.py:50), then the four dropout masks
+    of the reconstruction phase."""
+    r = {"noise": torch.rand((B, V))}
+    r.update(draw_step_rng(B, n_hidden, n_code, dropout, adversarial=False))
+    return r
+
+
 def fit_epoch_order(n):
     """Row order of one epoch: ``sklearn.utils.shuffle(X)`` (aae.py:815-817) with
     random_state=None permutes ``arange(n)`` with the global numpy generator."""

@@ -41,9 +41,14 @@ def _state(model):
 
 
 def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0, mean_len=6,
-             store_weights=True, k=10, adversarial=True, model_kwargs=None):
+             store_weights=True, k=10, adversarial=True, model_kwargs=None, dae=False):
     aae = ref.aae
-    cls = aae.AdversarialAutoEncoder if adversarial else aae.AutoEncoder
+    if dae:                     # aaerec/dae.py:144-314: the reference's DenoisingAutoEncoder
+        import aaerec.dae
+        cls = aaerec.dae.DenoisingAutoEncoder
+        adversarial = False
+    else:
+        cls = aae.AdversarialAutoEncoder if adversarial else aae.AutoEncoder
     steps_per_fit = ("ae_step", "disc_step", "gen_step") if adversarial else ("ae_step",)
     X = synth_sets(n, V, mean_len, min_len=2, seed=data_seed)
     conditions = None
@@ -102,7 +107,8 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
     topk = ref.evaluation.argtopk(masked, k)[1]
     out = dict(
         n=n, V=V, H=H, C=C, B=B, epochs=epochs, dropout=np.asarray(dropout, dtype=np.float64),
-        cond_dim=cond_dim, k=k, adversarial=int(adversarial),
+        cond_dim=cond_dim, k=k, adversarial=int(adversarial), dae=int(dae),
+        noise_factor=np.float64((model_kwargs or {}).get("noise_factor", 0.2)),
         normalize_inputs=int((model_kwargs or {}).get("normalize_inputs", True)),
         prior_scale=np.float64((model_kwargs or {}).get("prior_scale") or 0.0),
         gen_lr=np.float64((model_kwargs or {}).get("gen_lr", 0.001)),
@@ -167,6 +173,11 @@ def main():
     # tests/test_gpu_parity.py::test_edge_cases_empty_rows_unnormalized_prior_scale)
     run_case(ref, "aae_opts_unnorm_scale_lrs", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2),
              model_kwargs=dict(normalize_inputs=False, prior_scale=0.5, gen_lr=0.002, reg_lr=0.0005))
+    # DenoisingAutoEncoder (dae.py): zeros-noise corruption in front of the plain autoencoder step
+    run_case(ref, "dae_small_dropout", n=130, V=257, H=24, C=10, B=50, epochs=2, dropout=(.2, .2), dae=True,
+             model_kwargs=dict(noise_factor=0.3))
+    run_case(ref, "dae_h100_cond", n=96, V=520, H=100, C=50, B=32, epochs=2, dropout=(.2, .2), mean_len=8, cond_dim=7,
+             dae=True)
     ranking_case(ref)
 
 

@@ -11,6 +11,7 @@ AAE_CASES = ["aae_small_dropout", "aae_small_nodrop", "aae_small_cond", "aae_h10
              "aae_survey_nodrop", "aae_survey_dropout"]
 AE_CASES = ["ae_small_dropout", "ae_h100_cond"]      # the plain AutoEncoder (AAERecommender(adversarial=False))
 OPTION_CASES = ["aae_opts_unnorm_scale_lrs"]         # non-default normalize_inputs / prior_scale / learning rates
+DAE_CASES = ["dae_small_dropout", "dae_h100_cond"]   # DenoisingAutoEncoder (dae.py)
 
 
 def load_case(name):
@@ -21,6 +22,8 @@ def load_case(name):
     for k in ("n", "V", "H", "C", "B", "epochs", "cond_dim", "k"):
         g[k] = int(g[k])
     g["adversarial"] = bool(int(g.get("adversarial", 1)))
+    g["dae"] = bool(int(g.get("dae", 0)))
+    g["noise_factor"] = float(g.get("noise_factor", 0.2))
     g["normalize_inputs"] = bool(int(g.get("normalize_inputs", 1)))
     g["prior_scale"] = float(g.get("prior_scale", 0.0)) or None
     g["gen_lr"] = float(g.get("gen_lr", 0.001))
@@ -45,6 +48,8 @@ def oracle_replay(g, record_rng=False):
     if adv:
         model = O.OracleAAE(params, n_code=C, gen_lr=g["gen_lr"], reg_lr=g["reg_lr"],
                             normalize_inputs=g["normalize_inputs"])
+    elif g["dae"]:
+        model = O.OracleDAE(params, n_code=C, noise_factor=g["noise_factor"])
     else:
         model = O.OracleAE(params, n_code=C)
     X = g["X"]
@@ -56,7 +61,10 @@ def oracle_replay(g, record_rng=False):
         for s in range(0, X.shape[0], B):
             xb = Xs[s:s + B]
             cb = [cs[s:s + B]] if cs is not None else None
-            rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"], prior_scale=g["prior_scale"], adversarial=adv)
+            if g["dae"]:
+                rng = O.draw_dae_rng(xb.shape[0], V, H, C, g["dropout"])
+            else:
+                rng = O.draw_step_rng(xb.shape[0], H, C, g["dropout"], prior_scale=g["prior_scale"], adversarial=adv)
             losses.append(model.partial_fit(xb.toarray(), cb, rng))
             if record_rng:
                 rngs.append(rng)

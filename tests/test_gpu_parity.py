@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import AAE_CASES, AE_CASES, load_case, group, oracle_replay, rel_err
+from helpers import AAE_CASES, AE_CASES, DAE_CASES, load_case, group, oracle_replay, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -19,6 +19,11 @@ def _make_model(g, impl, **kw):
     conditions = None
     if g["cond_dim"]:
         conditions = ConditionList([("title", PrecomputedEmbeddingCondition(g["cond_dim"]))])
+    if g["dae"]:
+        from aaerec_b200.dae import DenoisingAutoEncoder
+        return DenoisingAutoEncoder(n_hidden=g["H"], n_code=g["C"], batch_size=g["B"], n_epochs=g["epochs"],
+                                    dropout=g["dropout"], noise_factor=g["noise_factor"], conditions=conditions,
+                                    verbose=False, rng="oracle", impl=impl, **kw)
     if not g["adversarial"]:
         return AutoEncoder(n_hidden=g["H"], n_code=g["C"], batch_size=g["B"], n_epochs=g["epochs"],
                            dropout=g["dropout"], conditions=conditions, verbose=False, rng="oracle", impl=impl, **kw)
@@ -28,7 +33,7 @@ def _make_model(g, impl, **kw):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("name", AAE_CASES + AE_CASES)
+@pytest.mark.parametrize("name", AAE_CASES + AE_CASES + DAE_CASES)
 def test_fit_matches_reference_golden(name, impl, capsys):
     """Whole fit loop (shuffle, ragged last batch, three phases, four Adam states) against the
     reference's recorded losses and final weights."""
@@ -245,3 +250,28 @@ def test_large_vocab_properties():
     untouched = np.setdiff1d(np.arange(V), np.unique(X.indices))
     W1_0 = params["enc.lin1.weight"].numpy()
     np.testing.assert_array_equal(sd["enc.lin1.weight"].numpy()[:, untouched[:5000]], W1_0[:, untouched[:5000]])
+
+
+def test_dae_native_corruption_drops_the_right_fraction():
+    """native-RNG corruption (aae_batch_corrupt with in-kernel Philox): each entry of the batch survives with
+    probability 1 - noise_factor, column order is kept, the same (seed, step) gives the same thinned batch."""
+    from aaerec_b200.engine import AAEEngine
+    from aaerec_b200.synth import synth_sets
+    V, B = 20000, 400
+    X = synth_sets(B, V, 30, seed=2)
+    kept = []
+    for rep in range(2):
+        eng = AAEEngine(V, 100, 50, max_batch=B, adversarial=False, seed=5)
+        eng.upload_csr(X.indptr.astype(np.int32), X.indices.astype(np.int32))
+        eng.corrupt_batch(B, 0.3)
+        torch.cuda.synchronize()
+        ip = eng.indptr[: B + 1].cpu().numpy()
+        ii = eng.indices[: int(ip[-1])].cpu().numpy()
+        kept.append((ip.copy(), ii.copy()))
+        frac = ip[-1] / X.nnz
+        assert 0.66 < frac < 0.74, frac
+        for r in range(B):
+            row = ii[ip[r]:ip[r + 1]]
+            full = X.indices[X.indptr[r]:X.indptr[r + 1]]
+            assert np.all(np.diff(row) > 0) and set(row.tolist()) <= set(full.tolist())
+    assert np.array_equal(kept[0][0], kept[1][0]) and np.array_equal(kept[0][1], kept[1][1])

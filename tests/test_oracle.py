@@ -3,11 +3,11 @@
 import numpy as np
 import pytest
 
-from helpers import AAE_CASES, AE_CASES, OPTION_CASES, load_case, group, oracle_replay, rel_err, GOLDEN
+from helpers import AAE_CASES, AE_CASES, OPTION_CASES, DAE_CASES, load_case, group, oracle_replay, rel_err, GOLDEN
 from oracle import aae_oracle as O
 
 
-@pytest.mark.parametrize("name", AAE_CASES + AE_CASES + OPTION_CASES)
+@pytest.mark.parametrize("name", AAE_CASES + AE_CASES + OPTION_CASES + DAE_CASES)
 def test_partial_fit_matches_reference(name):
     g = load_case(name)
     model, losses, _, _ = oracle_replay(g)
