@@ -289,30 +289,33 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finish_kernel(const float* _
     }
     __syncthreads();
     if (RESCORE && fits) {
-      // one THREAD per candidate: the 25 float4 loads of its W row are independent (memory-level parallelism; a warp
-      // per candidate was latency-bound: 514 us for 1000 rows), the h2 row is a shared-memory broadcast, the sum runs
-      // in ascending k (deterministic)
+      // EIGHT LANES per candidate (four candidates per warp pass): the lanes of a group read consecutive float4 of the
+      // candidate's 400-byte Wd3 row, so a warp-wide load touches 4 rows x 128 contiguous bytes (4 wavefronts) instead of
+      // 32 rows x 16 bytes (32 wavefronts: one thread per candidate was bound by the L1 wavefront rate, 329 us for 1000
+      // rows whatever the unrolling); the h2 row is a shared-memory broadcast; fixed reduction order (deterministic).
       const float* hrow = reinterpret_cast<const float*>(off_s + ((nsub + 4) & ~3));
+      const float4* h4 = reinterpret_cast<const float4*>(hrow);
       const int H4 = ra.H >> 2;
-      for (int c = tid; c < total; c += FIN_THREADS) {
+      const int sub = lane >> 3, l8 = lane & 7;
+      for (int c0 = warp * 4; c0 < total; c0 += (FIN_THREADS / 32) * 4) {
+        const int c = c0 + sub;
         const size_t o = (size_t)row * cap_out + c;
-        if (out_val[o] == -FLT_MAX) continue;                       // a known item: stays at the bottom
-        const int item = out_idx[o] - ra.v_begin;
-        const float4* wrow = reinterpret_cast<const float4*>(ra.Wd3 + (size_t)item * ra.H);
-        float a0 = 0.f, a1 = 0.f;
-        int c4 = 0;
-        for (; c4 + 1 < H4; c4 += 2) {
-          const float4 w0 = __ldg(wrow + c4), w1 = __ldg(wrow + c4 + 1);
-          const float4 h0 = reinterpret_cast<const float4*>(hrow)[c4], h1 = reinterpret_cast<const float4*>(hrow)[c4 + 1];
-          a0 = fmaf(w0.x, h0.x, a0); a0 = fmaf(w0.y, h0.y, a0); a0 = fmaf(w0.z, h0.z, a0); a0 = fmaf(w0.w, h0.w, a0);
-          a1 = fmaf(w1.x, h1.x, a1); a1 = fmaf(w1.y, h1.y, a1); a1 = fmaf(w1.z, h1.z, a1); a1 = fmaf(w1.w, h1.w, a1);
+        const bool live = c < total && out_val[o] != -FLT_MAX;       // -FLT_MAX: a known item, stays at the bottom
+        float acc = 0.f;
+        int item = 0;
+        if (live) {
+          item = out_idx[o] - ra.v_begin;
+          const float4* wrow = reinterpret_cast<const float4*>(ra.Wd3 + (size_t)item * ra.H);
+          for (int c4 = l8; c4 < H4; c4 += 8) {
+            const float4 w = __ldg(wrow + c4);
+            const float4 h = h4[c4];
+            acc = fmaf(w.x, h.x, acc); acc = fmaf(w.y, h.y, acc); acc = fmaf(w.z, h.z, acc); acc = fmaf(w.w, h.w, acc);
+          }
         }
-        if (c4 < H4) {
-          const float4 w0 = __ldg(wrow + c4);
-          const float4 h0 = reinterpret_cast<const float4*>(hrow)[c4];
-          a0 = fmaf(w0.x, h0.x, a0); a0 = fmaf(w0.y, h0.y, a0); a0 = fmaf(w0.z, h0.z, a0); a0 = fmaf(w0.w, h0.w, a0);
-        }
-        out_val[o] = (a0 + a1) + __ldg(ra.bd3 + item);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (live && l8 == 0) out_val[o] = acc + __ldg(ra.bd3 + item);
       }
     }
     if (tid == 0) {
