@@ -11,7 +11,8 @@
 //   * the survivors are re-scored exactly in fp32 and ranked (topk.cu), and a row whose k-th exact score does not
 //     clear tau_b is reported in n_bad (the caller falls back to the exact dense path): the result is exact.
 // Feed: W' = [Wd3 | bd3 | 0] is kept as a padded [Vloc, 104] fp32 matrix (aae_pad_weights; 416-byte rows) described by
-// a 2-D tensor map (box 32 floats x 128/CY rows, SWIZZLE_128B, K zero-filled to 128 by TMA out-of-bounds handling).  A
+// two 2-D tensor maps (three boxes of 32 floats x 128/CY rows, SWIZZLE_128B, for k = 0..95 and one box of 8 floats,
+// SWIZZLE_32B, for k = 96..103: a 52 KB stage holds K = 104 exactly, so four stages fit).  A
 // cluster of CY CTAs (CY row chunks of 128 query rows) shares every tile: CTA r loads rows [r*128/CY, (r+1)*128/CY) of
 // each of the 4 K-boxes and MULTICASTS them into the same stage of all CY CTAs (cp.async.bulk.tensor ...
 // .multicast::cluster), so a tile crosses L2 -> SM once per cluster instead of once per CTA.  Stage hand-over: full[s]
@@ -37,11 +38,13 @@ namespace cg = cooperative_groups;
 constexpr int BM = 128;                 // query rows per chunk (MMA M)
 constexpr int PN = 128;                 // items per tile (MMA N)
 constexpr int KP = 104;                 // padded K of W' rows (n_hidden 100 + bias + 3 zeros): 13 MMA K-steps
-constexpr int KBOX = 32;                // floats per TMA box row (128 bytes: one SWIZZLE_128B atom row)
-constexpr int NBOX = 4;                 // K boxes per tile (K zero-filled to 128)
+constexpr int KBOX = 32;                // floats per row of a big TMA box (128 bytes: one SWIZZLE_128B atom row)
+constexpr int NBOX = 3;                 // big K boxes per tile (k = 0..95)
+constexpr int KTAIL = KP - NBOX * KBOX; // 8 floats (k = 96..103): one SWIZZLE_32B box, exactly one MMA K-step
 constexpr int BOX_BYTES = PN * KBOX * 4;               // 16 KB
-constexpr int STAGE_BYTES = NBOX * BOX_BYTES;          // 64 KB
-constexpr int NSTAGE = 3;
+constexpr int TAIL_BYTES = PN * KTAIL * 4;             // 4 KB
+constexpr int STAGE_BYTES = NBOX * BOX_BYTES + TAIL_BYTES;   // 52 KB: K = 104 exactly, no zero-filled padding in smem
+constexpr int NSTAGE = 4;
 constexpr int NWE = 16;                 // epilogue warps
 constexpr int NT = 32 * (NWE + 2);      // + MMA warp + TMA warp
 constexpr int CW = PN / 4;              // accumulator columns per epilogue thread
@@ -93,6 +96,16 @@ __device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, int 
           smem_u32(dst)),
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
+}
+// K-major operand, SWIZZLE_32B (layout type 6): rows of 32 bytes, SBO = 256 bytes between 8-row groups
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
 }
 // K-major operand, SWIZZLE_128B (layout type 2), SBO = 1024 bytes between 8-row groups, Blackwell descriptor version
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -156,7 +169,9 @@ struct Sel2Args {
 };
 
 template <int CY>
-__global__ void __launch_bounds__(NT, 1) dec_out_select2_kernel(const __grid_constant__ CUtensorMap wmap, Sel2Args a) {
+__global__ void __launch_bounds__(NT, 1) dec_out_select2_kernel(const __grid_constant__ CUtensorMap wmap,
+                                                                const __grid_constant__ CUtensorMap wmap_tail,
+                                                                Sel2Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stages: align the dynamic window by hand (the launcher adds the slack)
   unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -190,6 +205,7 @@ __global__ void __launch_bounds__(NT, 1) dec_out_select2_kernel(const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_tail) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -244,6 +260,9 @@ __global__ void __launch_bounds__(NT, 1) dec_out_select2_kernel(const __grid_con
             if (CY > 1) tma_load_mc(dst + j * BOX_BYTES, &wmap, j * KBOX, row0, &bar_full[s], kMask);
             else tma_load(dst + j * BOX_BYTES, &wmap, j * KBOX, row0, &bar_full[s]);
           }
+          unsigned char* dst_t = stages + (size_t)s * STAGE_BYTES + NBOX * BOX_BYTES + (size_t)rank * (PN / CY) * (KTAIL * 4);
+          if (CY > 1) tma_load_mc(dst_t, &wmap_tail, NBOX * KBOX, row0, &bar_full[s], kMask);
+          else tma_load(dst_t, &wmap_tail, NBOX * KBOX, row0, &bar_full[s]);
         }
       }
       __syncwarp();
@@ -258,7 +277,9 @@ __global__ void __launch_bounds__(NT, 1) dec_out_select2_kernel(const __grid_con
           const uint32_t sbase = smem_u32(stages + (size_t)s * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < KP / 8; ++kk) {
-            const uint64_t bdesc = make_desc_sw128(sbase + (uint32_t)(kk >> 2) * BOX_BYTES + (uint32_t)(kk & 3) * 32u);
+            const uint64_t bdesc = (kk < NBOX * 4)
+                ? make_desc_sw128(sbase + (uint32_t)(kk >> 2) * BOX_BYTES + (uint32_t)(kk & 3) * 32u)
+                : make_desc_sw32(sbase + (uint32_t)NBOX * BOX_BYTES);
             mma_tf32_ts(tmem + T_ACC + (uint32_t)(acc * PN), tmem + T_A + 8 * kk, bdesc, idesc, kk ? 1u : 0u);
           }
           mma_commit(&bar_acc_full[acc]);
@@ -358,15 +379,15 @@ __global__ void __launch_bounds__(256) pad_weights_kernel(const float* __restric
 static std::mutex g_map_mutex;
 static std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
 
-static int get_tensor_map(const float* Wp, int Vloc, int cy, CUtensorMap* out) {
+static int get_tensor_map(const float* Wp, int Vloc, int cy, bool tail, CUtensorMap* out) {
   std::lock_guard<std::mutex> lock(g_map_mutex);
-  auto key = std::make_tuple((const void*)Wp, Vloc, cy);
+  auto key = std::make_tuple((const void*)Wp, Vloc, tail ? -cy : cy);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return AAE_OK; }
   CUtensorMap m;
   const cuuint64_t gdim[2] = {(cuuint64_t)s2::KP, (cuuint64_t)Vloc};
   const cuuint64_t gstride[1] = {(cuuint64_t)s2::KP * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)s2::KBOX, (cuuint32_t)(s2::PN / cy)};
+  const cuuint32_t box[2] = {(cuuint32_t)(tail ? s2::KTAIL : s2::KBOX), (cuuint32_t)(s2::PN / cy)};
   const cuuint32_t estr[2] = {1, 1};
   // The driver entry point is looked up through the runtime (cudaGetDriverEntryPoint), so the library has no link-time
   // dependency on libcuda.so.1 and still loads on a machine without a driver (CPU-side ABI tests, the build check).
@@ -386,8 +407,8 @@ static int get_tensor_map(const float* Wp, int Vloc, int cy, CUtensorMap* out) {
     encode = reinterpret_cast<EncodeFn>(fn);
   }
   CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, tail ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return AAE_E_CUDA;
@@ -448,7 +469,7 @@ void dec_out_select2_grid(int B, int n_sel, int* gx, int* gy) {
 }
 
 template <int CY>
-static int launch_select2(const CUtensorMap& map, const s2::Sel2Args& a, cudaStream_t s) {
+static int launch_select2(const CUtensorMap& map, const CUtensorMap& map_tail, const s2::Sel2Args& a, cudaStream_t s) {
   int gx = 1, gy = 1;
   int rc = grid_for<CY>(a.B, a.n_sel, &gx, &gy);
   if (rc) return rc;
@@ -463,7 +484,7 @@ static int launch_select2(const CUtensorMap& map, const s2::Sel2Args& a, cudaStr
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CY; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, s2::dec_out_select2_kernel<CY>, map, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, s2::dec_out_select2_kernel<CY>, map, map_tail, a);
   if (e != cudaSuccess) { set_error("dec_out_select2<%d>: %s", CY, cudaGetErrorString(e)); return AAE_E_CUDA; }
   return check_launch("dec_out_select2");
 }
@@ -474,18 +495,20 @@ int dec_out_select2(const float* h2, int B, int H, const float* Wp, int Vloc, in
                     int32_t* cand_idx, int cap_sub, cudaStream_t s) {
   if (H + 1 > s2::KP) { set_error("dec_out_select2: n_hidden %d > %d", H, s2::KP - 1); return AAE_E_UNSUPPORTED; }
   const int cy = pick_cy(B);
-  CUtensorMap map;
-  int rc = get_tensor_map(Wp, Vloc, cy, &map);
+  CUtensorMap map, map_tail;
+  int rc = get_tensor_map(Wp, Vloc, cy, false, &map);
+  if (rc) return rc;
+  rc = get_tensor_map(Wp, Vloc, cy, true, &map_tail);
   if (rc) return rc;
   s2::Sel2Args a;
   a.h2 = h2; a.B = B; a.H = H; a.Vloc = Vloc; a.v_begin = v_begin; a.tile_stride = tile_stride; a.n_sel = n_sel;
   a.filter = filter; a.out = out; a.ldo = ldo; a.out_by_visit = out_by_visit; a.tau = tau; a.cnt = cnt;
   a.cand_idx = cand_idx; a.cap_sub = cap_sub;
   switch (cy) {
-    case 8: return launch_select2<8>(map, a, s);
-    case 4: return launch_select2<4>(map, a, s);
-    case 2: return launch_select2<2>(map, a, s);
-    default: return launch_select2<1>(map, a, s);
+    case 8: return launch_select2<8>(map, map_tail, a, s);
+    case 4: return launch_select2<4>(map, map_tail, a, s);
+    case 2: return launch_select2<2>(map, map_tail, a, s);
+    default: return launch_select2<1>(map, map_tail, a, s);
   }
 }
 
