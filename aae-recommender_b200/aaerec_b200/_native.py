@@ -95,6 +95,7 @@ _SIGS = {
     "aae_peer_free": (I, [P]),
     "aae_peer_allreduce": (I, [AaePeers, I, P, I, P, I, I64, P]),
     "aae_peer_error": (I, [P, C.POINTER(I)]),
+    "aae_peer_bag_allreduce": (I, [AaePeers, I, P, P, I, P, P, I, I, I, I, P, I64, P]),
     "aae_trace_set": (I, [P]),
     "aae_trace_slots": (I, []),
 }

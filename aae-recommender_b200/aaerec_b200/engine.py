@@ -683,6 +683,20 @@ class AAEEngine(object):
         except Exception:   # noqa: BLE001 -- interpreter shutdown
             pass
 
+    def _gather_exchange(self, B, out, exchange):
+        """h1pre of an item-sharded engine: local partial sums of X.W1^T + all-reduce + bias.  One fused kernel over
+        the peer buffers when the batch fits it (<= 256 rows, n_hidden % 4 == 0), else aae_bag_fwd + the exchange."""
+        s = self._stream
+        if self.peer is not None and B <= 256 and self.H % 4 == 0 and B * self.H <= self.peer.n_max \
+                and os.environ.get("AAE_B200_FUSED_GATHER", "1") != "0":
+            call("aae_peer_bag_allreduce", self.peer.peers, exchange, ptr(self.indptr), ptr(self.indices), B,
+                 ptr(self.W1t), ptr(self.enc), self.H, self.normalize, self.v_begin, self.v_end, ptr(out),
+                 C.c_int64(self.peer.n_max), s())
+            return
+        call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H, self.normalize,
+             self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(out), s())
+        self._allreduce(out[:B], exchange)
+
     def launches_per_step(self):
         """Kernels of ours launched by one train_step (counted while enqueueing; a graph replay
         launches the same kernel nodes)."""
@@ -739,9 +753,7 @@ class AAEEngine(object):
              ptr(self.W1_m1), ptr(self.W1_v1), ptr(self.W1_m2), ptr(self.W1_v2), ptr(self.w1_last), H, st,
              ptr(self.ktab), s())
         if not fused:
-            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
-                 lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre), s())
-            self._allreduce(self.h1pre[:B], 0)
+            self._gather_exchange(B, self.h1pre, 0)
         call("aae_ae_fwd_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec), dr["ae_e1"],
              dr["ae_e2"], dr["ae_d1"], dr["ae_d2"], st, ptr(self.a1), ptr(self.a2), ptr(self.zc), ptr(self.dd1),
              ptr(self.h2), ptr(self.dh2), s())
@@ -809,9 +821,7 @@ class AAEEngine(object):
         H, st = self.H, ptr(self.state)
         lo, hi = self.v_begin, self.v_end
         if not fused:
-            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), H, self.normalize,
-                 lo, hi, 1 if self.rank == 0 else 0, ptr(self.h1pre2), s())
-            self._allreduce(self.h1pre2[:B], 2)
+            self._gather_exchange(B, self.h1pre2, 2)
         call("aae_disc_phase_bag", dims, bag, ptr(self.h1pre2), ptr(self.z_real) if injected else None,
              C.c_float(self.prior_scale), ptr(self.enc), ptr(self.disc), dr["disc_r1"], dr["disc_r2"], dr["disc_f1"],
              dr["disc_f2"], st, ptr(self.disc_acts), ptr(self.disc_grads), ptr(self.loss_sums[1:]), s())
@@ -993,9 +1003,7 @@ class AAEEngine(object):
             bag = N.bag(self.indptr, self.indices, self.W1t, self.normalize, self.v_begin, self.v_end)
         else:
             bag = N.bag()
-            call("aae_bag_fwd", ptr(self.indptr), ptr(self.indices), B, ptr(self.W1t), ptr(self.enc), self.H,
-                 self.normalize, self.v_begin, self.v_end, 1 if self.rank == 0 else 0, ptr(self.h1pre), self._stream())
-            self._allreduce(self.h1pre[:B], 3)
+            self._gather_exchange(B, self.h1pre, 3)
         call("aae_predict_tail_bag", dims, bag, ptr(self.h1pre), ptr(self.cond), ptr(self.enc), ptr(self.dec),
              ptr(self.h2), self._stream())
         return self.h2[:B]

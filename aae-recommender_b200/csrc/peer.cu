@@ -155,6 +155,105 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(aae_peers P, int e,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Encoder first layer of an item shard FUSED with its exchange (one launch instead of aae_bag_fwd + aae_peer_allreduce):
+// block b gathers the partial sums of batch rows [8b, 8b+8) from the local W1t rows (one warp per row, as bag_fwd_kernel)
+// straight into its exchange slot, signals, waits for the peers' block b, sums the rows over the ranks in rank order and
+// adds the bias -- out[b,:] = b1 + sum_r partial_r[b,:], bit-identical on every rank.  n_hidden % 4 == 0, B <= 8 * 32.
+// ---------------------------------------------------------------------------------------------
+constexpr int PXB_ROWS = 8;
+__global__ void __launch_bounds__(256) peer_bag_allreduce_kernel(aae_peers P, int e, const int32_t* __restrict__ indptr,
+                                                                 const int32_t* __restrict__ indices, int B,
+                                                                 const float* __restrict__ W1t,
+                                                                 const float* __restrict__ b1, int H, int normalize,
+                                                                 int v_begin, int v_end, float* __restrict__ out,
+                                                                 int64_t n_max, long long spin_cycles) {
+  PxHeader* my = reinterpret_cast<PxHeader*>(P.base[P.rank]);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x, nb = gridDim.x;
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(&my->seq[e]) + 1u;
+  const int par = (int)(seq & 1u);
+  float* mine = reinterpret_cast<float*>(px_slot(P.base[P.rank], e, par, n_max));
+  const int row = b * PXB_ROWS + warp;
+  const int H4 = H >> 2;
+  __shared__ int timed_out;
+  if (tid == 0) timed_out = 0;
+  // 1. gather + publish
+  if (row < B) {
+    const int s = indptr[row], en = indptr[row + 1];
+    const float scale = normalize ? 1.0f / fmaxf((float)(en - s), 1e-12f) : 1.0f;
+    for (int c = lane; c < H4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int j = s;
+      for (; j + 4 <= en; j += 4) {
+        const int i0 = indices[j], i1 = indices[j + 1], i2 = indices[j + 2], i3 = indices[j + 3];
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+        if (i0 >= v_begin && i0 < v_end) r0 = __ldg(reinterpret_cast<const float4*>(W1t + (size_t)(i0 - v_begin) * H) + c);
+        if (i1 >= v_begin && i1 < v_end) r1 = __ldg(reinterpret_cast<const float4*>(W1t + (size_t)(i1 - v_begin) * H) + c);
+        if (i2 >= v_begin && i2 < v_end) r2 = __ldg(reinterpret_cast<const float4*>(W1t + (size_t)(i2 - v_begin) * H) + c);
+        if (i3 >= v_begin && i3 < v_end) r3 = __ldg(reinterpret_cast<const float4*>(W1t + (size_t)(i3 - v_begin) * H) + c);
+        acc.x += (r0.x + r1.x) + (r2.x + r3.x);
+        acc.y += (r0.y + r1.y) + (r2.y + r3.y);
+        acc.z += (r0.z + r1.z) + (r2.z + r3.z);
+        acc.w += (r0.w + r1.w) + (r2.w + r3.w);
+      }
+      for (; j < en; ++j) {
+        const int i0 = indices[j];
+        if (i0 >= v_begin && i0 < v_end) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(W1t + (size_t)(i0 - v_begin) * H) + c);
+          acc.x += r0.x; acc.y += r0.y; acc.z += r0.z; acc.w += r0.w;
+        }
+      }
+      acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+      reinterpret_cast<float4*>(mine + (size_t)row * H)[c] = acc;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. signal, 3. wait (one thread per peer)
+  if (tid < P.world && tid != P.rank) {
+    PxHeader* peer = reinterpret_cast<PxHeader*>(P.base[tid]);
+    st_release_sys(&peer->flags[e][b][P.rank], seq);
+    const uint32_t* f = &my->flags[e][b][tid];
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+      if (clock64() - t0 > spin_cycles) {
+        my->err = 1u;
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  // 4. reduce the block's rows in rank order, add the bias
+  if (row < B) {
+    for (int c = lane; c < H4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < P.world; ++r) {
+        const float4* src = reinterpret_cast<const float4*>(px_slot(P.base[r], e, par, n_max)) + (size_t)row * H4 + c;
+        const float4 x = (r == P.rank) ? *src : ld_volatile_f4(src);
+        if (r == 0) acc = x;
+        else { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+      }
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b1) + c);
+      acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+      if (timed_out) acc.x = acc.y = acc.z = acc.w = __int_as_float(0x7fc00000);
+      reinterpret_cast<float4*>(out + (size_t)row * H)[c] = acc;
+    }
+  }
+  // 5. the last block to finish advances the sequence number
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const uint32_t done = atomicAdd(&my->ticket[e], 1u);
+    if (done == (uint32_t)nb - 1u) {
+      my->ticket[e] = 0u;
+      *reinterpret_cast<volatile uint32_t*>(&my->seq[e]) = seq;
+    }
+  }
+}
+
 }  // namespace aae
 
 using namespace aae;
@@ -222,6 +321,22 @@ int aae_peer_error(const void* base, int* err_host) {
   if (e != cudaSuccess) { set_error("aae_peer_error: %s", cudaGetErrorString(e)); return AAE_E_CUDA; }
   *err_host = (int)v;
   return AAE_OK;
+}
+
+int aae_peer_bag_allreduce(aae_peers peers, int exchange, const int32_t* indptr, const int32_t* indices, int B,
+                           const float* W1t, const float* b1, int H, int normalize, int v_begin, int v_end, float* out,
+                           int64_t n_max, void* stream) {
+  AAE_REQUIRE(peers.world >= 2 && peers.world <= AAE_PEER_MAX_WORLD, "world outside [2, AAE_PEER_MAX_WORLD]");
+  AAE_REQUIRE(peers.rank >= 0 && peers.rank < peers.world, "bad rank");
+  AAE_REQUIRE(exchange >= 0 && exchange < AAE_PEER_EXCHANGES, "bad exchange id");
+  AAE_REQUIRE(indptr && indices && W1t && b1 && out, "null pointer");
+  AAE_REQUIRE(B > 0 && B <= PXB_ROWS * PX_MAX_BLOCKS && (H & 3) == 0 && (int64_t)B * H <= n_max,
+              "fused gather + exchange handles batches of up to 256 rows, n_hidden % 4 == 0");
+  for (int r = 0; r < peers.world; ++r) AAE_REQUIRE(peers.base[r], "peer buffer not mapped");
+  const int blocks = cdiv(B, PXB_ROWS);
+  peer_bag_allreduce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(peers, exchange, indptr, indices, B, W1t, b1, H,
+                                                                  normalize, v_begin, v_end, out, n_max, 40000000000LL);
+  return check_launch("peer_bag_allreduce");
 }
 
 int aae_peer_allreduce(aae_peers peers, int exchange, float* data, int n, double* extra, int n_extra, int64_t n_max,

@@ -283,6 +283,12 @@ int aae_peer_free(void* base);
 int aae_peer_allreduce(aae_peers peers, int exchange, float* data, int n, double* extra, int n_extra, int64_t n_max,
                        void* stream);
 int aae_peer_error(const void* base, int* err_host);
+/* aae_bag_fwd of an item shard FUSED with its exchange (one launch): out[b,:] = b1 + sum over the ranks of the partial
+ * sums of X.W1^T over each rank's item range (aae.py:132-135 on item shards), bit-identical on every rank.  Batches of
+ * up to 256 rows, n_hidden % 4 == 0 (otherwise aae_bag_fwd + aae_peer_allreduce). */
+int aae_peer_bag_allreduce(aae_peers peers, int exchange, const int32_t* indptr, const int32_t* indices, int B,
+                           const float* W1t, const float* b1, int H, int normalize, int v_begin, int v_end, float* out,
+                           int64_t n_max, void* stream);
 
 /* Self-test of the tcgen05 operand views used by the tensor-core kernel (one GEMM, one CTA):
  * mode 1: D[128,32] = A[128,104].Bm[32,104]^T; mode 2: D[128,112] = A[128,32].Bm[32,112];
