@@ -29,7 +29,7 @@
 #define TC_WAIT_SLEEP_NS 40
 #endif
 #ifndef TC2_CW
-#define TC2_CW 8    // accumulator columns per epilogue thread of the pipelined kernel (8 or 16; measured: 8 -> 163 us, 16 -> 222 us)
+#define TC2_CW 16   // accumulator columns per epilogue thread of the pipelined kernel (two roles of 8 warps each)
 #endif
 #ifndef TC2_G1_FIRST
 #define TC2_G1_FIRST 1
@@ -55,6 +55,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
   return d;
+}
+// the same with a swizzle mode in bits [61,64) (1 = SWIZZLE_128B_BASE32B: the layout of MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return make_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor for kind::tf32, fp32 accumulate
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -808,26 +812,44 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
+// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 #ifndef K3_PF_MV
 #define K3_PF_MV 1
 #endif
 #ifndef K3_PF_AHEAD
 #define K3_PF_AHEAD 4
 #endif
+#ifdef K3X_TRACE
+// timing experiment only: clock64() of CTA 0 at the synchronisation points of tile iterations 8..39
+static __device__ long long k3x_tr[32 * 16];
+#define K3X_MARK(it, slot) do { if (blockIdx.x == 0 && (it) >= 8 && (it) < 40 && (threadIdx.x & 31) == 0) k3x_tr[((it) - 8) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define K3X_MARK(it, slot) do { } while (0)
+#endif
 // CWT = accumulator columns per epilogue thread (8: 16 epilogue warps, 16: 8 fatter warps with twice the
 // instruction-level parallelism and half the per-warp fixed work)
 template <int CWT> struct Tc2Cfg {
   static constexpr int NPART = TN / CWT;          // column parts per TMEM lane quarter
-  static constexpr int NWE = 4 * NPART;           // epilogue warps
-  static constexpr int NTT = 32 * NWE + 32;       // + the MMA / TMA warp
-  static constexpr int WCHT = 32 / NWE;           // W' chunks per thread
+  static constexpr int NWE = 4 * NPART;           // warps per epilogue role (E1 / loader warps, E2 warps)
+  static constexpr int NTT = 32 * NWE + 32;       // one role + the MMA warp (barriers 1, 3) or the copy warp (barrier 2)
+  static constexpr int NTHR = 64 * NWE + 64;      // E1 warps | E2 warps | MMA warp | copy warp
+  static constexpr int WCHT = 32 / NWE;           // W' chunks per loader thread
+  static_assert(NTHR <= 1024, "two epilogue roles of 4*TN/CWT warps each: CWT = 16");
 };
 // MODE (batches larger than one row chunk are walked chunk by chunk, one launch each; the weight gradient of the
 // chunks is summed in a global scratch [Vloc,H] + [Vloc] before the one Adam update):
 //   0  single chunk: gradient -> Adam                     1  first chunk:  gW  = dW'   (no Adam, no W/m/v stage)
 //   2  middle chunk: gW += dW'                            3  last chunk:   Adam with gW + dW'
 template <int SPLIT, int HC, int CWT, int MODE>
-__global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
+__global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel(
     const float* __restrict__ h2, int B, int Hrt, float* __restrict__ Wd3, float* __restrict__ bd3,
     float* __restrict__ mW, float* __restrict__ vW, float* __restrict__ mb, float* __restrict__ vb, int v_begin,
     int Vloc, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, float inv_n,
@@ -837,8 +859,11 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_g1, bar_g23;   // completion of G1(i) / of G3(i-1)+G2(i-1)
   __shared__ uint64_t bar_stage;         // E2 stage (W/m/v rows of one tile) filled by TMA
+  __shared__ uint64_t bar_dw[2];         // G3(i) complete: dW'^T buffer i&1 may be read by the E2 warps
+  __shared__ uint64_t bar_dwfree[2];     // the E2 warps have read dW'^T buffer i&1 (one arrival per warp)
   __shared__ uint32_t tmem_base_s;
   constexpr int NPART = Tc2Cfg<CWT>::NPART, NWE = Tc2Cfg<CWT>::NWE, NTT = Tc2Cfg<CWT>::NTT, WCHT = Tc2Cfg<CWT>::WCHT;
+  constexpr int NTHR = Tc2Cfg<CWT>::NTHR;
   __shared__ float red[NWE];
   const int H = HC ? HC : Hrt;
   const Geom g = make_geom(H);
@@ -866,44 +891,163 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
   const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
 
   trace_mark(TR_K3, 0);
-  if (warp == NWE) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (warp == 0) K3X_MARK(39, 0);
+  if (warp == 2 * NWE) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_g1, 1);
     mbar_init(&bar_g23, 1);
     mbar_init(&bar_stage, 1);
+    mbar_init(&bar_dw[0], 1);
+    mbar_init(&bar_dw[1], 1);
+    mbar_init(&bar_dwfree[0], NWE);
+    mbar_init(&bar_dwfree[1], NWE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int q = tid; q < smem_total / 16; q += NTT) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
-  __syncthreads();
-  {
-    const int ncg = g.Kp / 4;
-    for (int q = tid; q < BK * ncg; q += NTT) {
-      int r = q / ncg, cg = q - r * ncg;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  // The loads of the prologue are issued in batches (all loads of a batch before their first use): issued one by one
+  // they cost a global-memory round trip each, 12 us of every launch before the first tile.
+  constexpr int HB_BATCH = 5;
+  const int ncg0 = g.Kp / 4;
+  float4 hbx[HB_BATCH];
+#pragma unroll
+  for (int u = 0; u < HB_BATCH; ++u) {                       // first batch of the Hb fill: in flight during the zero fill
+    const int q = tid + u * NTHR;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < BK * ncg0) {
+      const int r = q / ncg0, c = (q - r * ncg0) * 4;
       if (r < B) {
-        int c = cg * 4;
         if (c + 3 < H) x = *reinterpret_cast<const float4*>(h2 + (size_t)r * H + c);
         else if (c == H) x.x = 1.0f;
       }
-      store_split4(hb_hi, hb_lo, r, cg, g.hb_sbo, x, with_lo);
     }
+    hbx[u] = x;
+  }
+  for (int q = tid; q < smem_total / 16; q += NTHR) reinterpret_cast<float4*>(smem)[q] = make_float4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) K3X_MARK(39, 1);
+  if (warp < 2 * NWE) {
+    // H2'^T -> TMEM (lane = hidden unit, column = batch row), BK columns; all epilogue warps, two 8-column chunks at a time
+    const int q4 = warp & 3, part = warp >> 2;               // TMEM lane quarter; chunk phase
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int k = q4 * 32 + lane;
+    constexpr int NP4 = 2 * NPART;
+    for (int c0 = part; c0 < BK / 8; c0 += 2 * NP4) {
+      float x[16];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * NP4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int b = c * 8 + j;
+          float v = 0.f;
+          if (c < BK / 8 && b < B) v = (k < H) ? h2[(size_t)b * H + k] : (k == H ? 1.0f : 0.f);
+          x[u * 8 + j] = v;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * NP4;
+        if (c < BK / 8) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hi[j] = tf32_hi(x[u * 8 + j]);
+            lo[j] = x[u * 8 + j] - hi[j];
+          }
+          tmem_st8(lane_addr + T2_HTH + c * 8, hi);
+          if (with_lo) tmem_st8(lane_addr + T2_HTL + c * 8, lo);
+        }
+      }
+    }
+    tmem_st_wait();
+  }
+#pragma unroll
+  for (int u = 0; u < HB_BATCH; ++u) {
+    const int q = tid + u * NTHR;
+    if (q < BK * ncg0) {
+      const int r = q / ncg0, cg = q - r * ncg0;
+      store_split4(hb_hi, hb_lo, r, cg, g.hb_sbo, hbx[u], with_lo);
+    }
+  }
+  for (int q = tid + HB_BATCH * NTHR; q < BK * ncg0; q += NTHR) {      // shapes beyond HB_BATCH chunks per thread
+    int r = q / ncg0, cg = q - r * ncg0;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < B) {
+      int c = cg * 4;
+      if (c + 3 < H) x = *reinterpret_cast<const float4*>(h2 + (size_t)r * H + c);
+      else if (c == H) x.x = 1.0f;
+    }
+    store_split4(hb_hi, hb_lo, r, cg, g.hb_sbo, x, with_lo);
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
   const uint32_t idesc_g1 = make_idesc(BM, TN, 0, 0);
   const uint32_t idesc_g2 = make_idesc(BM, g.Np, 0, 0);
+  if (warp == 0) K3X_MARK(39, 2);
 
-  if (warp == NWE) {
-    // ================= MMA issuer + TMA producer =================
+  if (warp == 2 * NWE) {
+    // ================= MMA issuer =================
+    // Two hand-overs per tile: barrier 3 = W'(it) is in Wb -> G1(it) is issued at once, one tile ahead of the backward
+    // GEMMs, so the tensor pipe has work while the epilogue warps are busy with the operand stores of tile it-1;
+    // barrier 1 = dZ(it-1), Dtb and Wtb are stored -> G3(it-1), G2(it-1).
     const SmemOp op_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE);
     const SmemOp op_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
+    // (MN-major B operands -- SWIZZLE_128B_BASE32B, probed in aae_tc_selftest modes 6/7 -- would let Wtb / Dtb be written
+    // as 16-byte vectors instead of transposing scalars, but the tensor pipe reads them ~50 % slower: measured, dropped)
     const SmemOp op_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
     const SmemOp op_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
+    const uint32_t idesc_g3 = idesc_g1, idesc_g2n = idesc_g2;
     const int ksteps_b = BK / 8;
-    // tile j of this CTA -> E2 stage (a ragged last tile is read from global memory by E2 instead)
+    uint32_t ph_f0 = 0, ph_f1 = 0;
+    for (int it = 0; it <= n_my; ++it) {
+      // K3X_* (here and below): timing experiments only (scripts/k3_experiments.sh); never defined in the product build
+      if (it < n_my) {
+        named_bar_sync(3, NTT);
+        tc_fence_after();
+        K3X_MARK(it, 0);
+        if (elect_one()) {
+#ifndef K3X_NO_G1
+          issue_gemm<SPLIT>(tmem + T2_Z + (uint32_t)(it & 1) * 32u, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
+#endif
+          mma_commit(&bar_g1);
+        }
+        __syncwarp();
+        K3X_MARK(it, 1);
+      }
+      if (it > 0) {
+        named_bar_sync(1, NTT);
+        tc_fence_after();
+        K3X_MARK(it, 14);
+      }
+      if (it > 2) {                 // G3(it-1) overwrites the dW'^T buffer that E2(it-3) reads
+        if ((it - 1) & 1) { mbar_wait(&bar_dwfree[1], ph_f1); ph_f1 ^= 1; } else { mbar_wait(&bar_dwfree[0], ph_f0); ph_f0 ^= 1; }
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        if (it > 0) {
+          const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
+#ifndef K3X_NO_G3
+          issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g3, 0u);
+#endif
+          mma_commit(&bar_dw[(it - 1) & 1]);       // the E2 warps start on dW'^T without waiting for G2
+#ifndef K3X_NO_G2
+          issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2n, it > 1 ? 1u : 0u);
+#endif
+          (void)bo;
+        }
+        mma_commit(&bar_g23);      // it == 0: nothing pending, completes at once (the epilogue's first wait)
+      }
+      __syncwarp();
+      K3X_MARK(it, 15);
+    }
+  } else if (warp == 2 * NWE + 1) {
+    // ================= copy warp: E2 stage refill, L2 prefetch =================
+    // The stage holds the W/m/v rows (and bias triplets) of ONE tile; it is refilled as soon as the E2 warps have read
+    // it into registers (barrier 2), while they are still computing and storing.
     auto stage_copy = [&](int j) {
       const int v0 = ((int)blockIdx.x + j * G) * TN;
       if (kAdam && Vloc - v0 >= TN) {
@@ -916,14 +1060,11 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         bulk_g2s(sB + TN, mb + v0, bbytes, &bar_stage);
         bulk_g2s(sB + 2 * TN, vb + v0, bbytes, &bar_stage);
       } else {
-        mbar_arrive(&bar_stage);
+        mbar_arrive(&bar_stage);     // ragged last tile / no Adam in this launch: E2 works on global memory
       }
     };
-    // L2 prefetch, K3_PF_AHEAD tiles ahead: the W rows that the loader warps read, and (K3_PF_MV) the m/v rows and
-    // bias triplets that the single-buffered E2 stage is refilled from.  The stage copy is issued only once the
-    // previous tile has been read out of it, so without the prefetch its HBM latency + transfer is exposed every
-    // tile and each SM has bytes in flight only part of the time; with it the refill is an L2 hit and the HBM
-    // streams of the next tiles stay open all the time.
+    // L2 prefetch, K3_PF_AHEAD tiles ahead: the W rows that the loader warps read and (K3_PF_MV) the m/v rows and
+    // bias triplets of the stage, so that the HBM streams of the next tiles stay open while this tile computes.
     auto prefetch_w = [&](int j) {
       if (j >= n_my) return;
       const int v0 = ((int)blockIdx.x + j * G) * TN;
@@ -941,100 +1082,26 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       }
 #endif
     };
-    if (elect_one()) {
+    if (lane == 0) {
       stage_copy(0);
       for (int j = 1; j < K3_PF_AHEAD; ++j) prefetch_w(j);
     }
     __syncwarp();
-    for (int it = 0; it <= n_my; ++it) {
-      named_bar_sync(1, NTT);
-      tc_fence_after();
-      if (elect_one()) {
-        // logits of the next tile first: its epilogue math then overlaps the backward GEMMs of this tile
-        // K3X_* (here and below): timing experiments only (scripts/k3_experiments.sh); never defined in the product build
-#ifndef K3X_NO_G1
-        if (it < n_my) issue_gemm<SPLIT>(tmem + T2_Z + (uint32_t)(it & 1) * 32u, op_hb, op_wb, g.Kp / 8, idesc_g1, 0u);
-#endif
-        mma_commit(&bar_g1);
-        if (it > 0) {
-          const uint32_t bo = (uint32_t)((it - 1) & 1) * 32u;
-#ifndef K3X_NO_G3
-          issue_gemm_ts<SPLIT>(tmem + T2_DW + bo, tmem + T2_HTH, tmem + T2_HTL, op_dt, ksteps_b, idesc_g1, 0u);
-#endif
-#ifndef K3X_NO_G2
-          issue_gemm_ts<SPLIT>(tmem + T2_DH, tmem + T2_DZH, tmem + T2_DZL, op_wt, TN / 8, idesc_g2, it > 1 ? 1u : 0u);
-#endif
-          (void)bo;
-        }
-        mma_commit(&bar_g23);
-        prefetch_w(it + K3_PF_AHEAD);
-      }
+    for (int j = 1; j < n_my; ++j) {
+      if (lane == 0) prefetch_w(j + K3_PF_AHEAD - 1);
+      named_bar_sync(2, NTT);          // E2(j-1) has read the stage
+      if (lane == 0) stage_copy(j);
       __syncwarp();
-      if (it >= 2) {
-        named_bar_sync(2, NTT);          // every epilogue thread has read tile it-2 out of the stage
-        if (elect_one()) stage_copy(it - 1);
-        __syncwarp();
-      }
     }
-  } else {
-    // ================= epilogue / loader warps =================
-    const int q4 = warp & 3, cpart = warp >> 2;      // TMEM lane quarter, 8-column part of the 32-wide tile
+  } else if (warp < NWE) {
+    // ================= E1 / loader warps: logits -> dZ, the W' tile -> Wb / Wtb =================
+    const int q4 = warp & 3, cpart = warp >> 2;      // TMEM lane quarter, CWT-column part of the 32-wide tile
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int brow = q4 * 32 + lane;                 // E1: batch row of this thread; E2: hidden unit
-    const AdamK ak = adam_load(st, 0);
-    // H2'^T -> TMEM (lane = hidden unit, column = batch row), BK columns
-    for (int c = cpart; c < BK / 8; c += NPART) {
-      float hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int b = c * 8 + j;
-        float x = 0.f;
-        if (b < B) x = (brow < H) ? h2[(size_t)b * H + brow] : (brow == H ? 1.0f : 0.f);
-        hi[j] = tf32_hi(x);
-        lo[j] = x - hi[j];
-      }
-      tmem_st8(lane_addr + T2_HTH + c * 8, hi);
-      if (with_lo) tmem_st8(lane_addr + T2_HTL + c * 8, lo);
-    }
-    tmem_st_wait();
+    const int brow = q4 * 32 + lane;                 // batch row of this thread
+    if (warp == 0) K3X_MARK(39, 3);
     const uint32_t dt_off = (uint32_t)(cpart * (CWT / 8)) * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
     const float rvf = (brow < B) ? 1.0f : 0.f;
-    // Positives of this thread's row inside THIS CTA's tiles, found once: a row has ~|set|/gridDim items per
-    // CTA, so up to four (tile iteration, 8-bit column mask) events live in registers and the tile loop only
-    // compares its counter with the next event.  More than four: per-tile bisection of the row (rare).
-    constexpr uint32_t EV_NONE = 0xffffffffu;
-    uint32_t ev0 = EV_NONE, ev1 = EV_NONE, ev2 = EV_NONE, ev3 = EV_NONE;   // (iteration << 16) | mask of my CWT columns
-    bool ev_over = false;
-    int row_p0 = 0, row_p1 = 0;
-    if (brow < B) {
-      row_p0 = indptr[brow];
-      row_p1 = indptr[brow + 1];
-      uint32_t last_it = EV_NONE >> 16;
-      for (int p = row_p0; p < row_p1; ++p) {
-        const int v = __ldg(indices + p) - v_begin;
-        if (v < 0 || v >= Vloc) continue;
-        const int t = v / TN;
-        if (t % G != (int)blockIdx.x) continue;
-        const int col = v - t * TN;
-        if (col / CWT != cpart) continue;             // another warp's columns
-        const uint32_t it_ = (uint32_t)(t / G), bit = 1u << (col % CWT);
-        if (it_ == last_it) {                          // same tile as the previous event: merge
-          if (ev3 != EV_NONE) ev3 |= bit;
-          else if (ev2 != EV_NONE) ev2 |= bit;
-          else if (ev1 != EV_NONE) ev1 |= bit;
-          else ev0 |= bit;
-        } else {
-          const uint32_t e = (it_ << 16) | bit;
-          if (ev0 == EV_NONE) ev0 = e;
-          else if (ev1 == EV_NONE) ev1 = e;
-          else if (ev2 == EV_NONE) ev2 = e;
-          else if (ev3 == EV_NONE) ev3 = e;
-          else ev_over = true;
-          last_it = it_;
-        }
-      }
-    }
     WChunk wc[WCHT];
     make_wchunks_t<WCHT, NWE>(wc, g);
     float4 wA[WCHT], wB[WCHT];
@@ -1046,141 +1113,58 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     }
     fence_async_smem();
     tc_fence_before();
-    named_bar_arrive(1, NTT);
-
-    // E2 addressing: normal lanes (k < H) walk 8 item rows at pitch H; lanes H+1..H+8 own one bias element
-    // each; all use the same immediate offsets j*H (bias lanes only ever touch j = 0).
-    const int kb = H & 31;                           // lane of hidden unit H inside its warp
-    const bool bias_warp = (q4 == (H >> 5));
-    const int jb = brow - (H + 1);                   // bias lanes: 0..7
-    const bool is_bias = (jb >= 0 && jb < CWT);
-    float* const eW = is_bias ? bd3 : Wd3;
-    float* const eM = is_bias ? mb : mW;
-    float* const eV = is_bias ? vb : vW;
-    const float* const sWp = is_bias ? sB + cpart * CWT + jb : sW + cpart * CWT * H + brow;
-    const float* const sMp = is_bias ? sB + TN + cpart * CWT + jb : sM + cpart * CWT * H + brow;
-    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CWT + jb : sV + cpart * CWT * H + brow;
-    const int ecnt_full = is_bias ? 1 : (brow < H ? CWT : 0);
-    uint32_t phase = 0, phase_e = 0;
+    named_bar_arrive(3, NTT);                        // W'(0) is in Wb
+    if (warp == 0) K3X_MARK(39, 5);
+    // Positives of this thread's row inside THIS CTA's tiles, found once (while G1 of the first tile runs): a row has
+    // ~|set|/gridDim items per CTA, so up to four (tile iteration, CWT-bit column mask) events live in registers and
+    // the tile loop only compares its counter with the next event.  More than four: per-tile bisection of the row (rare).
+    constexpr uint32_t EV_NONE = 0xffffffffu;
+    uint32_t ev0 = EV_NONE, ev1 = EV_NONE, ev2 = EV_NONE, ev3 = EV_NONE;   // (iteration << 16) | mask of my CWT columns
+    bool ev_over = false;
+    int row_p0 = 0, row_p1 = 0;
+    if (brow < B) {
+      row_p0 = indptr[brow];
+      row_p1 = indptr[brow + 1];
+      uint32_t last_it = EV_NONE >> 16;
+      for (int p0 = row_p0; p0 < row_p1; p0 += 8) {
+        int vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) vv[u] = (p0 + u < row_p1) ? __ldg(indices + p0 + u) - v_begin : -1;   // 8 loads in flight
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int v = vv[u];
+          if (v < 0 || v >= Vloc) continue;
+          const int t = v / TN;
+          if (t % G != (int)blockIdx.x) continue;
+          const int col = v - t * TN;
+          if (col / CWT != cpart) continue;             // another warp's columns
+          const uint32_t it_ = (uint32_t)(t / G), bit = 1u << (col % CWT);
+          if (it_ == last_it) {                          // same tile as the previous event: merge
+            if (ev3 != EV_NONE) ev3 |= bit;
+            else if (ev2 != EV_NONE) ev2 |= bit;
+            else if (ev1 != EV_NONE) ev1 |= bit;
+            else ev0 |= bit;
+          } else {
+            const uint32_t e = (it_ << 16) | bit;
+            if (ev0 == EV_NONE) ev0 = e;
+            else if (ev1 == EV_NONE) ev1 = e;
+            else if (ev2 == EV_NONE) ev2 = e;
+            else if (ev3 == EV_NONE) ev3 = e;
+            else ev_over = true;
+            last_it = it_;
+          }
+        }
+      }
+    }
+    if (warp == 0) K3X_MARK(39, 4);
+    uint32_t phase = 0;
     float loss_local = 0.f;
-
-    // E2 of tile index j (its dW'^T is complete): old W/m/v come from the TMA-filled stage
-    auto e2_apply = [&](int j_done) {
-      const int tile = blockIdx.x + j_done * G;
-      const int v0 = tile * TN;
-      const int nv = min(TN, Vloc - v0);
-      uint32_t gr[CWT];
-      TmemIO<CWT>::ld_issue(lane_addr + T2_DW + (uint32_t)(j_done & 1) * 32u + cpart * CWT, gr);
-      size_t eoff;
-      int ecnt;
-      if (is_bias) {
-        eoff = (size_t)v0 + cpart * CWT + jb;
-        ecnt = (cpart * CWT + jb < nv) ? 1 : 0;
-      } else {
-        eoff = (size_t)(v0 + cpart * CWT) * H + brow;
-        ecnt = (brow < H) ? max(0, min(CWT, nv - cpart * CWT)) : 0;
-      }
-      float* pW = eW + eoff;
-      float* pM = eM + eoff;
-      float* pV = eV + eoff;
-      float* pG = (MODE != 0) ? ((is_bias ? gB : gW) + eoff) : nullptr;
-      float pw[CWT], pm[CWT], pv[CWT], pg[CWT];
-#pragma unroll
-      for (int j = 0; j < CWT; ++j) pw[j] = pm[j] = pv[j] = 0.f;
-      if (MODE == 2 || MODE == 3) {                      // gradient of the earlier chunks (coalesced over the lanes)
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) pg[j] = (j < ecnt) ? pG[(size_t)j * H] : 0.f;
-      }
-      mbar_wait(&bar_stage, phase_e);
-      phase_e ^= 1;
-#ifdef K3X_NO_E2LD
-      if (false) {
-#else
-      if (kAdam) {
-#endif
-        if (nv == TN) {
-#pragma unroll
-          for (int j = 0; j < CWT; ++j) {
-            if (j < ecnt_full) {
-              pw[j] = sWp[j * H];
-              pm[j] = sMp[j * H];
-              pv[j] = sVp[j * H];
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CWT; ++j) {
-            if (j < ecnt) {
-              pw[j] = pW[(size_t)j * H];
-              pm[j] = pM[(size_t)j * H];
-              pv[j] = pV[(size_t)j * H];
-            }
-          }
-        }
-      }
-      if (j_done + 1 < n_my) named_bar_arrive(2, NTT);   // the stage may be refilled (tile j_done + 1)
-      float gw[CWT];
-      TmemIO<CWT>::ld_wait(gr);
-#pragma unroll
-      for (int j = 0; j < CWT; ++j) gw[j] = __uint_as_float(gr[j]);
-      if (bias_warp) {
-        float gb = 0.f;
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) {
-          float t = __shfl_sync(0xffffffffu, gw[j], kb);
-          if (jb == j) gb = t;
-        }
-        if (is_bias) gw[0] = gb;
-      }
-      if (MODE == 2 || MODE == 3) {
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) gw[j] += pg[j];
-      }
-      if (kAdam) {
-        // Adam (common.cuh adam_update, same operations in the same order per element), written stage by stage over the
-        // CWT independent elements: the per-element chain is ~10 dependent instructions incl. two MUFU, and with four
-        // warps per scheduler the element-after-element form left the issue slots idle (ncu: 11 stall samples per
-        // instruction in this block).
-        float dn[CWT];
-#ifndef K3X_NO_E2MATH
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) pm[j] = fmaf(ak.w1, gw[j] - pm[j], pm[j]);
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) pv[j] = fmaf(ak.w2 * gw[j], gw[j], pv[j] * ak.beta2);
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) dn[j] = fmaf(sqrt_approx(pv[j]), ak.inv_bc2_sqrt, ak.eps);
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) dn[j] = pm[j] * rcp_approx(dn[j]);
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) pw[j] = fmaf(-ak.step_size, dn[j], pw[j]);
-#else
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) { dn[j] = gw[j]; pw[j] += dn[j]; }
-#endif
-#ifndef K3X_NO_E2ST
-#pragma unroll
-        for (int j = 0; j < CWT; ++j) {
-          if (j < ecnt) {
-            pW[(size_t)j * H] = pw[j];
-            __stcs(pM + (size_t)j * H, pm[j]);
-            __stcs(pV + (size_t)j * H, pv[j]);
-          }
-        }
-#else
-        if (pw[0] + pm[1] + pv[2] == 1.2345e30f) pW[0] = pw[3];      // keep the values alive
-#endif
-      } else {
-#pragma unroll
-        for (int j = 0; j < CWT; ++j)
-          if (j < ecnt) pG[(size_t)j * H] = gw[j];
-      }
-    };
 
     for (int i = 0; i < n_my; ++i) {
       const int tile = blockIdx.x + i * G;
       const int v0 = tile * TN;
       const int nv = min(TN, Vloc - v0);
-      // positives of this tile among this thread's 8 columns
+      // positives of this tile among this thread's CWT columns
       uint32_t tb = 0u;
       if ((ev0 >> 16) == (uint32_t)i) {
         tb = ev0 & 0xffffu;
@@ -1200,18 +1184,24 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
           tb |= 1u << d;
         }
       }
-      const int vm = nv - cpart * CWT;                 // valid columns of this thread's 8 (>= 8: all)
+      const int vm = nv - cpart * CWT;                 // valid columns of this thread's CWT (>= CWT: all)
 
       // ---- E1(i), math part: needs only G1(i)
+      if (warp == 0) K3X_MARK(i, 2);
       mbar_wait(&bar_g1, phase);
       tc_fence_after();
+      if (warp == 0) K3X_MARK(i, 3);
       float dzh[CWT], dzl[CWT];
       {
         float z[CWT];
         uint32_t zr[CWT];
         TmemIO<CWT>::ld_issue(lane_addr + T2_Z + (uint32_t)(i & 1) * 32u + cpart * CWT, zr);
-        // W'(i+1) for G1(i+1): G1(i) has finished reading the buffer
-        if (i + 1 < n_my) store_wb_regs<WCHT>(wB, wc, wb_hi, wb_lo, with_lo);
+        // W'(i+1) for G1(i+1): G1(i) has finished reading the buffer; handed to the MMA warp at once
+        if (i + 1 < n_my) {
+          store_wb_regs<WCHT>(wB, wc, wb_hi, wb_lo, with_lo);
+          fence_async_smem();
+          named_bar_arrive(3, NTT);
+        }
         TmemIO<CWT>::ld_wait(zr);
 #pragma unroll
         for (int j = 0; j < CWT; ++j) z[j] = __uint_as_float(zr[j]);
@@ -1259,9 +1249,11 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
         }
       }
       // ---- operand stores: need G2/G3(i-1) to be done with dZ, Dtb and Wtb
+      if (warp == 0) K3X_MARK(i, 4);
       mbar_wait(&bar_g23, phase);
       phase ^= 1;
       tc_fence_after();
+      if (warp == 0) K3X_MARK(i, 5);
 #pragma unroll
       for (int j = 0; j < CWT; ++j) {
         const uint32_t o = dt_off + (uint32_t)(j >> 3) * g.dt_sbo + (uint32_t)(j & 7) * 16u;
@@ -1277,20 +1269,19 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
       fence_async_smem();
       tc_fence_before();
       named_bar_arrive(1, NTT);
+      if (warp == 0) K3X_MARK(i, 6);
 #pragma unroll
       for (int j = 0; j < WCHT; ++j) wA[j] = wB[j];
       if (i + 2 < n_my) {
         const int t2 = tile + 2 * G;
         load_w_regs_t<WCHT>(wB, wc, Wd3, bd3, H, t2 * TN, min(TN, Vloc - t2 * TN));
       }
-      // ---- E2(i-1): overlaps the MMAs of iteration i
-      if (i > 0) e2_apply(i - 1);
     }
     mbar_wait(&bar_g23, phase);                       // G2/G3 of the last tile
     tc_fence_after();
-    e2_apply(n_my - 1);
-    // ---- flush dh2 (lane = batch row, columns = hidden unit); the column order is rotated per CTA so that
-    // the 148 CTAs, which finish together, do not all hit the same addresses at the same time
+    if (warp == 0) K3X_MARK(39, 6);
+    // ---- flush dh2 (lane = batch row, columns = hidden unit) while the E2 warps finish the last tile; the column
+    // order is rotated per CTA so that the 148 CTAs, which finish together, do not all hit the same addresses at once
     {
       const int nch = g.Np / CWT;
       const int rot = (int)(blockIdx.x % (unsigned)nch);
@@ -1319,6 +1310,160 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     }
     float s = warp_sum(loss_local);
     if (lane == 0) red[warp] = s;
+    if (warp == 0) K3X_MARK(39, 7);
+  } else {
+    // ================= E2 warps: dW'^T(j) -> dec_optim on the W/m/v rows of tile j =================
+    // Lane = hidden unit k (the TMEM lane of dW'^T), CWT item rows at pitch H.  Lanes H+1..H+CWT of the warp that
+    // holds lane H own one bias element each: the bias gradients (lane H) are handed to them by shuffles and they
+    // run the same Adam code on bd3/mb/vb -- no divergent bias path.
+    const int we = warp - NWE;
+    const int q4 = we & 3, cpart = we >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int brow = q4 * 32 + lane;                 // hidden unit of this thread
+    const AdamK ak = adam_load(st, 0);
+    const int kb = H & 31;                           // lane of hidden unit H inside its warp
+    const bool bias_warp = (q4 == (H >> 5));
+    const int jb = brow - (H + 1);                   // bias lanes: 0..CWT-1
+    const bool is_bias = (jb >= 0 && jb < CWT);
+    float* const eW = is_bias ? bd3 : Wd3;
+    float* const eM = is_bias ? mb : mW;
+    float* const eV = is_bias ? vb : vW;
+    const float* const sWp = is_bias ? sB + cpart * CWT + jb : sW + cpart * CWT * H + brow;
+    const float* const sMp = is_bias ? sB + TN + cpart * CWT + jb : sM + cpart * CWT * H + brow;
+    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CWT + jb : sV + cpart * CWT * H + brow;
+    const int ecnt_full = is_bias ? 1 : (brow < H ? CWT : 0);
+    uint32_t phase_e = 0, ph_dw0 = 0, ph_dw1 = 0;
+    const uint32_t rt_zero = (uint32_t)smem_total >> 31;
+    for (int jt = 0; jt < n_my; ++jt) {
+      const int tile = blockIdx.x + jt * G;
+      const int v0 = tile * TN;
+      const int nv = min(TN, Vloc - v0);
+      size_t eoff;
+      int ecnt;
+      if (is_bias) {
+        eoff = (size_t)v0 + cpart * CWT + jb;
+        ecnt = (cpart * CWT + jb < nv) ? 1 : 0;
+      } else {
+        eoff = (size_t)(v0 + cpart * CWT) * H + brow;
+        ecnt = (brow < H) ? max(0, min(CWT, nv - cpart * CWT)) : 0;
+      }
+      float* pW = eW + eoff;
+      float* pM = eM + eoff;
+      float* pV = eV + eoff;
+      float* pG = (MODE != 0) ? ((is_bias ? gB : gW) + eoff) : nullptr;
+      float pw[CWT], pm[CWT], pv[CWT], pg[CWT];
+#pragma unroll
+      for (int j = 0; j < CWT; ++j) pw[j] = pm[j] = pv[j] = 0.f;
+      if (MODE == 2 || MODE == 3) {                      // gradient of the earlier chunks (coalesced over the lanes)
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pg[j] = (j < ecnt) ? pG[(size_t)j * H] : 0.f;
+      }
+      // old W/m/v from the TMA-filled stage; the stage is handed back for the refill as soon as it has been read
+      if (warp == NWE) K3X_MARK(jt, 8);
+      mbar_wait(&bar_stage, phase_e);
+      phase_e ^= 1;
+      if (warp == NWE) K3X_MARK(jt, 9);
+#ifdef K3X_NO_E2LD
+      if (false) {
+#else
+      if (kAdam) {
+#endif
+        if (nv == TN) {
+#pragma unroll
+          for (int j = 0; j < CWT; ++j) {
+            if (j < ecnt_full) {
+              pw[j] = sWp[j * H];
+              pm[j] = sMp[j * H];
+              pv[j] = sVp[j * H];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CWT; ++j) {
+            if (j < ecnt) {
+              pw[j] = pW[(size_t)j * H];
+              pm[j] = pM[(size_t)j * H];
+              pv[j] = pV[(size_t)j * H];
+            }
+          }
+        }
+      }
+      if (jt + 1 < n_my) {
+        // The stage may be refilled (tile jt + 1) -- but only once the loads above have RETURNED: bar.arrive does not
+        // order earlier shared-memory reads, and the refill (an L2 hit) can overtake loads that are still queued behind
+        // the other warps' traffic.  The barrier id is made to depend on every loaded register (rt_zero is 0 at run time).
+        uint32_t dep = 0u;
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) dep ^= __float_as_uint(pw[j]) ^ __float_as_uint(pm[j]) ^ __float_as_uint(pv[j]);
+        named_bar_arrive(2 + (int)(dep & rt_zero), NTT);
+      }
+      // dW'^T(jt): its own mbarrier per TMEM buffer (these warps run behind the MMA warp by up to two tiles)
+      if (jt & 1) { mbar_wait(&bar_dw[1], ph_dw1); ph_dw1 ^= 1; } else { mbar_wait(&bar_dw[0], ph_dw0); ph_dw0 ^= 1; }
+      tc_fence_after();
+      if (warp == NWE) K3X_MARK(jt, 10);
+      float gw[CWT];
+      {
+        uint32_t gr[CWT];
+        TmemIO<CWT>::ld_issue(lane_addr + T2_DW + (uint32_t)(jt & 1) * 32u + cpart * CWT, gr);
+        TmemIO<CWT>::ld_wait(gr);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) gw[j] = __uint_as_float(gr[j]);
+      }
+      // this dW'^T buffer may be overwritten by G3(jt + 2)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_dwfree[jt & 1]);
+      if (bias_warp) {
+        float gb = 0.f;
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) {
+          float t = __shfl_sync(0xffffffffu, gw[j], kb);
+          if (jb == j) gb = t;
+        }
+        if (is_bias) gw[0] = gb;
+      }
+      if (MODE == 2 || MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) gw[j] += pg[j];
+      }
+      if (kAdam) {
+        // Adam (common.cuh adam_update, same operations in the same order per element), written stage by stage over the
+        // CWT independent elements: the per-element chain is ~10 dependent instructions incl. two MUFU.
+        float dn[CWT];
+#ifndef K3X_NO_E2MATH
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pm[j] = fmaf(ak.w1, gw[j] - pm[j], pm[j]);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pv[j] = fmaf(ak.w2 * gw[j], gw[j], pv[j] * ak.beta2);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) dn[j] = fmaf(sqrt_approx(pv[j]), ak.inv_bc2_sqrt, ak.eps);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) dn[j] = pm[j] * rcp_approx(dn[j]);
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) pw[j] = fmaf(-ak.step_size, dn[j], pw[j]);
+#else
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) { dn[j] = gw[j]; pw[j] += dn[j]; }
+#endif
+#ifndef K3X_NO_E2ST
+#pragma unroll
+        for (int j = 0; j < CWT; ++j) {
+          if (j < ecnt) {
+            pW[(size_t)j * H] = pw[j];
+            __stcs(pM + (size_t)j * H, pm[j]);
+            __stcs(pV + (size_t)j * H, pv[j]);
+          }
+        }
+#else
+        if (pw[0] + pm[1] + pv[2] == 1.2345e30f) pW[0] = pw[3];      // keep the values alive
+#endif
+      } else {
+#pragma unroll
+        for (int j = 0; j < CWT; ++j)
+          if (j < ecnt) pG[(size_t)j * H] = gw[j];
+      }
+      if (warp == NWE) K3X_MARK(jt, 7);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1327,7 +1472,8 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTT, 1) dec_out_train_tc2_kernel(
     for (int w = 0; w < NWE; ++w) tot += (double)red[w];
     atomicAdd(loss_sum, tot);
   }
-  if (warp == NWE) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 0) K3X_MARK(39, 8);
+  if (warp == 2 * NWE) tmem_dealloc(tmem, TMEM_COLS);
   trace_mark(TR_K3, 1);
 }
 
@@ -1420,13 +1566,14 @@ __global__ void __launch_bounds__(NT, 1) dec_out_scores_tc_kernel(const float* _
 //   mode 2 (G2 form, A in TMEM):        D[128,112] = A[128,32]       . Bm[112,32]^T
 //   mode 3 (G3 form, A in TMEM):        D[128,32]  = A[128,128]      . Bm[32,128]^T
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const float* __restrict__ A,
+__global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode_in, const float* __restrict__ A,
                                                             const float* __restrict__ Bm, float* __restrict__ D,
                                                             int split) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar_mma;
   __shared__ uint32_t tmem_base_s;
   const Geom g = make_geom(100);
+  int mode = mode_in;
   unsigned char* hb_hi = smem;
   unsigned char* hb_lo = hb_hi + g.hb_bytes;
   unsigned char* wb_hi = hb_lo + g.hb_bytes;
@@ -1456,7 +1603,38 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
     *reinterpret_cast<float*>(hi + off) = h;
     if (with_lo) *reinterpret_cast<float*>(lo + off) = x - h;
   };
-  if (mode == 1) {
+  // modes 6 / 7 (+16*variant): the B operand of the G2 / G3 form MN-major (N contiguous) in the SWIZZLE_128B_BASE32B
+  // layout: rows of 128 bytes (32 N-elements) per K index, the four 32-byte chunks of a row XOR-ed with (K index & 3)
+  const int variant = mode >> 4;
+  mode &= 15;
+  unsigned char* pb_hi = smem;                 // probe buffers (the Hb region is unused in these modes)
+  unsigned char* pb_lo = smem + 16384;
+  if (mode == 6 || mode == 7) {
+    const int acols = (mode == 6) ? TN : BM;
+    const uint32_t th = (mode == 6) ? TM_DZH : TM_HTH, tl = (mode == 6) ? TM_DZL : TM_HTL;
+    for (int c = cpart; c < acols / CW; c += NT / 128) {
+      float hi[CW], lo[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        float x = A[(size_t)row * acols + c * CW + j];
+        hi[j] = tf32_hi(x);
+        lo[j] = x - hi[j];
+      }
+      tmem_st8(lane_addr + th + c * CW, hi);
+      if (with_lo) tmem_st8(lane_addr + tl + c * CW, lo);
+    }
+    tmem_st_wait();
+    const int nN = (mode == 6) ? g.Np : TN, nK = (mode == 6) ? TN : BM;
+    for (int q = tid; q < nN * nK; q += NT) {
+      const int n = q / nK, kk = q % nK;
+      const int blk = n >> 5, nn = n & 31;
+      const int sw = (variant == 2) ? 0 : (kk & 3);
+      const uint32_t off = (uint32_t)blk * 4096u + (uint32_t)kk * 128u + (uint32_t)(((nn >> 3) ^ sw) * 32) + (uint32_t)(nn & 7) * 4u;
+      const float x = Bm[q], h = tf32_hi(x);
+      *reinterpret_cast<float*>(pb_hi + off) = h;
+      if (with_lo) *reinterpret_cast<float*>(pb_lo + off) = x - h;
+    }
+  } else if (mode == 1) {
     for (int q = tid; q < BM * g.Kp; q += NT) split_store(hb_hi, hb_lo, q / g.Kp, q % g.Kp, CORE, g.hb_sbo, A[q]);
     for (int q = tid; q < TN * g.Kp; q += NT) split_store(wb_hi, wb_lo, q / g.Kp, q % g.Kp, CORE, g.wb_sbo, Bm[q]);
   } else {
@@ -1487,7 +1665,24 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
     const SmemOp o_hb = make_op(hb_hi, hb_lo, CORE, g.hb_sbo, 2 * CORE), o_wb = make_op(wb_hi, wb_lo, CORE, g.wb_sbo, 2 * CORE);
     const SmemOp o_wt = make_op(wt_hi, wt_lo, g.wt_lbo, g.wt_sbo, 2 * g.wt_lbo);
     const SmemOp o_dt = make_op(dt_hi, dt_lo, g.dt_lbo, g.dt_sbo, 2 * g.dt_lbo);
-    if (elect_one()) {
+    const bool leader = elect_one();
+    if (leader && (mode == 6 || mode == 7)) {
+      uint32_t lbo = 4096u, sbo = 512u;
+      if (variant == 1) { lbo = 512u; sbo = 4096u; }
+      if (variant == 3) sbo = 1024u;
+      SmemOp o;
+      o.hi = make_desc_sw(smem_u32(pb_hi), lbo, sbo, 1u);
+      o.lo = make_desc_sw(smem_u32(pb_lo), lbo, sbo, 1u);
+      o.step16 = 1024u >> 4;                       // 8 K rows of 128 bytes per k-step
+      if (mode == 6) {
+        if (split == 3) issue_gemm_ts<3>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, o, TN / 8, make_idesc(BM, g.Np, 0, 1), 0u);
+        else issue_gemm_ts<1>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, o, TN / 8, make_idesc(BM, g.Np, 0, 1), 0u);
+      } else {
+        if (split == 3) issue_gemm_ts<3>(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, o, BM / 8, make_idesc(BM, TN, 0, 1), 0u);
+        else issue_gemm_ts<1>(tmem + TM_DW, tmem + TM_HTH, tmem + TM_HTL, o, BM / 8, make_idesc(BM, TN, 0, 1), 0u);
+      }
+      mma_commit(&bar_mma);
+    } else if (leader) {
       if (split == 3) {
         if (mode == 1) issue_gemm<3>(tmem + TM_Z, o_hb, o_wb, g.Kp / 8, make_idesc(BM, TN, 0, 0), 0u);
         else if (mode == 2) issue_gemm_ts<3>(tmem + TM_DH, tmem + TM_DZH, tmem + TM_DZL, o_wt, TN / 8, make_idesc(BM, g.Np, 0, 0), 0u);
@@ -1503,8 +1698,8 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode, const floa
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
-  const int ncols = (mode == 2) ? g.Np : TN;
-  const uint32_t tsrc = (mode == 1) ? TM_Z : (mode == 2 ? TM_DH : TM_DW);
+  const int ncols = (mode == 2 || mode == 6) ? g.Np : TN;
+  const uint32_t tsrc = (mode == 1) ? TM_Z : ((mode == 2 || mode == 6) ? TM_DH : TM_DW);
   for (int c = cpart; c < ncols / CW; c += NT / 128) {
     float d[CW];
     tmem_ld8(lane_addr + tsrc + c * CW, d);
@@ -1897,7 +2092,7 @@ static int launch_tc2(const float* h2, int B, int H, float* Wd3, float* bd3, flo
     set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
-  kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTT, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+  kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTHR, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
                                                    (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem, gW, gB);
   return check_launch("dec_out_train(tc2)");
 }
@@ -2028,3 +2223,9 @@ extern "C" int aae_tc_selftest(int mode, const float* A, const float* Bm, float*
   tc::tc_selftest_kernel<<<1, tc::NT, smem, as_stream(stream)>>>(mode, A, Bm, D, split);
   return check_launch("tc_selftest");
 }
+
+#ifdef K3X_TRACE
+extern "C" int aae_k3x_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, aae::tc::k3x_tr, sizeof(long long) * 32 * 16);
+}
+#endif
