@@ -132,7 +132,7 @@ def last_error():
 
 
 # kernels launched per entry point (for the bench's gpu_launches claim); memcpy-only calls count 0
-KERNELS = {"aae_upload_batch": 0, "aae_batch_gather": 2, "aae_batch_corrupt": 2, "aae_rank_counts": 3, "aae_masked_topk": 2, "aae_predict_topk": 6, "aae_predict_topk2": 8, "aae_trace_set": 0, "aae_trace_slots": 0,
+KERNELS = {"aae_upload_batch": 0, "aae_w1_sweep_blocked": 2, "aae_batch_gather": 2, "aae_batch_corrupt": 2, "aae_rank_counts": 3, "aae_masked_topk": 2, "aae_predict_topk": 6, "aae_predict_topk2": 8, "aae_trace_set": 0, "aae_trace_slots": 0,
            "aae_peer_alloc": 0, "aae_peer_open": 0, "aae_peer_close": 0, "aae_peer_free": 0, "aae_peer_error": 0}
 TRACE_NAMES = ("batch_prepare", "w1_sweep_untouched", "ae_fwd", "dec_out_train", "ae_bwd", "ae_wgrad", "w1_rows_update_1",
                "disc_phase", "disc_wgrad", "gen_phase", "gen_wgrad", "w1_rows_update_2", "step_finish", "bag_fwd", "w1_catchup")

@@ -123,7 +123,7 @@ class AAEEngine(object):
         self.overlap_sweep = bool(overlap_sweep) and os.environ.get("AAE_B200_NO_OVERLAP", "") == ""
         self.branches = os.environ.get("AAE_B200_NO_BRANCH", "") == ""   # parallel graph branches (debug switch)
         # 64-thread sweep CTAs per SM that run beside the decoder-output kernel (0: the stand-alone wide sweep)
-        self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "2"))
+        self.sweep_ctas = int(os.environ.get("AAE_B200_SWEEP_CTAS", "4"))   # measured at the MPD shape: 2 -> 1517, 4 -> 1443, 8 -> 1467 us per step
         # W1t Adam policy: rows outside the batch are swept in G time-blocked groups (1 = dense sweep every step)
         # (measured at V=2M: 2.01 / 1.82 / 1.67 ms per step for G = 8 / 16 / 32 -- the group sweep runs exposed behind
         # the decoder kernel; V=200k: no difference)

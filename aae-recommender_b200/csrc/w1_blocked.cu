@@ -145,14 +145,71 @@ __global__ void __launch_bounds__(T) w1_sweep_blocked_kernel(const int32_t* __re
     r1 = min(Vloc, r0 + rpg);
     to = t;
   }
-  for (int r = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < r1; r += warps) {
-    if (!flush && __ldg(slot_of + r) >= 0) continue;
-    const int from = last[r];
-    if (from >= to) continue;
-    replay_row((size_t)r * H, H, from, to, W, m1, v1, m2, v2, st, ktab, lane);
-    if (lane == 0) last[r] = to;
+  if ((H & 3) == 0) {
+    // Flat walk over the float4 columns of the row range: with one warp per row only H/4 of the 32 lanes work (25 of 32
+    // at n_hidden 100) and the replay is MUFU-bound.  A row's columns may then belong to two warps, so `last` is not
+    // written here (the second warp would find the row up to date and skip its part): w1_last_kernel does it afterwards.
+    const int H4 = H >> 2;
+    const long long n4 = (long long)(r1 - r0) * H4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    AdamK k1, k2;
+    k1.w1 = k2.w1 = (float)(1.0 - 0.9);
+    k1.beta2 = k2.beta2 = st->beta2;
+    k1.w2 = k2.w2 = (float)(1.0 - 0.999);
+    k1.eps = k2.eps = st->eps;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
+      const int r = r0 + (int)(e / H4);
+      if (!flush && __ldg(slot_of + r) >= 0) continue;
+      const int from = last[r];
+      const int n = to - from;
+      if (n <= 0) continue;
+      const size_t q = (size_t)r0 * H4 + (size_t)e;
+      float4 p = __ldcs(reinterpret_cast<const float4*>(W) + q);
+      float4 a = __ldcs(reinterpret_cast<const float4*>(m1) + q);
+      float4 b = __ldcs(reinterpret_cast<const float4*>(v1) + q);
+      float4 c = __ldcs(reinterpret_cast<const float4*>(m2) + q);
+      float4 d = __ldcs(reinterpret_cast<const float4*>(v2) + q);
+      for (int j = 1; j <= n; ++j) {       // the same operations in the same order as replay4
+        const float4 kk = __ldg(reinterpret_cast<const float4*>(ktab) + ((from + j) & (AAE_KTAB_SLOTS - 1)));
+        k1.step_size = kk.x; k2.step_size = kk.y;
+        k1.inv_bc2_sqrt = k2.inv_bc2_sqrt = kk.z;
+        adam_update_zero(k1, p.x, a.x, b.x); adam_update_zero(k2, p.x, c.x, d.x);
+        adam_update_zero(k1, p.y, a.y, b.y); adam_update_zero(k2, p.y, c.y, d.y);
+        adam_update_zero(k1, p.z, a.z, b.z); adam_update_zero(k2, p.z, c.z, d.z);
+        adam_update_zero(k1, p.w, a.w, b.w); adam_update_zero(k2, p.w, c.w, d.w);
+      }
+      reinterpret_cast<float4*>(W)[q] = p;
+      __stcs(reinterpret_cast<float4*>(m1) + q, a);
+      __stcs(reinterpret_cast<float4*>(v1) + q, b);
+      __stcs(reinterpret_cast<float4*>(m2) + q, c);
+      __stcs(reinterpret_cast<float4*>(v2) + q, d);
+    }
+  } else {
+    for (int r = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < r1; r += warps) {
+      if (!flush && __ldg(slot_of + r) >= 0) continue;
+      const int from = last[r];
+      if (from >= to) continue;
+      replay_row((size_t)r * H, H, from, to, W, m1, v1, m2, v2, st, ktab, lane);
+      if (lane == 0) last[r] = to;
+    }
   }
   trace_mark(TR_SWEEP, 1);
+}
+// rows swept by the flat walk above -> last[r] = to
+__global__ void __launch_bounds__(256) w1_last_kernel(const int32_t* __restrict__ slot_of, int Vloc, int32_t* last,
+                                                      const aae_step_state* __restrict__ st, int G, int flush) {
+  const int t = st->t;
+  int r0 = 0, r1 = Vloc, to = t - 1;
+  if (!flush) {
+    const int rpg = (Vloc + G - 1) / G;
+    r0 = (t % G) * rpg;
+    r1 = min(Vloc, r0 + rpg);
+    to = t;
+  }
+  for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+    if (!flush && __ldg(slot_of + r) >= 0) continue;
+    if (last[r] < to) last[r] = to;
+  }
 }
 
 }  // namespace aae
@@ -191,6 +248,11 @@ int aae_w1_sweep_blocked(const int32_t* slot_of, int Vloc, int H, float* W, floa
   else
     w1_sweep_blocked_kernel<256><<<8 * sm_count(), 256, 0, as_stream(stream)>>>(slot_of, Vloc, H, W, m1, v1, m2, v2,
                                                                              last, st, ktab, G, flush);
+  if ((H & 3) == 0) {
+    const int rows = flush ? Vloc : (Vloc + G - 1) / G;
+    w1_last_kernel<<<std::max(1, std::min(2 * sm_count(), (rows + 255) / 256)), 256, 0, as_stream(stream)>>>(slot_of, Vloc, last,
+                                                                                                            st, G, flush);
+  }
   return check_launch("w1_sweep_blocked");
 }
 

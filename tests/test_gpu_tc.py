@@ -38,13 +38,13 @@ def test_tc_operand_views(split, tol):
     assert (D - want).abs().max() / want.abs().max() < tol
 
 
-def _run_train(impl, B, V, H=100, seed=0, steps=2):
+def _run_train(impl, B, V, H=100, seed=0, steps=2, wscale=0.1, bshift=0.0):
     from aaerec_b200 import _native as N
     from aaerec_b200.synth import synth_sets
     g = torch.Generator().manual_seed(seed)
     dev = "cuda"
-    W = (torch.rand(V, H, generator=g) * 0.2 - 0.1).to(dev)
-    b = (torch.rand(V, generator=g) * 0.2 - 0.1).to(dev)
+    W = ((torch.rand(V, H, generator=g) * 2 - 1) * wscale).to(dev)
+    b = (torch.rand(V, generator=g) * 0.2 - 0.1 + bshift).to(dev)
     mW, vW = torch.zeros_like(W), torch.zeros_like(W)
     mb, vb = torch.zeros_like(b), torch.zeros_like(b)
     X = synth_sets(B, V, 9, seed=seed + 1)
@@ -89,6 +89,20 @@ def test_tc_train_variants_match_fp32_kernel(B, V, H, impl):
     got, Wg, bg, mg, vg = _run_train(impl, B, V, H=H, steps=3)
     for (lr, dr), (lg, dg) in zip(ref, got):
         assert abs(lg - lr) / abs(lr) < 2e-6
+        assert _rel(dg, dr) < 2e-5
+    assert _rel(Wg, Wr) < 2e-6 and _rel(bg, br) < 2e-6
+    assert _rel(mg, mr) < 2e-5 and _rel(vg, vr) < 4e-5
+
+
+@pytest.mark.parametrize("wscale,bshift", [(0.5, 0.0), (0.4, -14.0), (0.15, -22.0)])
+def test_tc_train_wide_logits_match_fp32_kernel(wscale, bshift):
+    """Logits far outside (-16, 16): deep-negative values (everyday a few dozen steps into training; they stay on the
+    tensor-core kernel's fast paths), values >= 16 and positives (ATen's clamped edge formulas, per element)."""
+    B, V = 100, 6400
+    ref, Wr, br, mr, vr = _run_train(0, B, V, steps=2, wscale=wscale, bshift=bshift)
+    got, Wg, bg, mg, vg = _run_train(1, B, V, steps=2, wscale=wscale, bshift=bshift)
+    for (lr, dr), (lg, dg) in zip(ref, got):
+        assert abs(lg - lr) / abs(lr) < 5e-6
         assert _rel(dg, dr) < 2e-5
     assert _rel(Wg, Wr) < 2e-6 and _rel(bg, br) < 2e-6
     assert _rel(mg, mr) < 2e-5 and _rel(vg, vr) < 4e-5
