@@ -1101,7 +1101,6 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
     if (warp == 0) K3X_MARK(39, 3);
     const uint32_t dt_off = (uint32_t)(cpart * (CWT / 8)) * g.dt_sbo + (uint32_t)(brow >> 2) * g.dt_lbo + (uint32_t)(brow & 3) * 4u;
     const float inv_n_row = (brow < B) ? inv_n : 0.f;
-    const float rvf = (brow < B) ? 1.0f : 0.f;
     WChunk wc[WCHT];
     make_wchunks_t<WCHT, NWE>(wc, g);
     float4 wA[WCHT], wB[WCHT];
@@ -1211,17 +1210,38 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
           zhi = fmaxf(zhi, z[j]);
           zlo = fminf(zlo, z[j]);
         }
-        // Three paths.  The target is 0 nearly everywhere, and for target 0 and z < 16 ATen's clamped formula
+        // Four paths.  The target is 0 nearly everywhere, and for target 0 and z < 16 ATen's clamped formula
         // (common.cuh bce_term) equals softplus(z) / sigmoid(z)/N to far below 1e-6 relative -- for ANY negative depth:
         // below z = -16.6 ATen's own fp32 loss term log(1 - x) is exactly 0, as is log(1 + e^z) here.
-        //   P1  whole warp clean and -16 < z < 16: no branch on the sign of z, ONE lg2 per four elements (its loss term
-        //       z + log(1+e^-z) cancels for deep-negative z, which is why it stops at -16)
-        //   P2  this thread clean (no positive, full tile, z < 16), any negative depth: the same through e^-|z|
+        //   P0  whole warp clean and z <= 0 (the usual state of a model after a few dozen steps: mean logit -5 .. -10):
+        //       sigmoid = 1/(1+e^-z), loss = -log(1 - sigmoid) as ATen writes it, ONE lg2 per four elements, any depth
+        //   P1  whole warp clean and -16 < z < 16 (mixed signs, the first steps): loss = z + log(1+e^-z), which cancels
+        //       for deep-negative z -- hence the -16
+        //   P2  this thread clean (no positive, full tile, z < 16), mixed signs and deep: through e^-|z|
         //   P3  per element: positives, z >= 16 and ragged tiles through bce_term, the rest as in P2
-        // Logits below -16 are everyday values a few dozen steps into training; when they took the per-element path the
-        // whole warp waited for it and the kernel ran 1.7x slower (2.0 instead of 1.2 ms at V = 2M).
+        // Logits below -16 are everyday values; when they took the per-element path the whole warp waited for it and
+        // the kernel ran 1.7x slower (2.0 instead of 1.2 ms at V = 2M).  Rows >= B (dead lanes) never veto a warp path.
+        const bool live = brow < B;
         const bool clean = (tb == 0u) && (vm >= CWT) && (zhi < 16.0f);
-        if (__all_sync(0xffffffffu, clean && zlo > -16.0f)) {
+        if (__all_sync(0xffffffffu, !live || (clean && zhi <= 0.0f))) {
+          float pr[CWT / 4];
+#pragma unroll
+          for (int q = 0; q < CWT / 4; ++q) pr[q] = 1.0f;
+#pragma unroll
+          for (int j = 0; j < CWT; ++j) {
+            const float u = ex2_approx(-1.4426950408889634f * z[j]);     // e^-z >= 1
+            const float r = rcp_approx(1.0f + u);                         // sigmoid(z) in (0, 0.5]
+            const float d = r * inv_n_row;
+            pr[j >> 2] *= 1.0f - r;                                        // in [0.5, 1]: no cancellation
+            const float h = tf32_hi(d);
+            dzh[j] = h;
+            dzl[j] = d - h;
+          }
+          float lg = 0.f;
+#pragma unroll
+          for (int q = 0; q < CWT / 4; ++q) lg += lg2_approx(pr[q]);
+          if (live) loss_local = fmaf(lg, -0.6931471805599453f, loss_local);
+        } else if (__all_sync(0xffffffffu, !live || (clean && zlo > -16.0f))) {
           // sigmoid(z) = 1/(1+e^-z) and -log(1-sigmoid(z)) = z + log(1+e^-z); the logarithms of four elements are taken
           // as ONE lg2 of the product of their (1+e^-z) <= 8.9e6 (product < 6.3e27): 7 FP32 + 2 MUFU per element
           float sz = 0.f;
@@ -1247,7 +1267,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
           float lg = 0.f;
 #pragma unroll
           for (int q = 0; q < CWT / 4; ++q) lg += lg2_approx(pr[q]);
-          loss_local = fmaf(rvf, fmaf(lg, 0.6931471805599453f, sz), loss_local);
+          if (live) loss_local += fmaf(lg, 0.6931471805599453f, sz);
         } else if (clean) {
           // u = e^-|z| in (0,1]: sigmoid(z) = 1/(1+u) or u/(1+u), softplus(z) = max(z,0) + log(1+u); products <= 16
           float sz = 0.f;
@@ -1269,7 +1289,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
           float lg = 0.f;
 #pragma unroll
           for (int q = 0; q < CWT / 4; ++q) lg += lg2_approx(pr[q]);
-          loss_local = fmaf(rvf, fmaf(lg, 0.6931471805599453f, sz), loss_local);
+          if (live) loss_local += fmaf(lg, 0.6931471805599453f, sz);
         } else {
 #pragma unroll
           for (int j = 0; j < CWT; ++j) {

@@ -338,37 +338,19 @@ class Ctx(object):
         return eng
 
 
-IDLE_S = float(os.environ.get("AAE_BENCH_IDLE_S", "1.0"))
-
-
-def idle(ctx):
-    """The B200 is power-limited on this workload: W + K steps that follow an idle second run at full speed, the same
-    steps ~0.1 s into continuous work are 1.2-1.4x slower (`sustained` reports that regime, and so does
-    roofline.after_sustained).  A K-step leg is a burst by construction (25 steps = 40 ms); so that every burst leg
-    starts from the same board state -- and not from the heat of whatever ran before it -- the board idles for IDLE_S
-    seconds before the leg's own warm-up steps."""
-    import torch
-    torch.cuda.synchronize()
-    if IDLE_S > 0:
-        time.sleep(IDLE_S)
-    ctx.barrier()
-
-
 def train_leg(ctx, eng, dev_batches, B, K, W):
     """K partial_fit steps on batches already resident in HBM, after W warm-up steps; device seconds."""
     import torch
     n = len(dev_batches)
     # The time-blocked W1 Adam replays the pending zero-gradient steps of one row group per step: its cost grows for the
     # first G steps of an engine's life (1, 2, ... G replays per row) and is constant afterwards.  The timed region must
-    # see the constant cost: a fresh engine first runs G + 3 untimed steps, the board idles (see idle()), and then come
-    # the W warm-up steps and the K timed steps exactly as --warmup / --steps say.
+    # see the constant cost: a fresh engine first runs G + 3 untimed steps, and then come the W warm-up steps and the K
+    # timed steps exactly as --warmup / --steps say.
     aged = 0
     while eng.steps_done < eng.w1_groups + 3:          # untimed: bring the sweep to its steady-state cost
         eng.set_batch_device(*dev_batches[aged % n])
         eng.train_step(B)
         aged += 1
-    if aged:
-        idle(ctx)
     for i in range(W):
         eng.set_batch_device(*dev_batches[i % n])
         eng.train_step(B)
@@ -411,7 +393,6 @@ def e2e_leg(ctx, eng, batches, B, K, W, cond=None):
     memory, inside the timed region; the host reads the losses of step i-2 when it reuses that step's slot."""
     import torch
     n = len(batches)
-    idle(ctx)
     for i in range(3):                       # untimed: captures the host-entry graph
         ip, ii, cc = batches[i % n]
         eng.train_step_host(ip, ii, cc)
@@ -432,9 +413,8 @@ def e2e_leg(ctx, eng, batches, B, K, W, cond=None):
     return t0.elapsed_time(t1) * 1e-3, h2d // max(K, 1)
 
 
-def k3_roofline(ctx, eng, B, V, traffic=None, from_idle=True):
-    """The decoder-output kernel (K3) and the dense W1 sweep timed alone on their stream, CUDA events; from an idle board
-    like the K-step legs (from_idle) or in whatever state the board is in (after the sustained loop)."""
+def k3_roofline(ctx, eng, B, V, traffic=None):
+    """The decoder-output kernel (K3) and the dense W1 sweep timed alone on their stream, CUDA events."""
     import torch
     from aaerec_b200._native import call, ptr
     Vl = eng.Vloc
@@ -452,8 +432,6 @@ def k3_roofline(ctx, eng, B, V, traffic=None, from_idle=True):
     kern = {}
     for name, fn, alg_bytes in (("dec_out_train", k3, 24.0 * (Vl * H + Vl) + 8.0 * B * H),
                                 ("w1_sweep_untouched", sweep, 40.0 * Vl * H + 4.0 * Vl)):
-        if from_idle:
-            idle(ctx)
         for _ in range(3):
             fn()
         ts = time_kernel(fn, 10, ctx.stream)
@@ -523,7 +501,7 @@ def train_workload(ctx, name, K, W, with_roofline=True, with_sustained=True, B=N
     out["ms_per_step"] = sec / K * 1e3
     cold_roofline = None
     if with_roofline:
-        # right behind the timed steps, i.e. in the same clock / power state as `value`: the dominant kernel alone on its
+        # right behind the timed steps, i.e. in the same board state as `value`: the dominant kernel alone on its
         # stream, and the in-graph duration of every kernel of one step (globaltimer marks of first / last block)
         eng.set_batch_device(*dev_batches[0])
         cold_roofline = k3_roofline(ctx, eng, B, V)
@@ -551,10 +529,10 @@ def train_workload(ctx, name, K, W, with_roofline=True, with_sustained=True, B=N
     if with_roofline:
         out["roofline"] = cold_roofline
         if with_sustained:
-            # the same kernel again after >= 1 s of back-to-back steps: the board is power-limited by then (sw_power_cap)
-            # and the heavy kernels slow down by 1.2-1.5x although the reported SM clock stays near its maximum
+            # the same kernel again after >= 1 s of back-to-back steps: the board runs at its power cap by then
+            # (sw_power_cap) and the heavy kernels are ~5-10 % slower although the reported SM clock stays near its maximum
             eng.set_batch_device(*dev_batches[0])
-            hot = k3_roofline(ctx, eng, B, V, from_idle=False)
+            hot = k3_roofline(ctx, eng, B, V)
             out["roofline"]["after_sustained"] = {"ms": hot["ms"], "achieved": hot["achieved"], "frac": hot["frac"]}
     out["nnz_mean"] = float(np.mean([len(b[1]) for b in batches]))
     return out, eng, batches
@@ -811,10 +789,9 @@ def run_ours(args):
                    "pre_aging_note": "the time-blocked sweep replays 1..G pending steps per row during an engine's first G "
                                      "steps and G afterwards: a fresh engine runs G + 3 untimed steps before the W warm-up "
                                      "and K timed steps, so that the timed steps pay the constant (steady-state) cost",
-                   "board_state": "every K-step leg is a burst (W warm-up + K timed steps) that starts from a board that "
-                                  "idled %.1f s; ~0.1 s into continuous work the board is power limited and the same step "
-                                  "is 1.2-1.4x slower: `sustained` (>= 1 s of back-to-back steps) and "
-                                  "roofline.after_sustained report that regime" % IDLE_S,
+                   "board_state": "the K timed steps follow ~60 ms of untimed steps; `sustained` (>= 1 s of back-to-back "
+                                  "steps, board at its power cap) is 5-8 % slower, roofline.after_sustained is the dominant "
+                                  "kernel in that state",
                    "mean_items_per_set": main["nnz_mean"] / B,
                    "l2": "per-step working set %.2f GB per GPU >> 126 MB L2 (no flush needed)"
                          % (main["step_moved_bytes_per_gpu"] / 1e9)},

@@ -37,8 +37,8 @@ for target in [int(x) for x in os.environ.get("AGES", "0,30,60,100,160,260").spl
     age0 = eng.steps_done
     b = burst()
     torch.cuda.synchronize(); time.sleep(1.5)
-    bench.IDLE_S = 0.0
-    r = bench.k3_roofline(ctx, eng, B, V, from_idle=False)
+    pass
+    r = bench.k3_roofline(ctx, eng, B, V)
     time.sleep(1.0)
     tl = bench.step_timeline(eng, dev, B)
     print("age %3d: burst %.3f ms/step | K3 alone %.3f ms | isolated step: K3 %.0f sweep %.0f span %.0f us"
