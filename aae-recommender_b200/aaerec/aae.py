@@ -1,18 +1,19 @@
 """``aaerec.aae`` of the overlay: the reference module's namespace with the hot-path classes replaced.
 
-``from aaerec.aae import AAERecommender, DecodingRecommender`` (main.py:13) keeps working: names the B200 package
-does not provide (``DecodingRecommender``, ``Encoder`` ...) come from the reference's own ``aae.py`` when it is
-importable; ``AAERecommender``, ``AdversarialAutoEncoder`` and ``AutoEncoder`` are the CUDA-backed ones.
+``from aaerec.aae import AAERecommender, DecodingRecommender`` (main.py:13) keeps working: ``AAERecommender``,
+``AdversarialAutoEncoder``, ``AutoEncoder`` and ``DecodingRecommender`` are the CUDA-backed ones; names the B200 package
+does not provide (``Encoder``, ``Decoder`` ...) come from the reference's own ``aae.py`` when it is importable.
 """
 import importlib.util
 import os
 import sys
 
 from aaerec_b200.aae import AAERecommender, AdversarialAutoEncoder, AutoEncoder  # noqa: F401
+from aaerec_b200.decoding import DecodingRecommender  # noqa: F401
 
 from . import REFERENCE_DIR
 
-_B200 = ("AAERecommender", "AdversarialAutoEncoder", "AutoEncoder")
+_B200 = ("AAERecommender", "AdversarialAutoEncoder", "AutoEncoder", "DecodingRecommender")
 reference_module = None
 if REFERENCE_DIR is not None:
     _name = __package__ + "._reference_aae"

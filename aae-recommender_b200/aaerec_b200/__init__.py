@@ -9,7 +9,7 @@ from .condition import (ConditionList, ConditionBase, ConcatenationBasedConditio
 
 __all__ = ["Recommender", "ConditionList", "ConditionBase", "ConcatenationBasedConditioning",
            "PrecomputedEmbeddingCondition", "AAERecommender", "AdversarialAutoEncoder", "AutoEncoder", "AAEEngine",
-           "DAERecommender", "DenoisingAutoEncoder"]
+           "DAERecommender", "DenoisingAutoEncoder", "DecodingRecommender", "VAERecommender", "VAE"]
 
 
 def __getattr__(name):
@@ -19,6 +19,12 @@ def __getattr__(name):
     if name in ("DAERecommender", "DenoisingAutoEncoder"):
         from . import dae
         return getattr(dae, name)
+    if name == "DecodingRecommender":
+        from .decoding import DecodingRecommender
+        return DecodingRecommender
+    if name in ("VAERecommender", "VAE"):
+        from . import vae
+        return getattr(vae, name)
     if name == "AAEEngine":
         from .engine import AAEEngine
         return AAEEngine

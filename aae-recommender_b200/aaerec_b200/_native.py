@@ -96,6 +96,12 @@ _SIGS = {
     "aae_peer_allreduce": (I, [AaePeers, I, P, I, P, I, I64, P]),
     "aae_peer_error": (I, [P, C.POINTER(I)]),
     "aae_peer_bag_allreduce": (I, [AaePeers, I, P, P, I, P, P, I, I, I, I, P, I64, P]),
+    "aae_decoder_fwd": (I, [AaeDims, P, P, AaeDrop, AaeDrop, P, P, P, P, I, P]),
+    "aae_decoder_bwd": (I, [AaeDims, P, P, AaeDrop, AaeDrop, P, P, P, P, P, P]),
+    "aae_decoder_wgrad": (I, [AaeDims, P, P, P, P, P, AdamBlock, P, P]),
+    "aae_vae_fwd": (I, [AaeDims, AaeBag, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "aae_vae_bwd": (I, [AaeDims, P, P, P, P, P, P, P, P, P, P, P]),
+    "aae_vae_wgrad": (I, [AaeDims, P, P, P, P, P, P, P, AdamBlock, AdamBlock, P, P]),
     "aae_trace_set": (I, [P]),
     "aae_trace_slots": (I, []),
 }

@@ -151,6 +151,10 @@ class _OptimView(object):
 class AdversarialAutoEncoder(object):
     """ Adversarial Autoencoder (aae.py:589) """
     adversarial = True
+    _announce = True       # fit() prints the reference's "Using condition, code size" line (aae.py:776-780)
+
+    def _log_losses(self, losses):
+        log_losses(*losses)
 
     def __init__(self,
                  n_hidden=100,
@@ -333,7 +337,7 @@ class AdversarialAutoEncoder(object):
                                     cond_on_device=leaves is not None)
         self._cond_end(leaves, B)
         if self.verbose:
-            log_losses(*self.losses())
+            self._log_losses(self.losses())
         return self
 
     def _phase(self, phase, batch, condition_data):
@@ -392,10 +396,12 @@ class AdversarialAutoEncoder(object):
         use_condition = _check_conditions(self.conditions, condition_data)
         if use_condition:
             code_size = self.n_code + self.conditions.size_increment()
-            print(("" if self.adversarial else "[ae] ") + "Using condition, code size:", code_size)
+            if self._announce:
+                print(("" if self.adversarial else "[ae] ") + "Using condition, code size:", code_size)
         else:
             code_size = self.n_code
-            print(("" if self.adversarial else "[ae] ") + "Not using condition, code size:", code_size)
+            if self._announce:
+                print(("" if self.adversarial else "[ae] ") + "Not using condition, code size:", code_size)
         X = _canonical_csr(X, "training matrix")
         self._build(X.shape[1], code_size)
         eng = self.engine
@@ -437,7 +443,7 @@ class AdversarialAutoEncoder(object):
                     if self.record_losses:
                         self.loss_history.append(cur)
                     if self.verbose:
-                        log_losses(*cur)
+                        self._log_losses(cur)
             if self.verbose:
                 print()
             torch.cuda.synchronize(eng.dev)

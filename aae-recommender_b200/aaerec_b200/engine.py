@@ -88,6 +88,17 @@ class _Branch(object):
 
 
 class AAEEngine(object):
+    has_encoder = True      # False: no sparse first layer / W1t (the decoder-only engine of engine_siblings.py)
+
+    def enc_sizes(self):
+        return enc_block_sizes(self.H, self.C)
+
+    def dec_sizes(self):
+        return dec_block_sizes(self.H, self.Cp)
+
+    def disc_sizes(self):
+        return disc_block_sizes(self.H, self.C)
+
     def __init__(self, n_items, n_hidden=100, n_code=50, cond_dim=0, gen_lr=1e-3, reg_lr=1e-3,
                  dropout=(.2, .2), prior_scale=None, normalize_inputs=True, device=None,
                  rank=0, world=1, group=None, impl="auto", seed=0, max_batch=128, max_nnz=None,
@@ -143,15 +154,16 @@ class AAEEngine(object):
         z = lambda *s: torch.zeros(*s, **f32)
         # inference-only engines (set-sharded predict replicas) carry the weights without the six [V,H] Adam tensors
         zm = (lambda *s: torch.zeros(*((1,) + tuple(s[1:])), **f32)) if self.inference_only else z
-        self.W1t = z(Vl, H)
-        self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2 = (zm(Vl, H) for _ in range(4))
+        Vw = Vl if self.has_encoder else 1
+        self.W1t = z(Vw, H)
+        self.W1_m1, self.W1_v1, self.W1_m2, self.W1_v2 = (zm(Vw, H) for _ in range(4))
         self.Wd3 = z(Vl, H)
         self.Wd3_m, self.Wd3_v = (zm(Vl, H) for _ in range(2))
         self.bd3 = z(Vl)
         self.bd3_m, self.bd3_v = (zm(Vl) for _ in range(2))
-        self.n_enc = sum(s for _, s in enc_block_sizes(H, Cc))
-        self.n_dec = sum(s for _, s in dec_block_sizes(H, Cp))
-        self.n_disc = sum(s for _, s in disc_block_sizes(H, Cc))
+        self.n_enc = max(1, sum(s for _, s in self.enc_sizes()))
+        self.n_dec = max(1, sum(s for _, s in self.dec_sizes()))
+        self.n_disc = max(1, sum(s for _, s in self.disc_sizes()))
         self.enc, self.enc_m1, self.enc_v1, self.enc_m2, self.enc_v2, self.g_enc = (z(self.n_enc) for _ in range(6))
         self.dec, self.dec_m, self.dec_v, self.g_dec = (z(self.n_dec) for _ in range(4))
         self.disc, self.disc_m, self.disc_v, self.g_disc = (z(self.n_disc) for _ in range(4))

@@ -344,6 +344,40 @@ int aae_batch_gather(const int64_t* indptr_all, const int32_t* indices_all, cons
 int aae_batch_corrupt(const int32_t* in_indptr, const int32_t* in_indices, int B, int V, float p, const float* noise,
                       const aae_step_state* st, int32_t* out_indptr, int32_t* out_indices, void* stream);
 
+/* ---- sibling recommenders on the same decoder output layer -------------------------------
+ * DecodingRecommender (aae.py:461-584): "only the decoder part of the AAE" -- the reference's Decoder (aae.py:149-178)
+ * fed with the concatenated condition encodings inp [B,D] (aae.py:499-507), BCE against the item sets, one Adam
+ * (aae.py:522-523).  d.C must be 0, d.D = input width.  dec block: [Wd1 (H*D) | bd1 (H) | Wd2 (H*H) | bd2 (H)];
+ * lin3 + sigmoid + BCE + its backward + Adam is aae_dec_out_train, predict ranks h2 through the K5 entry points.
+ *   aae_decoder_fwd  : h2 = relu(drop(lin2(relu(drop(lin1(inp))))))  (train == 0: eval mode, dd1 may be NULL)
+ *   aae_decoder_bwd  : dh2 -> g_d2, g_d1 (pre-activation gradients)
+ *   aae_decoder_wgrad: weight / bias gradients of lin1, lin2 (+ Adam in place, as aae_ae_wgrad) */
+int aae_decoder_fwd(aae_dims d, const float* inp, const float* dec, aae_drop d1, aae_drop d2, const aae_step_state* st,
+                    float* dd1, float* h2, float* dh2_zero, int train, void* stream);
+int aae_decoder_bwd(aae_dims d, const float* dh2, const float* dec, aae_drop d1, aae_drop d2, const aae_step_state* st,
+                    const float* dd1, const float* h2, float* g_d2, float* g_d1, void* stream);
+int aae_decoder_wgrad(aae_dims d, const float* inp, const float* dd1, const float* g_d2, const float* g_d1,
+                      float* g_dec, aae_adam_block dec_opt, const aae_step_state* st, void* stream);
+/* VAE (vae.py:47-266): fc1 (the sparse first layer: W1t gather, as aae_bag) -> relu -> fc21 | fc22 -> z = eps *
+ * exp(logvar/2) + mu (vae.py:107-110) -> [z | cond] -> fc3 -> relu -> fc4 (= Wd3/bd3: aae_dec_out_train / K5); loss =
+ * BCE + KLD (vae.py:132-145), ONE Adam over all parameters (vae.py:90-91).  No dropout.
+ * enc block: [b1 (H) | Wml (2C*H) | bml (2C)] (rows 0..C-1 of Wml = fc21.weight, C..2C-1 = fc22.weight),
+ * dec block: [W3 (H*(C+D)) | b3 (H)].
+ *   aae_vae_fwd : eps [B,C] != NULL: the reference's randn draws (oracle-RNG mode), NULL: in-kernel Philox.  Writes
+ *                 a1 = relu(fc1), mulv = (mu | logvar) [B,2C], eps_used, zc, h3 (any of the first four may be NULL in
+ *                 predict) and adds KLD = -0.5 sum(1 + logvar - mu^2 - exp(logvar)) to kld_sum[0] (may be NULL).
+ *   aae_vae_bwd : dh3 -> g_3 (fc3 pre-activation), g_ml = (dmu | dlogvar) incl. the KLD gradient, g_h1 (fc1
+ *                 pre-activation; aae_w1_rows_update applies it to the touched rows of W1t)
+ *   aae_vae_wgrad: gradients of b1, fc21/fc22, fc3 (+ Adam in place) */
+int aae_vae_fwd(aae_dims d, aae_bag bag, const float* h1pre, const float* cond, const float* eps, const float* enc,
+                const float* dec, const aae_step_state* st, float* a1, float* mulv, float* eps_used, float* zc,
+                float* h3, float* dh3_zero, double* kld_sum, void* stream);
+int aae_vae_bwd(aae_dims d, const float* dh3, const float* enc, const float* dec, const float* eps_used, const float* a1,
+                const float* mulv, const float* h3, float* g_3, float* g_ml, float* g_h1, void* stream);
+int aae_vae_wgrad(aae_dims d, const float* a1, const float* zc, const float* g_3, const float* g_ml, const float* g_h1,
+                  float* g_enc, float* g_dec, aae_adam_block enc_opt, aae_adam_block dec_opt,
+                  const aae_step_state* st, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end call): copies a CSR batch from pinned host memory. */
 int aae_upload_batch(const int32_t* indptr_host, const int32_t* indices_host, int B, int nnz, int32_t* indptr,
                      int32_t* indices, void* stream);

@@ -3,7 +3,9 @@
 This file is the *oracle*: a dense, autograd-free, float32 restatement of what
 ``/root/reference/aaerec/aae.py`` computes for one ``partial_fit`` (reconstruction,
 discriminator and generator phases), for ``predict`` and for the ranking tail
-(``remove_non_missing`` + ``argtopk``).  It exists to check the CUDA kernels; it is
+(``remove_non_missing`` + ``argtopk``), plus the sibling models that share the decoder
+output layer: AutoEncoder, DenoisingAutoEncoder (dae.py), DecodingRecommender (aae.py:461-584)
+and VAE (vae.py:47-266).  It exists to check the CUDA kernels; it is
 never imported by the product package.  Only ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s CPU-baseline legs may import it.
 
@@ -350,6 +352,106 @@ def draw_dae_rng(B, V, n_hidden, n_code, dropout=(.2, .2)):
     r = {"noise": torch.rand((B, V))}
     r.update(draw_step_rng(B, n_hidden, n_code, dropout, adversarial=False))
     return r
+
+
+class OracleDecoder(object):
+    """DecodingRecommender (aae.py:461-584): the reference's ``Decoder`` (aae.py:149-178: lin1 -> drop -> relu -> lin2 ->
+    drop -> relu -> lin3 -> sigmoid) on the concatenated condition encodings (aae.py:495-507), BCE(y_pred + TINY,
+    y + TINY) (aae.py:510), one Adam at ``lr`` over the mlp's parameters (aae.py:522-523).  ``params``: lin1/lin2/lin3."""
+
+    def __init__(self, params, lr=0.001):
+        self.net = OracleAAE.__new__(OracleAAE)
+        self.net.p = {"dec." + k: torch.as_tensor(np.asarray(v)).clone().float() for k, v in params.items()}
+        self.optim = Adam(_names(DEC), lr)
+
+    @property
+    def p(self):
+        return {k[4:]: v for k, v in self.net.p.items()}
+
+    def partial_fit(self, cond, Y, rng=None):
+        """aae.py:490-520.  cond: list of [B, D_i] float matrices (concatenated in order); Y dense [B,V] 0/1;
+        rng['ae_dec'] = the two dropout masks (Decoder.drop1, drop2)."""
+        inp = torch.cat([torch.as_tensor(np.asarray(c), dtype=torch.float32) for c in cond], dim=1)
+        Y = torch.as_tensor(np.asarray(Y), dtype=torch.float32)
+        masks = (rng or NO_DROPOUT)["ae_dec"]
+        x, cache = self.net._mlp3_fwd("dec", inp, masks)
+        xin, tin, N = x + TINY, Y + TINY, Y.numel()
+        loss = ((tin - 1) * torch.log1p(-xin).clamp_min(-100) - tin * torch.log(xin).clamp_min(-100)).mean()
+        dx = (xin - tin) / ((1 - xin) * xin).clamp_min(1e-12) / N
+        grads = {}
+        self.net._mlp3_bwd("dec", dx * (1 - x) * x, cache, masks, grads)
+        self.optim.step(self.net.p, grads)
+        return float(loss)
+
+    def predict(self, cond):
+        """aae.py:555-584 for one batch (eval mode)."""
+        inp = torch.cat([torch.as_tensor(np.asarray(c), dtype=torch.float32) for c in cond], dim=1)
+        return self.net._mlp3_fwd("dec", inp, (None, None))[0].numpy()
+
+
+VAE_LAYERS = ("fc1", "fc21", "fc22", "fc3", "fc4")
+
+
+class OracleVAE(object):
+    """VAE (vae.py:47-266), dense and autograd-free: h1 = relu(fc1(normalize(x))); mu, logvar = fc21(h1), fc22(h1);
+    z = eps * exp(logvar / 2) + mu (vae.py:103-110); conditions concatenated on z (vae.py:120-123); recon =
+    sigmoid(fc4(relu(fc3(z)))); loss = BCELoss()(recon, x) [mean: the later ``size_average = False`` assignment is
+    inert, vae.py:127-130] + KLD, KLD = -0.5 * sum(1 + logvar - mu^2 - exp(logvar)) (vae.py:136-143); one Adam over all
+    parameters (vae.py:90-91).  ``eps`` = the step's ``torch.randn_like(std)`` draw."""
+
+    def __init__(self, params, n_code=50, lr=0.001, normalize_inputs=True):
+        self.p = {k: torch.as_tensor(np.asarray(v)).clone().float() for k, v in params.items()}
+        self.n_code = n_code
+        self.normalize_inputs = normalize_inputs
+        self.optim = Adam(_names(VAE_LAYERS), lr)
+
+    def _fwd(self, X, cond, eps):
+        p = self.p
+        Xn = X / X.abs().sum(1, keepdim=True).clamp_min(1e-12) if self.normalize_inputs else X
+        pre1 = _linear(Xn, p["fc1.weight"], p["fc1.bias"])
+        h1 = torch.relu(pre1)
+        mu = _linear(h1, p["fc21.weight"], p["fc21.bias"])
+        lv = _linear(h1, p["fc22.weight"], p["fc22.bias"])
+        std = (lv * 0.5).exp()
+        z = eps * std + mu
+        zc = z if cond is None else torch.cat([z] + list(cond), dim=1)
+        pre3 = _linear(zc, p["fc3.weight"], p["fc3.bias"])
+        h3 = torch.relu(pre3)
+        x = torch.sigmoid(_linear(h3, p["fc4.weight"], p["fc4.bias"]))
+        return x, (Xn, pre1, h1, mu, lv, std, zc, pre3, h3)
+
+    def partial_fit(self, X, cond=None, eps=None):
+        """vae.py:147-186; returns the step's loss (BCE mean + KLD sum) as the reference computes it."""
+        p = self.p
+        X = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+        eps = torch.as_tensor(np.asarray(eps), dtype=torch.float32)
+        if cond is not None:
+            cond = [torch.as_tensor(np.asarray(c), dtype=torch.float32) for c in cond]
+        x, (Xn, pre1, h1, mu, lv, std, zc, pre3, h3) = self._fwd(X, cond, eps)
+        N = X.numel()
+        bce = ((X - 1) * torch.log1p(-x).clamp_min(-100) - X * torch.log(x).clamp_min(-100)).mean()
+        kld = -0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp())
+        dpre4 = (x - X) / ((1 - x) * x).clamp_min(1e-12) / N * (1 - x) * x
+        g = {"fc4.weight": dpre4.t() @ h3, "fc4.bias": dpre4.sum(0)}
+        dpre3 = (dpre4 @ p["fc4.weight"]) * (pre3 > 0).float()
+        g["fc3.weight"], g["fc3.bias"] = dpre3.t() @ zc, dpre3.sum(0)
+        dz = (dpre3 @ p["fc3.weight"])[:, : self.n_code]
+        dmu = dz + mu
+        dlv = dz * eps * 0.5 * std + 0.5 * (lv.exp() - 1)
+        g["fc21.weight"], g["fc21.bias"] = dmu.t() @ h1, dmu.sum(0)
+        g["fc22.weight"], g["fc22.bias"] = dlv.t() @ h1, dlv.sum(0)
+        dpre1 = (dmu @ p["fc21.weight"] + dlv @ p["fc22.weight"]) * (pre1 > 0).float()
+        g["fc1.weight"], g["fc1.bias"] = dpre1.t() @ Xn, dpre1.sum(0)
+        self.optim.step(p, g)
+        return float(bce + kld)
+
+    def predict(self, X, cond=None, eps=None):
+        """vae.py:231-266 for one batch: the full forward, sampling included."""
+        X = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+        eps = torch.as_tensor(np.asarray(eps), dtype=torch.float32)
+        if cond is not None:
+            cond = [torch.as_tensor(np.asarray(c), dtype=torch.float32) for c in cond]
+        return self._fwd(X, cond, eps)[0].numpy()
 
 
 def fit_epoch_order(n):

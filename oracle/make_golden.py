@@ -132,6 +132,131 @@ def run_case(ref, name, n, V, H, C, B, epochs, dropout, cond_dim=0, data_seed=0,
     return out
 
 
+def _matrix_condition(ref, dim):
+    class MatrixCondition(ref.condition.ConcatenationBasedConditioning):
+        """precomputed float rows, concatenated on the code (condition.py:300-316, 363-369)"""
+
+        def __init__(self, d):
+            self._d = d
+
+        def encode(self, inputs):
+            return torch.as_tensor(inputs, dtype=torch.float32)
+
+        def size_increment(self):
+            return self._d
+    return ref.condition.ConditionList([("title", MatrixCondition(dim))])
+
+
+def run_vae_case(ref, name, n, V, H, C, B, epochs, cond_dim=0, data_seed=0, mean_len=6, k=10, lr=0.001):
+    """aaerec/vae.py:47-266: the UNMODIFIED reference VAE -- construction, fit, predict.  Per-step losses
+    are captured by wrapping ``loss_function``; predict is run after ``torch.manual_seed(123)`` so that its eval-mode
+    reparametrisation draws (vae.py:252-256) can be replayed."""
+    import aaerec.vae
+    cls = aaerec.vae.VAE
+    X = synth_sets(n, V, mean_len, min_len=2, seed=data_seed)
+    cond = conditions = cond_data = None
+    if cond_dim:
+        cond = (np.random.RandomState(data_seed + 1).randn(n, cond_dim) * 0.5).astype(np.float32)
+        conditions = _matrix_condition(ref, cond_dim)
+        cond_data = [cond]
+    losses = []
+    orig = cls.loss_function
+
+    def recording(self, *a, **kw):
+        val = orig(self, *a, **kw)
+        losses.append(float(val))
+        return val
+    cls.loss_function = recording
+    try:
+        torch.manual_seed(42)      # vae.py:30 executes this at import; redo it per case
+        np.random.seed(42)
+        model = cls(V, V, n_hidden=H, n_code=C, lr=lr, batch_size=B, n_epochs=epochs, conditions=conditions,
+                    verbose=False, device=torch.device("cpu"))
+        init = {k_: v.detach().cpu().numpy().copy() for k_, v in model.state_dict().items()}
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.fit(X, condition_data=cond_data)
+        n_fit = len(losses)
+        final = {k_: v.detach().cpu().numpy().copy() for k_, v in model.state_dict().items()}
+        torch.manual_seed(123)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pred = model.predict(X[:40], condition_data=[cond[:40]] if cond_dim else None)
+    finally:
+        cls.loss_function = orig
+    masked = ref.evaluation.remove_non_missing(pred, X[:40].toarray(), copy=True)
+    out = dict(n=n, V=V, H=H, C=C, B=B, epochs=epochs, cond_dim=cond_dim, k=k, lr=np.float64(lr), predict_seed=123,
+               indptr=X.indptr.astype(np.int32), indices=X.indices.astype(np.int32),
+               losses=np.asarray(losses[:n_fit], dtype=np.float64), pred=pred.astype(np.float32),
+               topk=ref.evaluation.argtopk(masked, k)[1].astype(np.int64))
+    if cond_dim:
+        out["cond"] = cond
+    for k_, v in init.items():
+        out["init/" + k_] = v
+    for k_, v in final.items():
+        out["final/" + k_] = v
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "steps", n_fit, "first", losses[0], "last", losses[n_fit - 1])
+
+
+def run_decoder_case(ref, name, n, V, H, D, B, epochs, dropout, data_seed=0, mean_len=6, k=10, lr=0.001):
+    """aaerec/aae.py:461-584: the UNMODIFIED reference DecodingRecommender -- ``fit(condition_data, Y)``
+    and ``predict(test_set)`` on a minimal Bags stand-in.  Per-step losses are captured by wrapping the module's
+    ``F.binary_cross_entropy``."""
+    aae = ref.aae
+    Y = synth_sets(n, V, mean_len, min_len=2, seed=data_seed)
+    cond = (np.random.RandomState(data_seed + 1).randn(n, D) * 0.5).astype(np.float32)
+    conditions = _matrix_condition(ref, D)
+    losses = []
+    orig = aae.F.binary_cross_entropy
+
+    def recording(*a, **kw):
+        val = orig(*a, **kw)
+        losses.append(float(val))
+        return val
+
+    class QueryBags(object):
+        def __init__(self, rows):
+            self.rows = rows
+
+        def size(self, dim):
+            return self.rows
+
+        def get_attributes(self, keys):
+            return [cond[: self.rows]]
+
+        def tocsr(self):
+            return Y[: self.rows]
+    aae.F.binary_cross_entropy = recording
+    try:
+        torch.manual_seed(42)
+        np.random.seed(42)
+        rec = aae.DecodingRecommender(conditions, n_epochs=epochs, batch_size=B, n_hidden=H, lr=lr, verbose=False,
+                                      dropout=dropout)
+        # initial weights: replay the construction of Decoder(D, H, V) (aae.py:524-527) under the same seed
+        st = torch.get_rng_state()
+        dec0 = aae.Decoder(D, H, V, dropout=dropout)
+        init = {k_: v.detach().cpu().numpy().copy() for k_, v in dec0.state_dict().items()}
+        torch.set_rng_state(st)
+        with contextlib.redirect_stdout(io.StringIO()):
+            rec.fit([cond], Y)
+        n_fit = len(losses)
+        final = {k_: v.detach().cpu().numpy().copy() for k_, v in rec.mlp.state_dict().items()}
+        with contextlib.redirect_stdout(io.StringIO()):
+            pred = rec.predict(QueryBags(40))
+    finally:
+        aae.F.binary_cross_entropy = orig
+    masked = ref.evaluation.remove_non_missing(pred, Y[:40].toarray(), copy=True)
+    out = dict(n=n, V=V, H=H, D=D, B=B, epochs=epochs, dropout=np.asarray(dropout, dtype=np.float64), k=k,
+               lr=np.float64(lr), indptr=Y.indptr.astype(np.int32), indices=Y.indices.astype(np.int32), cond=cond,
+               losses=np.asarray(losses[:n_fit], dtype=np.float64), pred=pred.astype(np.float32),
+               topk=ref.evaluation.argtopk(masked, k)[1].astype(np.int64))
+    for k_, v in init.items():
+        out["init/" + k_] = v
+    for k_, v in final.items():
+        out["final/" + k_] = v
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "steps", n_fit, "first", losses[0], "last", losses[n_fit - 1])
+
+
 def ranking_case(ref):
     rs = np.random.RandomState(7)
     Y = rs.rand(9, 64).astype(np.float32)
@@ -178,7 +303,18 @@ def main():
              model_kwargs=dict(noise_factor=0.3))
     run_case(ref, "dae_h100_cond", n=96, V=520, H=100, C=50, B=32, epochs=2, dropout=(.2, .2), mean_len=8, cond_dim=7,
              dae=True)
-    ranking_case(ref)
+    # sibling models on the same decoder output layer
+    if "vae_small".startswith(only):
+        run_vae_case(ref, "vae_small", n=130, V=257, H=24, C=10, B=50, epochs=2)
+    if "vae_h100_cond".startswith(only):
+        run_vae_case(ref, "vae_h100_cond", n=96, V=520, H=100, C=50, B=32, epochs=2, mean_len=8, cond_dim=7)
+    if "decoder_small_dropout".startswith(only):
+        run_decoder_case(ref, "decoder_small_dropout", n=130, V=257, H=24, D=9, B=50, epochs=2, dropout=(.2, .2))
+    if "decoder_h100_nodrop".startswith(only):
+        run_decoder_case(ref, "decoder_h100_nodrop", n=96, V=520, H=100, D=30, B=32, epochs=2, dropout=(0, 0),
+                         mean_len=8)
+    if "ranking".startswith(only):
+        ranking_case(ref)
 
 
 if __name__ == "__main__":

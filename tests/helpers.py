@@ -76,3 +76,87 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ---- sibling models on the same decoder output layer -------------------------------------------------
+VAE_CASES = ["vae_small", "vae_h100_cond"]                         # aaerec/vae.py
+DECODER_CASES = ["decoder_small_dropout", "decoder_h100_nodrop"]   # DecodingRecommender, aaerec/aae.py:461-584
+
+
+def load_sibling_case(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g["X"] = sp.csr_matrix((np.ones(len(g["indices"]), dtype=np.float32), g["indices"], g["indptr"]),
+                           shape=(int(g["n"]), int(g["V"])))
+    for k in ("n", "V", "H", "C", "D", "B", "epochs", "cond_dim", "k", "predict_seed"):
+        if k in g:
+            g[k] = int(g[k])
+    g["lr"] = float(g["lr"])
+    if "dropout" in g:
+        g["dropout"] = tuple(float(x) for x in g["dropout"])
+    return g
+
+
+def linear_init(shapes):
+    """nn.Linear modules constructed in the given order on the CPU generator (stock init)."""
+    p = {}
+    for name, fin, fout in shapes:
+        lin = torch.nn.Linear(fin, fout)
+        p[name + ".weight"] = lin.weight.detach().clone()
+        p[name + ".bias"] = lin.bias.detach().clone()
+    return p
+
+
+def oracle_replay_vae(g):
+    """oracle.OracleVAE over a golden case as the reference runs it: VAE(...) construction under seed 42 (vae.py:76-87),
+    fit (vae.py:188-229), then predict of the first 40 rows under ``predict_seed``."""
+    from oracle import aae_oracle as O
+    V, H, C, B, Dc = g["V"], g["H"], g["C"], g["B"], g["cond_dim"]
+    cond = g.get("cond")
+    torch.manual_seed(42)
+    np.random.seed(42)
+    params = linear_init([("fc1", V, H), ("fc21", H, C), ("fc22", H, C), ("fc3", C + Dc, H), ("fc4", H, V)])
+    init = {k: v.clone() for k, v in params.items()}
+    model = O.OracleVAE(params, n_code=C, lr=g["lr"])
+    X = g["X"]
+    losses, steps = [], []
+    for _ in range(g["epochs"]):
+        perm = O.fit_epoch_order(X.shape[0])
+        Xs = X[perm]
+        cs = cond[perm] if cond is not None else None
+        for s in range(0, X.shape[0], B):
+            xb = Xs[s:s + B]
+            cb = [cs[s:s + B]] if cs is not None else None
+            eps = torch.randn((xb.shape[0], C), dtype=torch.float32)       # vae.py:109 on the CPU generator
+            losses.append(model.partial_fit(xb.toarray(), cb, eps))
+            steps.append((xb, cb, eps))
+    torch.manual_seed(g["predict_seed"])
+    preds = []
+    for s in range(0, 40, B):
+        e = min(s + B, 40)
+        eps = torch.randn((e - s, C), dtype=torch.float32)
+        preds.append(model.predict(X[s:e].toarray(), [cond[s:e]] if cond is not None else None, eps))
+    return model, np.asarray(losses), np.vstack(preds), init, steps
+
+
+def oracle_replay_decoder(g):
+    """oracle.OracleDecoder over a golden case as DecodingRecommender.fit runs it (aae.py:522-545)."""
+    from oracle import aae_oracle as O
+    V, H, D, B = g["V"], g["H"], g["D"], g["B"]
+    cond = g["cond"]
+    torch.manual_seed(42)
+    np.random.seed(42)
+    params = linear_init([("lin1", D, H), ("lin2", H, H), ("lin3", H, V)])
+    init = {k: v.clone() for k, v in params.items()}
+    model = O.OracleDecoder(params, lr=g["lr"])
+    Y = g["X"]
+    losses = []
+    for _ in range(g["epochs"]):
+        perm = O.fit_epoch_order(Y.shape[0])
+        Ys, cs = Y[perm], cond[perm]
+        for s in range(0, Y.shape[0], B):
+            yb = Ys[s:s + B]
+            b = yb.shape[0]
+            masks = (O.draw_masks((b, H), g["dropout"][0], 1)[0], O.draw_masks((b, H), g["dropout"][1], 1)[0])
+            losses.append(model.partial_fit([cs[s:s + B]], yb.toarray(), {"ae_dec": masks}))
+    pred = np.vstack([model.predict([cond[s:min(s + B, 40)]]) for s in range(0, 40, B)])
+    return model, np.asarray(losses), pred, init
