@@ -60,6 +60,20 @@ __device__ __forceinline__ void replay1(const float* __restrict__ ktab, const aa
   }
 }
 
+// Cold elements.  A zero-gradient step computes  m' = m - 0.1 m,  v' = beta2 v,  W' = fma(-step, m' / denom, W)  with
+// denom >= eps.  With |m| <= 2^-110, 1/denom <= 1e8 (eps >= 1e-8) and step <= 2^10 the increment of W is below 2^-73 in
+// magnitude: for |W| >= 2^-40 (ulp >= 2^-63) the fma rounds back to W exactly, and for m == +0 the increment is -0 and
+// W' == W for every W.  m decays by 0.9 per step, so an item's row turns cold ~650 steps after its last occurrence
+// (it never reaches 0: round-to-nearest parks it on a denormal) and stays cold until it is in a batch again.
+constexpr float kColdM = 7.7037198e-34f;     // 2^-110
+constexpr float kColdWMin = 9.0949470e-13f;  // 2^-40
+__device__ __forceinline__ bool cold4(const float4& m) {
+  return fmaxf(fmaxf(fabsf(m.x), fabsf(m.y)), fmaxf(fabsf(m.z), fabsf(m.w))) <= kColdM;   // NaN -> false
+}
+__device__ __forceinline__ bool zero4(const float4& x) {      // all four are +0 (bit pattern 0; -0 does not qualify)
+  return (__float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w)) == 0u;
+}
+
 // One warp brings row r from step `from` to step `to` (to - from pending steps), lanes over the float4 columns.
 __device__ __forceinline__ void replay_row(size_t row_off, int H, int from, int to, float* __restrict__ W,
                                            float* __restrict__ m1, float* __restrict__ v1, float* __restrict__ m2,
@@ -157,6 +171,9 @@ __global__ void __launch_bounds__(T) w1_sweep_blocked_kernel(const int32_t* __re
     k1.beta2 = k2.beta2 = st->beta2;
     k1.w2 = k2.w2 = (float)(1.0 - 0.999);
     k1.eps = k2.eps = st->eps;
+    // cold4()'s bound needs 1/denom <= 1/eps <= 1e8 and step sizes <= 2^10; the pending steps are earlier than step t,
+    // their step sizes (lr / (1 - 0.9^t)) at most 10x the current ones
+    const bool cold_ok = st->eps >= 1e-8f && st->step_size_gen <= 1.0f && st->step_size_reg <= 1.0f;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
       const int r = r0 + (int)(e / H4);
       if (!flush && __ldg(slot_of + r) >= 0) continue;
@@ -164,11 +181,37 @@ __global__ void __launch_bounds__(T) w1_sweep_blocked_kernel(const int32_t* __re
       const int n = to - from;
       if (n <= 0) continue;
       const size_t q = (size_t)r0 * H4 + (size_t)e;
-      float4 p = __ldcs(reinterpret_cast<const float4*>(W) + q);
       float4 a = __ldcs(reinterpret_cast<const float4*>(m1) + q);
       float4 b = __ldcs(reinterpret_cast<const float4*>(v1) + q);
       float4 c = __ldcs(reinterpret_cast<const float4*>(m2) + q);
       float4 d = __ldcs(reinterpret_cast<const float4*>(v2) + q);
+      float4 p;
+      if (cold_ok && cold4(a) && cold4(c)) {
+        // Cold elements (long-tail items: never in a batch, or not for hundreds of steps).  See cold4(): W cannot
+        // change, so the sqrt / reciprocal / W update of every pending step is skipped; the moments still decay
+        // through the same fp32 operations in the same order.  Results are bit-identical to the full replay.
+        if (zero4(a) && zero4(c) && zero4(b) && zero4(d)) continue;    // never touched: every update is the identity
+        bool w_safe = zero4(a) && zero4(c);
+        if (!w_safe) {
+          p = __ldcs(reinterpret_cast<const float4*>(W) + q);
+          w_safe = fminf(fminf(fabsf(p.x), fabsf(p.y)), fminf(fabsf(p.z), fabsf(p.w))) >= kColdWMin;
+        }
+        if (w_safe) {
+          for (int j = 1; j <= n; ++j) {
+            a.x = fmaf(k1.w1, -a.x, a.x); a.y = fmaf(k1.w1, -a.y, a.y); a.z = fmaf(k1.w1, -a.z, a.z); a.w = fmaf(k1.w1, -a.w, a.w);
+            c.x = fmaf(k2.w1, -c.x, c.x); c.y = fmaf(k2.w1, -c.y, c.y); c.z = fmaf(k2.w1, -c.z, c.z); c.w = fmaf(k2.w1, -c.w, c.w);
+            b.x *= k1.beta2; b.y *= k1.beta2; b.z *= k1.beta2; b.w *= k1.beta2;
+            d.x *= k2.beta2; d.y *= k2.beta2; d.z *= k2.beta2; d.w *= k2.beta2;
+          }
+          __stcs(reinterpret_cast<float4*>(m1) + q, a);
+          __stcs(reinterpret_cast<float4*>(v1) + q, b);
+          __stcs(reinterpret_cast<float4*>(m2) + q, c);
+          __stcs(reinterpret_cast<float4*>(v2) + q, d);
+          continue;
+        }
+      } else {
+        p = __ldcs(reinterpret_cast<const float4*>(W) + q);
+      }
       for (int j = 1; j <= n; ++j) {       // the same operations in the same order as replay4
         const float4 kk = __ldg(reinterpret_cast<const float4*>(ktab) + ((from + j) & (AAE_KTAB_SLOTS - 1)));
         k1.step_size = kk.x; k2.step_size = kk.y;

@@ -482,12 +482,30 @@ def step_bytes(eng):
     return (24.0 + 40.0 / eng.w1_groups) * eng.Vloc * H
 
 
-def train_workload(ctx, name, K, W, with_roofline=True, with_sustained=True, B=None, cond_dim=0, with_e2e=True):
-    """value / e2e / roofline of one training workload; returns (dict, engine, batches)."""
+COLD_M = 2.0 ** -110      # csrc/w1_blocked.cu kColdM
+
+
+def w1_cold_row_frac(eng):
+    """Fraction of this rank's W1 rows whose first moments (both optimizers) are all cold (|m| <= 2^-110, incl. rows
+    that never were in a batch): the time-blocked sweep skips the W update of those rows (exactly)."""
+    cold = (eng.W1_m1.abs().amax(1) <= COLD_M) & (eng.W1_m2.abs().amax(1) <= COLD_M)
+    return float(cold.float().mean().item())
+
+
+def train_workload(ctx, name, K, W, with_roofline=True, with_sustained=True, B=None, cond_dim=0, with_e2e=True,
+                   hot_w1=False):
+    """value / e2e / roofline of one training workload; returns (dict, engine, batches).  hot_w1: every W1 row starts
+    with live Adam moments (as if every item had been in a recent batch): the worst case of the time-blocked sweep,
+    none of its rows is cold."""
     import torch
     n_batches = min(K + W, 32 if WORKLOADS[name][0] > 500000 else 64)
     _, batches, V, B = make_batches(name, n_batches, cond_dim=cond_dim, B=B)
     eng = ctx.engine(V, B, batches, cond_dim=cond_dim)
+    if hot_w1:
+        g = torch.Generator(device=eng.dev).manual_seed(5)
+        for m, v in ((eng.W1_m1, eng.W1_v1), (eng.W1_m2, eng.W1_v2)):
+            m.normal_(0.0, 1e-3, generator=g)
+            v.uniform_(1e-7, 1e-6, generator=g)
     dev_batches = [tuple(torch.as_tensor(x, device=eng.dev) for x in (ip, ii) + ((cc,) if cc is not None else ()))
                    for ip, ii, cc in batches]
     from aaerec_b200 import _native as N
@@ -535,6 +553,7 @@ def train_workload(ctx, name, K, W, with_roofline=True, with_sustained=True, B=N
             hot = k3_roofline(ctx, eng, B, V)
             out["roofline"]["after_sustained"] = {"ms": hot["ms"], "achieved": hot["achieved"], "frac": hot["frac"]}
     out["nnz_mean"] = float(np.mean([len(b[1]) for b in batches]))
+    out["w1_cold_row_frac"] = w1_cold_row_frac(eng)
     return out, eng, batches
 
 
@@ -668,6 +687,16 @@ def run_ours(args):
     main, eng, batches = train_workload(ctx, head, K, W)
     clocks = sampler.stop() if sampler else None
     V, B = eng.V, WORKLOADS[head][5]
+
+    def hot_leg():
+        # the same K steps with every W1 row hot (live Adam moments everywhere): the other end of the bracket
+        h, e, _ = train_workload(ctx, head, K, W, with_roofline=False, with_sustained=False, with_e2e=False, hot_w1=True)
+        e.close()
+        del e
+        torch.cuda.empty_cache()
+        return {"value": h["value"], "unit": "sets/s", "ms_per_step": h["ms_per_step"], "steps": K,
+                "w1_cold_row_frac": h["w1_cold_row_frac"]}
+    hot = hot_leg() if (args.no_extra and world == 1) else None
     exchange, graph, groups = eng._exchange_kind, eng.use_graph, eng.w1_groups
     if args.kernel_times and world == 1:
         from aaerec_b200 import _native as N
@@ -723,6 +752,7 @@ def run_ours(args):
         eng.close()
         del eng
         torch.cuda.empty_cache()
+        hot = hot_leg()
         # ---------------- the other BASELINE configs as extra legs ----------------
         Ke = max(10, min(K, 50))
         if head == "mpd":
@@ -785,6 +815,15 @@ def run_ours(args):
                    "decoder_kernel": main["decoder_kernel"], "cuda_graph": graph,
                    "rng": "in-kernel Philox (native)",
                    "w1_policy": "dense-Adam-equivalent, time-blocked in %d groups (exact)" % groups,
+                   "w1_cold_rows": {"frac": main["w1_cold_row_frac"],
+                                    "note": "the sweep skips the W update of elements whose first moments are <= 2^-110 "
+                                            "(it cannot change W: bit-identical, tests/test_gpu_parity.py) -- rows that "
+                                            "never were in a batch or not for ~650 steps.  This run starts from fresh "
+                                            "moments and cycles through %d batches, so nearly every row outside them is "
+                                            "cold; `w1_all_rows_hot` is the same measurement with live moments in EVERY "
+                                            "row (no cold row at all), a long training run lies between the two "
+                                            "(DESIGN.md 4: ~55 %% of the rows cold under this Zipf law, more on real "
+                                            "long-tail catalogues)" % len(batches)},
                    "pre_aging_steps": groups + 3,
                    "pre_aging_note": "the time-blocked sweep replays 1..G pending steps per row during an engine's first G "
                                      "steps and G afterwards: a fresh engine runs G + 3 untimed steps before the W warm-up "
@@ -799,6 +838,7 @@ def run_ours(args):
         "roofline": dict(main["roofline"], step_moved_bytes=main["step_moved_bytes_per_gpu"],
                          step_frac=main["step_frac_timed"], step_frac_sustained=main["step_frac"]),
         "tensor_frac": main["tensor_frac"],
+        "w1_all_rows_hot": hot,
         "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "clocks": clocks,
     }
     if parity is not None:

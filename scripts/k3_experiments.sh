@@ -13,7 +13,7 @@ if [ "$1" = "build" ]; then
     name=${v%%:*}; defs=$(echo ${v#*:} | tr ',' ' ')
     ( nvcc $FLAGS $defs -c $CS/dec_out_tc.cu -o $VD/k3x_$name.o && \
       nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $VD/lib_k3x_$name.so $VD/k3x_$name.o \
-        $BD/api.o $BD/bag.o $BD/w1_blocked.o $BD/mlp.o $BD/dec_out_simt.o $BD/dec_out_select2.o $BD/topk.o $BD/peer.o && echo built $name ) &
+        $(ls $BD/*.o | grep -v /dec_out_tc.o) && echo built $name ) &
   done
   wait
 else

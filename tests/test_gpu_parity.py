@@ -275,3 +275,59 @@ def test_dae_native_corruption_drops_the_right_fraction():
             full = X.indices[X.indptr[r]:X.indptr[r + 1]]
             assert np.all(np.diff(row) > 0) and set(row.tolist()) <= set(full.tolist())
     assert np.array_equal(kept[0][0], kept[1][0]) and np.array_equal(kept[0][1], kept[1][1])
+
+
+def test_w1_sweep_cold_rows_bit_identical_to_full_replay():
+    """The time-blocked sweep skips the W update (sqrt / reciprocal / fma) of COLD elements -- first moments of
+    magnitude <= 2^-110, incl. never-touched rows -- because it cannot change W (w1_blocked.cu cold4).  Checked bit for
+    bit against the full replay (aae_w1_catchup replays every pending step with the complete Adam arithmetic) on
+    crafted rows: zero, tiny, denormal and negative-zero moments, weights below 2^-40, hot rows, and mixtures inside one
+    float4."""
+    import ctypes as C
+    from aaerec_b200 import _native as N
+    V, H, T = 4096, 100, 41
+    g = torch.Generator().manual_seed(7)
+    W = (torch.rand(V, H, generator=g) * 0.2 - 0.1)
+    m1 = torch.randn(V, H, generator=g) * 1e-3
+    v1 = torch.rand(V, H, generator=g) * 1e-5
+    m2 = torch.randn(V, H, generator=g) * 1e-3
+    v2 = torch.rand(V, H, generator=g) * 1e-5
+    kind = torch.arange(V) % 8
+    for m, v in ((m1, v1), (m2, v2)):
+        m[kind == 0] = 0.0; v[kind == 0] = 0.0                        # never touched
+        m[kind == 1] *= 1e-32                                          # cold (~1e-35), v alive
+        m[kind == 2] = 4 * 2.0 ** -149                                 # parked on a denormal
+        m[kind == 3] = -0.0; v[kind == 3] = 0.0                        # negative zero
+        m[kind == 4] = 0.0                                             # zero moment, v alive
+    m2[kind == 5] *= 1e-32                                             # cold in one optimizer only -> full path
+    W[kind == 1, ::7] = 1e-20                                          # tiny weights among cold moments -> full path
+    W[kind == 2, ::5] = 0.0
+    m1[kind == 6, ::4] *= 1e-32                                        # cold and hot elements inside one float4
+    # kind 7: ordinary hot rows
+    state = torch.zeros(48, dtype=torch.uint8, device="cuda")
+    ktab = torch.zeros(64 * 4, device="cuda")
+    N.call("aae_step_state_init", N.ptr(state), 1e-3, 1e-3, C.c_uint64(0), None)
+    for _ in range(T):
+        N.call("aae_step_tick", N.ptr(state), None)
+        N.call("aae_ktab_write", N.ptr(state), N.ptr(ktab), None)
+    dev = lambda *ts: [t.clone().cuda() for t in ts]
+    A = dev(W, m1, v1, m2, v2)
+    Bc = dev(W, m1, v1, m2, v2)
+    last_a = torch.zeros(V, dtype=torch.int32, device="cuda")
+    last_b = torch.zeros(V, dtype=torch.int32, device="cuda")
+    claim = torch.zeros(V, dtype=torch.int32, device="cuda")
+    # A: flush sweep (flat walk with the cold path), every row from step 0 to T-1
+    N.call("aae_w1_sweep_blocked", None, V, H, *[N.ptr(t) for t in A], N.ptr(last_a), N.ptr(state), N.ptr(ktab), 32, 1, 0,
+           None)
+    # B: the batch catch-up (full arithmetic), one "set" holding every item
+    indptr = torch.tensor([0, V], dtype=torch.int32, device="cuda")
+    indices = torch.arange(V, dtype=torch.int32, device="cuda")
+    N.call("aae_w1_catchup", N.ptr(indptr), N.ptr(indices), 1, 0, V, N.ptr(claim), *[N.ptr(t) for t in Bc], N.ptr(last_b),
+           H, N.ptr(state), N.ptr(ktab), None)
+    torch.cuda.synchronize()
+    assert torch.equal(last_a, last_b) and int(last_a.min()) == T - 1
+    for name, a, b in zip(("W", "m1", "v1", "m2", "v2"), A, Bc):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), name
+    # the replay did something: hot rows moved, never-touched rows did not
+    assert not torch.equal(A[0][kind == 7].cpu(), W[kind == 7])
+    assert torch.equal(A[0][kind == 0].cpu(), W[kind == 0])
