@@ -499,6 +499,10 @@ class AdversarialAutoEncoder(object):
         Multi-GPU: ``shard='items'`` ranks every query against the local item shard and merges the per-shard lists
         (one all-gather per batch); ``shard='sets'`` gives every rank a full-weight replica (built once) and its own
         slice of the query rows -- no communication in the query loop; the slices are exchanged at the end."""
+        if k is None or k > self.MAX_TOPK:
+            # argtopk's k=None / k >= size branch (evaluation.py:48-52): the full ranking of every row
+            return self._full_ranking(X, eng_k=k, condition_data=condition_data, mask_known=mask_known,
+                                      return_scores=return_scores)
         if shard == "sets" and self.engine.world > 1:
             return self._predict_topk_set_sharded(X, k, condition_data, mask_known, return_scores)
         eng = self.engine
@@ -518,6 +522,37 @@ class AdversarialAutoEncoder(object):
         return (idx, val) if return_scores else idx
 
 
+
+    MAX_TOPK = 4096       # envelope of the selection kernels (aae_masked_topk / aae_predict_topk2)
+
+    def _full_ranking(self, X, eng_k, condition_data, mask_known, return_scores):
+        """All items of every row in descending order of remove_non_missing(predict(X), X) -- ``argtopk(.., k=None)``
+        (evaluation.py:48-52), or its first ``k`` columns for a k beyond the selection kernels' envelope.  The [B, V]
+        logit matrix is built by the decoder kernel and sorted on the device (known items last, ties by lower item id);
+        this is the unbounded-metric convenience path, not the hot path: MRR / MAP over the whole vocabulary come from
+        ``evaluate_topk`` (rank counts), which never sorts."""
+        eng = self.engine
+        if eng.world > 1:
+            raise NotImplementedError("full rankings (k=None or k > %d) on item shards: use evaluate_topk for unbounded "
+                                      "metrics, or a single-GPU / set-sharded replica" % self.MAX_TOPK)
+        n, V = X.shape[0], eng.V
+        kk = V if eng_k is None else min(eng_k, V)
+        idx = np.empty((n, kk), dtype=np.int64)
+        val = np.empty((n, kk), dtype=np.float32) if return_scores else None
+        dev = torch.empty(self.batch_size, V, dtype=torch.float32, device=eng.dev)
+        for start, end, B in self._iter_batches(X, condition_data):
+            eng.scores(B, dev, apply_sigmoid=False)
+            sc = dev[:B]
+            if mask_known:
+                ip = eng.indptr[:B + 1].long()
+                cols = eng.indices[:int(ip[-1])].long()
+                rows = torch.repeat_interleave(torch.arange(B, device=eng.dev), ip[1:] - ip[:-1])
+                sc[rows, cols] = -float("inf")
+            v, i = torch.sort(sc, dim=1, descending=True, stable=True)
+            idx[start:end] = i[:, :kk].cpu().numpy()
+            if return_scores:
+                val[start:end] = v[:, :kk].cpu().numpy()
+        return (idx, val) if return_scores else idx
 
     def _predict_topk_set_sharded(self, X, k, condition_data, mask_known, return_scores):
         import torch.distributed as dist

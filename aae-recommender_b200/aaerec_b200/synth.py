@@ -11,10 +11,15 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def synth_sets(n, V, mean_len, min_len=2, max_len=None, seed=0, zipf=1.0, dtype=np.float32):
+def synth_sets(n, V, mean_len, min_len=2, max_len=None, seed=0, zipf=1.0, dtype=np.float32, len_choices=None):
+    """``len_choices``: draw each set's length uniformly from these values instead of clip(Poisson(mean_len)) -- the
+    MPD challenge's query sets hold 1 / 5 / 10 / 25 / 100 seed tracks (eval/mpd/create_dev_set.py:16-17)."""
     rs = np.random.RandomState(seed)
-    lens = rs.poisson(mean_len, n)
-    lens = np.clip(lens, min_len, max_len if max_len else None)
+    if len_choices is not None:
+        lens = rs.choice(np.asarray(len_choices, dtype=np.int64), size=n)
+    else:
+        lens = rs.poisson(mean_len, n)
+        lens = np.clip(lens, min_len, max_len if max_len else None)
     lens = np.minimum(lens, V).astype(np.int64)
     w = 1.0 / np.arange(1, V + 1, dtype=np.float64) ** zipf
     cdf = np.cumsum(w)

@@ -482,6 +482,7 @@ def step_bytes(eng):
     return (24.0 + 40.0 / eng.w1_groups) * eng.Vloc * H
 
 
+MPD_QUERY_LENS = (1, 5, 10, 25, 100)     # seed-track counts of the MPD challenge (create_dev_set.py:16-17)
 COLD_M = 2.0 ** -110      # csrc/w1_blocked.cu kColdM
 
 
@@ -721,10 +722,11 @@ def run_ours(args):
         if head == "mpd":
             sweep = {}
             for Bq in (1000, 4000, 16000, 64000):
-                Xq = synth_sets(Bq, V, 25, 1, 100, seed=4321)
+                Xq = synth_sets(Bq, V, 25, 1, 100, seed=4321, len_choices=MPD_QUERY_LENS)
                 pr = predict_leg(ctx, eng, Xq, 100, 5 if Bq <= 4000 else 2)
-                pr["config"] = {"workload": "mpd-shaped (BASELINE configs[4]): V=%d items, query batch %d sets, k=100, "
-                                            "known items masked, item-sharded x%d" % (V, Bq, world)}
+                pr["config"] = {"workload": "mpd-shaped (BASELINE configs[4]): V=%d items, query batch %d sets with 1/5/10/25/100 "
+                                            "seed items each (uniformly; before de-duplication), k=100, known items masked, "
+                                            "item-sharded x%d" % (V, Bq, world)}
                 sweep["B%d" % Bq] = pr
             extra["mpd_predict"] = sweep["B1000"]
             extra["mpd_predict_sweep"] = {k: {"value": v["value"], "e2e": v["e2e"]["value"], "ms_per_batch": v["ms_per_batch"],
@@ -737,7 +739,7 @@ def run_ours(args):
                 rep = eng.make_replica(max_batch=1024)
                 ss = {}
                 for Bq in (1000, 4000, 16000, 64000):
-                    Xq = synth_sets(Bq, V, 25, 1, 100, seed=4321)
+                    Xq = synth_sets(Bq, V, 25, 1, 100, seed=4321, len_choices=MPD_QUERY_LENS)
                     per = (Bq + world - 1) // world
                     Xl = Xq[rank * per:min(Bq, (rank + 1) * per)]
                     pr = predict_leg(ctx, rep, Xl, 100, 5 if Bq <= 4000 else 2, rows_total=Bq)

@@ -133,3 +133,31 @@ def test_batch_gather_matches_scipy_row_indexing():
             assert eng.indptr[: B + 1].cpu().numpy().tolist() == sub.indptr.tolist()
             assert eng.indices[:nnz].cpu().numpy().tolist() == sub.indices.tolist()
             np.testing.assert_array_equal(eng.cond[:B].cpu().numpy(), cs[start:start + B])
+
+
+def test_full_ranking_k_none_matches_reference_argtopk():
+    """argtopk(remove_non_missing(predict(X), X), k=None) (evaluation.py:48-52): every item of every row in descending
+    order; also a k beyond the selection kernels' envelope.  Compared with the oracle's chain outside logit near-ties;
+    known items come last."""
+    from aaerec_b200.synth import synth_sets
+    V, B = 6000, 50
+    O, oracle, model, X = _steps_vs_oracle(V=V, B=B, steps=1, mean_len=9)
+    Xq = synth_sets(37, V, 12, 1, 60, seed=5)
+    dense = Xq.toarray()
+    logits = oracle.logits(dense)
+    full = model.predict_topk(Xq, None)
+    assert full.shape == (37, V) and full.dtype == np.int64
+    assert np.array_equal(np.sort(full, axis=1), np.tile(np.arange(V), (37, 1)))       # a permutation per row
+    rows = np.arange(37)[:, None]
+    n_known = dense.sum(1).astype(int)
+    for r in range(37):
+        assert set(full[r, V - n_known[r]:]) == set(np.nonzero(dense[r])[0])           # known items at the bottom
+        head = logits[r, full[r, :V - n_known[r]]]
+        assert np.all(head[:-1] >= head[1:] - 2e-6 * np.abs(head[1:]) - 1e-7)           # descending by the oracle's logits
+    k = 5000                                                                            # > MAX_TOPK: same path, k columns
+    top = model.predict_topk(Xq, k)
+    assert np.array_equal(top, full[:, :k])
+    ref = O.rank_topk(oracle.predict(dense), dense, 100)
+    mism = full[:, :100] != ref
+    assert mism.mean() < 0.02
+    assert np.all(np.abs(logits[rows, full[:, :100]][mism] - logits[rows, ref][mism]) <= 2e-6 * np.abs(logits[rows, ref][mism]) + 1e-7)
