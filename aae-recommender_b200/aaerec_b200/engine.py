@@ -720,10 +720,11 @@ class AAEEngine(object):
         self._launches_per_step = N.launch_count() - n0
 
     def _enqueue_step_impl(self, B, injected):
-        """One partial_fit as 11 launches, 9 of them on the dependent chain:
-        [ae_fwd+gather] -> K3 -> ae_bwd -> w1_rows_update || ae_wgrad -> [disc_phase+gather] -> disc_wgrad ->
-        [gen_phase+gather] -> w1_rows_update || gen_wgrad -> step_finish, with batch_prepare -> W1 sweep on a side
-        branch under the decoder kernel.  Item-sharded runs gather separately (the partial sums are all-reduced)."""
+        """One partial_fit as 15 launches (single GPU), 11 of them on the dependent chain:
+        w1_catchup -> [ae_fwd+gather] -> K3 -> ae_bwd -> w1_rows_update || ae_wgrad -> [disc_phase+gather] -> disc_wgrad
+        -> [gen_phase+gather] -> w1_rows_update || gen_wgrad -> step_finish, with batch_prepare on a side branch and the
+        W1 group sweep (+ its `last` stamp) on a side branch under the step's latency-bound tail.  Item-sharded runs
+        gather in a kernel fused with the exchange of the partial sums (aae_peer_bag_allreduce)."""
         ctx = self._phase_ctx(B, injected)
         self._enqueue_ae(ctx)
         if self.adversarial:
