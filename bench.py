@@ -177,6 +177,40 @@ def reference_fit_timed(workload, K, W, use_cuda, budget_s):
     return steps, stamps[-1] - stamps[W], "reference"
 
 
+def reference_predict_timed(workload, n_query, use_cuda, k=100):
+    """The unmodified reference's ranking chain on ``n_query`` query sets of the workload: model.predict (aae.py:840-870,
+    dense [n,V] probabilities) -> remove_non_missing (evaluation.py:183-199, as the harness calls it, evaluation.py:375)
+    -> argtopk(., k) (evaluation.py:20-58).  Returns seconds (None without oracle/_ref)."""
+    import torch
+    from oracle import reference_loader as RL
+    from aaerec_b200.synth import synth_sets
+    if not RL.reference_available():
+        return None
+    V, mean_len, lo, hi, seed, B, _ = WORKLOADS[workload]
+    ref = RL.load_reference()
+    if use_cuda:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    model = ref.aae.AdversarialAutoEncoder(n_hidden=H, n_code=C, n_epochs=1, batch_size=B, verbose=False)
+    torch.manual_seed(42)
+    np.random.seed(42)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        model.fit(synth_sets(B, V, mean_len, lo, hi, seed))      # one step: builds the modules (and warms torch up)
+    if workload == "mpd":
+        Xq = synth_sets(n_query, V, 25, 1, 100, seed=4321, len_choices=MPD_QUERY_LENS)
+    else:
+        Xq = synth_sets(n_query, V, mean_len, lo, hi, seed=1234)
+    ev = ref.evaluation
+    t0 = time.perf_counter()
+    pred = np.asarray(model.predict(Xq))
+    pred = ev.remove_non_missing(pred, Xq, copy=True)
+    top = ev.argtopk(pred, k)
+    dt = time.perf_counter() - t0
+    assert top[1].shape == (n_query, k)
+    return dt
+
+
 def cpu_port_run(workload, steps, warmup, threads=None):
     """Fallback when oracle/_ref is absent: the reference's algorithm (dense, as aae.py does it) through the oracle
     port, all host threads."""
@@ -213,6 +247,17 @@ def run_reference(args, use_cuda=False):
     torch.set_num_threads(threads)                       # torchrun exports OMP_NUM_THREADS=1: undo its effect
     V, _, _, _, _, B, _ = WORKLOADS[args.workload]
     K, W = args.steps, max(args.warmup, 3)
+    if args.impl == "reference-predict":
+        # internal leg: the reference's predict + remove_non_missing + argtopk on the host cores
+        nq = args.predict_batch
+        sec = reference_predict_timed(args.workload, nq, use_cuda)
+        line = {"impl": "reference-predict", "unavailable": "oracle/_ref absent"} if sec is None else {
+            "impl": "reference-predict", "metric": "top-100 predict sets/sec", "value": nq / sec, "unit": "sets/s",
+            "cores": threads, "kind": "reference",
+            "sample": "%d query sets through the unmodified reference's model.predict + remove_non_missing + argtopk(k=100) "
+                      "(host CPU, CUDA hidden, torch %d threads; dense [n,V] float32 matrix), %.1f s" % (nq, threads, sec)}
+        print(json.dumps(line), flush=True)
+        return
     res = reference_fit_timed(args.workload, K, W, use_cuda, args.budget)
     if res is None:
         res = cpu_port_run(args.workload, min(K, 20), min(W, 3))
@@ -807,6 +852,14 @@ def run_ours(args):
         g = _sub_bench(["--impl", "reference-gpu", "--workload", head, "--steps", "20", "--warmup", "5", "--budget", "20"], 600)
         gpu_ref = {"value": g["value"], "unit": "sets/s", "ms_per_step": g["ms_per_step"],
                    "what": g["cpu_baseline"]["sample"]} if "value" in g else g
+        if not args.no_extra:
+            # the reference's ranking chain on the host cores, bounded samples (V=2M: 200 sets = two dense 800 MB batches)
+            if "mpd_predict" in extra:
+                extra["mpd_predict"]["cpu_baseline"] = _sub_bench(
+                    ["--impl", "reference-predict", "--workload", "mpd", "--predict-batch", "200"], 600)
+            if "pubmed" in extra and "predict" in extra["pubmed"]:
+                extra["pubmed"]["predict"]["cpu_baseline"] = _sub_bench(
+                    ["--impl", "reference-predict", "--workload", "pubmed", "--predict-batch", "1000"], 600)
     line = {
         "metric": "AAE train item-sets/sec", "value": main["value"], "unit": "sets/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
@@ -883,7 +936,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "reference-predict"])
     ap.add_argument("--workload", default="mpd", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default="auto", help="decoder-output kernel: auto|simt|tc|tf32")
     ap.add_argument("--no-graph", action="store_true")
@@ -895,7 +948,7 @@ def main():
     ap.add_argument("--predict-batch", type=int, default=1000)
     ap.add_argument("--budget", type=float, default=120.0, help="reference arm: seconds of timed work before it stops")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-predict"):
         run_reference(args, use_cuda=False)
     elif args.impl == "reference-gpu":
         run_reference(args, use_cuda=True)
