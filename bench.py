@@ -458,8 +458,15 @@ def e2e_leg(ctx, eng, batches, B, K, W, cond=None):
     return t0.elapsed_time(t1) * 1e-3, h2d // max(K, 1)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the decoder-output training kernel on a whole (unsharded)
+# vocabulary at batch 100, from the `ncu --set full` captures summarised in profiles/r02_k3_dec_out_train_tc2_final.txt
+K3_NCU_TRAFFIC = {2000000: 2.698415e9 + 2.381553e9, 200000: 258.995968e6 + 191.858432e6}
+
+
 def k3_roofline(ctx, eng, B, V, traffic=None):
     """The decoder-output kernel (K3) and the dense W1 sweep timed alone on their stream, CUDA events."""
+    if traffic is None and eng.world == 1 and B == 100:
+        traffic = K3_NCU_TRAFFIC.get(V)
     import torch
     from aaerec_b200._native import call, ptr
     Vl = eng.Vloc

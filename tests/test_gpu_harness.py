@@ -104,8 +104,9 @@ def test_reference_evaluation_harness_runs_both_recommenders(tmp_path, monkeypat
 
 
 def test_aaerec_overlay_package_resolves(monkeypatch):
-    """sys.path = [aae-recommender_b200, <reference>]: aaerec.aae.AAERecommender is ours, DecodingRecommender and every
-    other aaerec module are the reference's (main.py:13-22 imports keep working)."""
+    """sys.path = [aae-recommender_b200, <reference>]: the recommender classes of aaerec.aae / aaerec.dae / aaerec.vae are
+    ours, the rest of those modules' namespaces and every other aaerec module are the reference's (main.py:13-22 imports
+    keep working)."""
     ref = _reference()
     from oracle import reference_loader as RL
     saved = {k: v for k, v in sys.modules.items() if k == "aaerec" or k.startswith("aaerec.")}
@@ -122,7 +123,17 @@ def test_aaerec_overlay_package_resolves(monkeypatch):
         import aaerec_b200.aae as B
         assert aaerec.REFERENCE_DIR is not None
         assert A.AAERecommender is B.AAERecommender and A.AdversarialAutoEncoder is B.AdversarialAutoEncoder
-        assert A.reference_module is not None and A.DecodingRecommender is A.reference_module.DecodingRecommender
+        # the recommenders of main.py:98-124 are the B200 classes, everything else of the module is the reference's
+        import aaerec.dae as Dm
+        import aaerec.vae as Vm
+        import aaerec_b200.decoding as BD
+        import aaerec_b200.dae as BDae
+        import aaerec_b200.vae as BVae
+        assert A.DecodingRecommender is BD.DecodingRecommender
+        assert Dm.DAERecommender is BDae.DAERecommender and Vm.VAERecommender is BVae.VAERecommender
+        assert A.reference_module is not None and A.Encoder is A.reference_module.Encoder
+        assert Dm.reference_module is not None and Dm.zeros_noise is Dm.reference_module.zeros_noise
+        assert Vm.reference_module is not None
         assert ConditionList.__module__ == "aaerec.condition" and "aaerec_b200" not in ConditionList.__module__
     finally:
         for k in [k for k in sys.modules if k == "aaerec" or k.startswith("aaerec.")]:
