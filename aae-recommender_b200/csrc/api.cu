@@ -1,7 +1,6 @@
 // C-ABI glue: error reporting, device check and the dispatchers of the decoder output layer.
 #include <stdarg.h>
 #include <string.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace aae {
@@ -22,14 +21,6 @@ int check_launch(const char* what) {
     return AAE_E_CUDA;
   }
   return AAE_OK;
-}
-
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("AAE_B200_PDL");
-    return e && *e && *e != '0';
-  }();
-  return on;
 }
 
 int sm_count() {

@@ -213,8 +213,6 @@ __global__ void __launch_bounds__(256) w1_rows_update_kernel(const int32_t* __re
                                                              float* __restrict__ m, float* __restrict__ v, int H,
                                                              const aae_step_state* __restrict__ st, int which,
                                                              int32_t* last) {
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   const AdamK k = adam_load(st, which);
   const int n = min(*n_uniq, cap);
   const int lane = threadIdx.x & 31;
@@ -324,8 +322,6 @@ __global__ void __launch_bounds__(256) w1_rows_update_wide_kernel(const int32_t*
                                                                   float* __restrict__ m, float* __restrict__ v, int H,
                                                                   const aae_step_state* __restrict__ st, int which,
                                                              int32_t* last) {
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   const AdamK k = adam_load(st, which);
   const int n = min(*n_uniq, cap);
   const int lane = threadIdx.x & 31;
@@ -354,8 +350,6 @@ __global__ void __launch_bounds__(256) step_finish_kernel(int32_t* slot_of, cons
                                                           const int32_t* __restrict__ n_uniq, int cap, double* sums,
                                                           int n_sums, double n_total, int B, float* out,
                                                           aae_step_state* st, float* ktab) {
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   trace_mark(TR_FINISH, 0);
   int n = min(*n_uniq, cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) slot_of[uniq[s]] = -1;
@@ -479,21 +473,21 @@ int aae_w1_rows_update(const int32_t* uniq, const int32_t* n_uniq, int cap, cons
   AAE_REQUIRE(uniq && n_uniq && csc_off && csc_row && indptr && dh1 && W && m && v && st, "null pointer");
   int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)cap * 32, 256)));
   if ((H & 3) == 0 && H <= 128)
-    launch_chain(w1_rows_update_kernel<true>, dim3(blocks), dim3(256), 0, as_stream(stream), uniq, n_uniq, cap, csc_off,
-                 csc_row, indptr, normalize, dh1, W, m, v, H, st, which, last);
+    w1_rows_update_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                      normalize, dh1, W, m, v, H, st, which, last);
   else if (H <= 128)
-    launch_chain(w1_rows_update_kernel<false>, dim3(blocks), dim3(256), 0, as_stream(stream), uniq, n_uniq, cap, csc_off,
-                 csc_row, indptr, normalize, dh1, W, m, v, H, st, which, last);
+    w1_rows_update_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                       normalize, dh1, W, m, v, H, st, which, last);
   else
-    launch_chain(w1_rows_update_wide_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), uniq, n_uniq, cap, csc_off,
-                 csc_row, indptr, normalize, dh1, W, m, v, H, st, which, last);
+    w1_rows_update_wide_kernel<<<blocks, 256, 0, as_stream(stream)>>>(uniq, n_uniq, cap, csc_off, csc_row, indptr,
+                                                                     normalize, dh1, W, m, v, H, st, which, last);
   return check_launch("w1_rows_update");
 }
 int aae_step_finish(int32_t* slot_of, const int32_t* uniq, const int32_t* n_uniq, int cap, double* sums, int n_sums,
                     double n_total, int B, float* losses, aae_step_state* st, float* ktab, void* stream) {
   AAE_REQUIRE(slot_of && uniq && n_uniq && sums && losses && st && n_sums >= 3, "null pointer");
-  launch_chain(step_finish_kernel, dim3(std::min(4 * sm_count(), std::max(1, cdiv(cap, 256)))), dim3(256), 0,
-               as_stream(stream), slot_of, uniq, n_uniq, cap, sums, n_sums, n_total, B, losses, st, ktab);
+  step_finish_kernel<<<std::min(4 * sm_count(), std::max(1, cdiv(cap, 256))), 256, 0, as_stream(stream)>>>(
+      slot_of, uniq, n_uniq, cap, sums, n_sums, n_total, B, losses, st, ktab);
   return check_launch("step_finish");
 }
 int aae_w1_sweep_untouched(const int32_t* slot_of, int r_begin, int r_end, int H, float* W, float* m1, float* v1,

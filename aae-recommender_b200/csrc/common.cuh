@@ -23,35 +23,6 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int sm_count();
 
 // ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch for the kernels of the training step's dependent chain (11 launches, most of them
-// 5-25 us long): every chain kernel lets its successor launch at once (griddepcontrol.launch_dependents at its top: the
-// successor's CTAs become resident and run their input-independent prologue while this kernel works) and waits for its
-// predecessor's completion -- and memory flush -- before it touches global memory (griddepcontrol.wait).  Each kernel
-// waits for its immediate predecessor, which waited for its own: completion is transitive along the chain.
-// launch_chain() adds the launch attribute when pdl_enabled() (AAE_B200_PDL, default in api.cu); without the
-// attribute both instructions are no-ops.
-// ---------------------------------------------------------------------------------------------
-bool pdl_enabled();
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-template <typename... KArgs, typename... Args>
-static inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  if (pdl_enabled()) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-  }
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface in check_launch (cudaGetLastError)
-}
-
-// ---------------------------------------------------------------------------------------------
 // Adam, one element.  torch/optim/adam.py::_single_tensor_adam:
 //   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); denom = sqrt(v)/sqrt(1-b2^t) + eps;
 //   p.addcdiv_(m, denom, -lr/(1-b1^t))

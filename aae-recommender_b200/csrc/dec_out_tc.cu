@@ -895,8 +895,6 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
   const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;     // tiles blockIdx.x, +G, ... (grid <= n_tiles)
   const uint32_t T2_HTH = T2_DH + (uint32_t)g.Np, T2_HTL = T2_HTH + (uint32_t)BK;
 
-  pdl_launch_dependents();   // chain kernel (common.cuh): the successor may launch (it cannot become resident before
-                             // this CTA exits: the kernel owns the SM's shared memory)
   trace_mark(TR_K3, 0);
   if (warp == 0) K3X_MARK(39, 0);
   if (warp == 2 * NWE) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -910,7 +908,6 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
     mbar_init(&bar_dwfree[1], NWE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  pdl_wait();                // TMEM allocation and barrier setup overlapped the predecessor's tail; from here on global memory
   // The loads of the prologue are issued in batches (all loads of a batch before their first use): issued one by one
   // they cost a global-memory round trip each, 12 us of every launch before the first tile.
   constexpr int HB_BATCH = 5;
@@ -2207,8 +2204,8 @@ static int launch_tc2(const float* h2, int B, int H, float* Wd3, float* bd3, flo
     set_error("dec_out_train(tc2): smem %zu: %s", smem, cudaGetErrorString(e));
     return AAE_E_CUDA;
   }
-  launch_chain(kern, dim3(grid), dim3(tc::Tc2Cfg<TC2_CW>::NTHR), smem, s, h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc,
-               indptr, indices, (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem, gW, gB);
+  kern<<<grid, tc::Tc2Cfg<TC2_CW>::NTHR, smem, s>>>(h2, B, H, Wd3, bd3, mW, vW, mb, vb, v_begin, Vloc, indptr, indices,
+                                                   (float)(1.0 / n_total), st, dh2, loss_sum, (int)smem, gW, gB);
   return check_launch("dec_out_train(tc2)");
 }
 

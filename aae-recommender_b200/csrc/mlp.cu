@@ -23,8 +23,6 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_fwd_kernel(aae_dims d, aae_bag
                                                              float* a1, float* a2, float* zc, float* dd1, float* h2,
                                                              float* dh2_zero, int train) {
   extern __shared__ __align__(16) float sm[];
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   __shared__ LayerW layers[4];
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   const int ld = max(H, Cp);
@@ -82,8 +80,6 @@ __global__ void __launch_bounds__(MLP_THREADS) ae_bwd_kernel(aae_dims d, const f
                                                              const float* __restrict__ h2, float* g_d2, float* g_d1,
                                                              float* g_z, float* g_e2, float* g_h1) {
   extern __shared__ __align__(16) float sm[];
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   __shared__ LayerW layers[4];
   const int H = d.H, C = d.C, Cp = d.C + d.D, B = d.B;
   const int ld = max(H, Cp);
@@ -168,8 +164,6 @@ __global__ void __launch_bounds__(MLP_THREADS) disc_phase_kernel(aae_dims d, aae
                                                                  const aae_step_state* st, float* acts, float* grads,
                                                                  double* loss_sum) {
   extern __shared__ __align__(16) float sm[];
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   __shared__ LayerW layers[10];
   const int H = d.H, C = d.C, B = d.B;
   const int ld = max(H, C);
@@ -280,8 +274,6 @@ __global__ void __launch_bounds__(MLP_THREADS) gen_phase_kernel(aae_dims d, aae_
                                                                 float* g_z, float* g_e2, float* g_h1,
                                                                 double* loss_sum) {
   extern __shared__ __align__(16) float sm[];
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   __shared__ LayerW layers[9];
   const int H = d.H, C = d.C, B = d.B;
   const int ld = max(H, C);
@@ -350,7 +342,7 @@ int aae_ae_fwd_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* con
   AAE_REQUIRE(d.D == 0 || cond, "condition rows missing");
   AAE_REQUIRE(d.B > 0 && d.H > 0 && d.C > 0 && d.H <= 2048 && d.C + d.D <= 4096, "size outside envelope");
   int ld = std::max(d.H, d.C + d.D);
-  LAUNCH_R_CHAIN(ae_fwd_kernel, d.B, 2 * ld, stream, d, bag, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2,
+  LAUNCH_R(ae_fwd_kernel, d.B, 2 * ld, stream, d, bag, h1pre, cond, enc, dec, e1, e2, d1, d2, st, a1, a2, zc, dd1, h2,
            dh2_zero, 1);
   return check_launch("ae_fwd");
 }
@@ -373,7 +365,7 @@ int aae_ae_bwd(aae_dims d, const float* dh2, const float* enc, const float* dec,
                const float* h2, float* g_d2, float* g_d1, float* g_z, float* g_e2, float* g_h1, void* stream) {
   AAE_REQUIRE(dh2 && enc && dec && st && a1 && a2 && dd1 && h2 && g_d2 && g_d1 && g_z && g_e2 && g_h1, "null pointer");
   int ld = std::max(d.H, d.C + d.D);
-  LAUNCH_R_CHAIN(ae_bwd_kernel, d.B, 3 * ld, stream, d, dh2, enc, dec, e1, e2, d1, d2, st, a1, a2, dd1, h2, g_d2, g_d1, g_z,
+  LAUNCH_R(ae_bwd_kernel, d.B, 3 * ld, stream, d, dh2, enc, dec, e1, e2, d1, d2, st, a1, a2, dd1, h2, g_d2, g_d1, g_z,
            g_e2, g_h1);
   return check_launch("ae_bwd");
 }
@@ -389,12 +381,12 @@ int aae_disc_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float*
     size_t smem_ = sizeof(float) * ((size_t)(5 * ld + 2) * R_ + 2 * STAGE_FLOATS + SCRATCH_FLOATS(d)) + 64;
     if (R_ == 1) {
       cudaFuncSetAttribute(disc_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
-      launch_chain(disc_phase_kernel<1>, dim3(cdiv(d.B, 1), 2), dim3(MLP_THREADS), smem_, as_stream(stream),
-                   d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+      disc_phase_kernel<1><<<dim3(cdiv(d.B, 1), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
+          d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
     } else {
       cudaFuncSetAttribute(disc_phase_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
-      launch_chain(disc_phase_kernel<4>, dim3(cdiv(d.B, 4), 2), dim3(MLP_THREADS), smem_, as_stream(stream),
-                   d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
+      disc_phase_kernel<4><<<dim3(cdiv(d.B, 4), 2), MLP_THREADS, smem_, as_stream(stream)>>>(
+          d, bag, h1pre, z_real, prior_scale, enc, disc, r1, r2, f1, f2, st, acts, grads, loss_sum);
     }
   }
   return check_launch("disc_phase");
@@ -406,7 +398,7 @@ int aae_gen_phase_bag(aae_dims d, aae_bag bag, const float* h1pre, const float* 
   AAE_REQUIRE(enc && disc && st && a1 && a2 && g_z && g_e2 && g_h1 && loss_sum, "null pointer");
   AAE_REQUIRE(check_bag(bag, h1pre), "neither a complete bag nor h1pre given");
   int ld = std::max(d.H, d.C);
-  LAUNCH_R_CHAIN(gen_phase_kernel, d.B, 7 * ld + 2, stream, d, bag, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2,
+  LAUNCH_R(gen_phase_kernel, d.B, 7 * ld + 2, stream, d, bag, h1pre, enc, disc, e1, e2, q1, q2, st, a1, a2, g_z, g_e2,
            g_h1, loss_sum);
   return check_launch("gen_phase");
 }
@@ -434,7 +426,7 @@ int aae_ae_wgrad(aae_dims d, const float* a1, const float* a2, const float* zc, 
   add_job(js, g_d1, H, nullptr, 0, B, H, 1, g_dec, dop, off); off += H;
   add_job(js, g_d2, H, dd1, H, B, H, H, g_dec, dop, off); off += (size_t)H * H;
   add_job(js, g_d2, H, nullptr, 0, B, H, 1, g_dec, dop, off);
-  return launch_jobs(js, as_stream(stream), true);
+  return launch_jobs(js, as_stream(stream));
 }
 
 int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_disc, aae_adam_block disc_opt,
@@ -454,7 +446,7 @@ int aae_disc_wgrad(aae_dims d, const float* acts, const float* grads, float* g_d
   add_job(js, grads + H, GW, nullptr, 0, 2 * B, H, 1, g_disc, qo, off); off += H;
   add_job(js, grads + 2 * H, GW, acts + C + H, AW, 2 * B, 1, H, g_disc, qo, off); off += H;
   add_job(js, grads + 2 * H, GW, nullptr, 0, 2 * B, 1, 1, g_disc, qo, off);
-  return launch_jobs(js, as_stream(stream), true);
+  return launch_jobs(js, as_stream(stream));
 }
 
 int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z, const float* g_e2, const float* g_h1,
@@ -471,7 +463,7 @@ int aae_gen_wgrad(aae_dims d, const float* a1, const float* a2, const float* g_z
   add_job(js, g_e2, H, nullptr, 0, B, H, 1, g_enc, eo, off); off += H;
   add_job(js, g_z, C, a2, H, B, C, H, g_enc, eo, off); off += (size_t)C * H;
   add_job(js, g_z, C, nullptr, 0, B, C, 1, g_enc, eo, off);
-  return launch_jobs(js, as_stream(stream), true);
+  return launch_jobs(js, as_stream(stream));
 }
 
 }  // extern "C"

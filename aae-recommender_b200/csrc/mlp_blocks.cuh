@@ -370,8 +370,6 @@ struct WJobs {
 constexpr int WG_OUT = 64;    // outputs per CTA
 constexpr int WG_PARTS = 4;   // threads per output (split of the batch rows)
 static __global__ void __launch_bounds__(WG_OUT * WG_PARTS) small_wgrad_kernel(WJobs jobs) {
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   __shared__ float part_s[WG_PARTS][WG_OUT];
   const int el = threadIdx.x % WG_OUT, part = threadIdx.x / WG_OUT;
   const int idx = blockIdx.x * WG_OUT + el;
@@ -438,11 +436,8 @@ static void add_job(WJobs& js, const float* dY, int ldy, const float* X, int ldx
   j.begin = js.total;
   js.total += O * I;
 }
-static int launch_jobs(const WJobs& js, cudaStream_t s, bool chain = false) {
-  if (chain)
-    launch_chain(small_wgrad_kernel, dim3(cdiv(js.total, WG_OUT)), dim3(WG_OUT * WG_PARTS), 0, s, js);
-  else
-    small_wgrad_kernel<<<cdiv(js.total, WG_OUT), WG_OUT * WG_PARTS, 0, s>>>(js);
+static int launch_jobs(const WJobs& js, cudaStream_t s) {
+  small_wgrad_kernel<<<cdiv(js.total, WG_OUT), WG_OUT * WG_PARTS, 0, s>>>(js);
   return check_launch("small_wgrad");
 }
 
@@ -450,20 +445,6 @@ static inline int rows_per_cta(int B) { return B > 2048 ? 4 : 1; }
 #define SCRATCH_FLOATS(d) ((MLP_THREADS / 32) * (d).H + 8)
 
 }  // namespace aae
-
-// the same for a kernel of the training step's dependent chain (programmatic dependent launch, common.cuh)
-#define LAUNCH_R_CHAIN(kernel, B, smem_floats_per_row, stream, ...)                                    \
-  do {                                                                                                 \
-    int R_ = rows_per_cta(B);                                                                          \
-    size_t smem_ = sizeof(float) * ((size_t)(smem_floats_per_row) * R_ + 2 * STAGE_FLOATS + SCRATCH_FLOATS(d)) + 64; \
-    if (R_ == 1) {                                                                                     \
-      cudaFuncSetAttribute(kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);        \
-      launch_chain(kernel<1>, dim3(cdiv(B, 1)), dim3(MLP_THREADS), smem_, as_stream(stream), __VA_ARGS__); \
-    } else {                                                                                           \
-      cudaFuncSetAttribute(kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);        \
-      launch_chain(kernel<4>, dim3(cdiv(B, 4)), dim3(MLP_THREADS), smem_, as_stream(stream), __VA_ARGS__); \
-    }                                                                                                  \
-  } while (0)
 
 #define LAUNCH_R(kernel, B, smem_floats_per_row, stream, ...)                                          \
   do {                                                                                                 \

@@ -114,8 +114,6 @@ __global__ void __launch_bounds__(256) w1_catchup_kernel(const int32_t* __restri
                                                          float* __restrict__ m2, float* __restrict__ v2, int32_t* last,
                                                          int H, const aae_step_state* __restrict__ st,
                                                          const float* __restrict__ ktab) {
-  pdl_launch_dependents();   // chain kernel: the successor may launch; nothing below touches global memory before
-  pdl_wait();                // the predecessor has completed (common.cuh)
   trace_mark(TR_CATCHUP, 0);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -275,8 +273,8 @@ int aae_w1_catchup(const int32_t* indptr, const int32_t* indices, int B, int v_b
   AAE_REQUIRE(indptr && indices && claim && W && m1 && v1 && m2 && v2 && last && st && ktab, "null pointer");
   AAE_REQUIRE(B > 0 && H > 0, "bad size");
   int blocks = std::min(8 * sm_count(), std::max(1, cdiv((int64_t)B * 16 * 32, 256)));
-  launch_chain(w1_catchup_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), indptr, indices, B, v_begin, v_end, claim,
-               W, m1, v1, m2, v2, last, H, st, ktab);
+  w1_catchup_kernel<<<blocks, 256, 0, as_stream(stream)>>>(indptr, indices, B, v_begin, v_end, claim, W, m1, v1, m2, v2,
+                                                          last, H, st, ktab);
   return check_launch("w1_catchup");
 }
 
