@@ -278,8 +278,8 @@ int aae_peer_open(const unsigned char* handle, void** base_out);
 int aae_peer_close(void* base);
 int aae_peer_free(void* base);
 /* data[0..n) <- sum over ranks (in place); extra[0..n_extra) (doubles, n_extra <= 4, may be NULL) likewise.  Every rank
- * must call with the same exchange id, n and n_max, in the same order.  A wait that exceeds ~2 s sets an error flag
- * (aae_peer_error) instead of hanging. */
+ * must call with the same exchange id, n and n_max, in the same order.  A wait that exceeds ~20 s poisons the result with
+ * NaN and sets an error flag (aae_peer_error) instead of hanging or summing stale slots. */
 int aae_peer_allreduce(aae_peers peers, int exchange, float* data, int n, double* extra, int n_extra, int64_t n_max,
                        void* stream);
 int aae_peer_error(const void* base, int* err_host);

@@ -234,6 +234,29 @@ def test_reference_arm_prints_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_predict_leg_and_query_set_lengths():
+    # the predict legs' host baseline: the reference's own model.predict + remove_non_missing + argtopk (no GPU needed)
+    import json
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    from aaerec_b200.synth import synth_sets
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference-predict", "--workload",
+                          "econbiz", "--predict-batch", "150"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference-predict"
+    if "unavailable" not in d:            # oracle/_ref (or /root/reference) present
+        assert d["kind"] == "reference" and d["value"] > 0 and d["unit"] == "sets/s" and d["cores"] >= 1
+    # the MPD challenge's query lengths (create_dev_set.py:16-17): 1 / 5 / 10 / 25 / 100 seed items, before de-duplication
+    X = synth_sets(400, 50000, 25, 1, 100, seed=3, len_choices=(1, 5, 10, 25, 100))
+    lens = np.diff(X.indptr)
+    assert set(np.unique(lens)) <= set(range(1, 101)) and lens.max() > 60 and (lens == 1).sum() > 30
+    assert (X.data == 1).all() and all(np.all(np.diff(X.indices[X.indptr[r]:X.indptr[r + 1]]) > 0) for r in range(400))
+
+
 def test_peer_struct_layout():
     import ctypes
     from aaerec_b200 import _native as N
