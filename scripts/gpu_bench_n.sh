@@ -3,7 +3,7 @@
 N=${1:-4}
 mkdir -p gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
-  bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench$N exit $?"
+  bench.py --gpus $N --steps 20 --warmup 5 $BENCH_ARGS > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench$N exit $?"
 tail -c 400 gpurun_out/bench_n$N.err
 python - <<PY
 import json
