@@ -261,3 +261,38 @@ def test_peer_struct_layout():
     import ctypes
     from aaerec_b200 import _native as N
     assert ctypes.sizeof(N.AaePeers) == 8 * 8 + 8      # void* base[8]; int rank, world
+
+
+def test_w1_cold_element_bound_holds_in_float32():
+    """The arithmetic behind the cold-row shortcut of the time-blocked W1 sweep (csrc/w1_blocked.cu cold4): with
+    |m| <= 2^-110, denom >= eps = 1e-8, step <= 2^10 and |W| >= 2^-40 the zero-gradient Adam update
+    W' = fma(-step, m' / denom, W) returns W bit for bit (float32, round to nearest), so skipping it is exact; the moments
+    keep decaying through the unchanged operations.  (The kernel itself is checked bit for bit against the full replay
+    on the GPU: test_w1_sweep_cold_rows_bit_identical_to_full_replay.)"""
+    import numpy as np
+    rs = np.random.RandomState(0)
+    n = 200000
+    f32 = np.float32
+    m = (rs.uniform(-1, 1, n) * 2.0 ** -110).astype(f32)
+    m[::7] = f32(2.0 ** -110)                                     # the threshold itself
+    m[1::7] = f32(-(2.0 ** -110))
+    v = (rs.uniform(0, 1, n) ** 8).astype(f32)                    # second moments from 0 to 1
+    v[::5] = 0
+    w_mag = 2.0 ** rs.uniform(-40, 2, n)
+    w = (np.where(rs.rand(n) < 0.5, -1, 1) * w_mag).astype(f32)
+    w[::11] = f32(2.0 ** -40)                                     # the smallest admitted magnitude, a power of two
+    step = (2.0 ** rs.uniform(-20, 10, n)).astype(f32)
+    inv_bc2_sqrt = (1.0 / np.sqrt(1.0 - 0.999 ** rs.randint(1, 5000, n))).astype(f32)
+    eps = f32(1e-8)
+    m1 = (m - f32(0.1) * m).astype(f32)                          # fma(w1, -m, m) up to one rounding: magnitude only shrinks
+    assert np.all(np.abs(m1) <= np.abs(m))
+    denom = (np.sqrt(v).astype(f32) * inv_bc2_sqrt + eps).astype(f32)
+    assert np.all(denom >= eps)
+    q = (m1 / denom).astype(f32)
+    # the fma is exact in float64 here (24-bit x 24-bit product, then one addition), rounded once to float32
+    w_new = (w.astype(np.float64) - step.astype(np.float64) * q.astype(np.float64)).astype(f32)
+    assert np.array_equal(w_new.view(np.int32), w.view(np.int32))
+    # m == +0: the increment is -0 and W' == W for EVERY W, also tiny and zero weights
+    w_any = np.concatenate([w, f32([0.0, 1e-44, -1e-44, 1e-30])])
+    w_any_new = (w_any.astype(np.float64) - np.float64(1024.0) * np.float64(0.0)).astype(f32)
+    assert np.array_equal(w_any_new.view(np.int32), w_any.view(np.int32))
