@@ -884,7 +884,7 @@ def run_ours(args):
                                             "moments and cycles through %d batches, so nearly every row outside them is "
                                             "cold; `w1_all_rows_hot` is the same measurement with live moments in EVERY "
                                             "row (no cold row at all), a long training run lies between the two "
-                                            "(DESIGN.md 4: ~55 %% of the rows cold under this Zipf law, more on real "
+                                            "(DESIGN.md 4: ~65 %% of the rows cold under this Zipf law, more on real "
                                             "long-tail catalogues)" % len(batches)},
                    "pre_aging_steps": groups + 3,
                    "pre_aging_note": "the time-blocked sweep replays 1..G pending steps per row during an engine's first G "
