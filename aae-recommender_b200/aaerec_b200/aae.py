@@ -11,7 +11,8 @@ Additions that are not in the reference (defaults keep the reference's behaviour
   ``evaluate_topk(X, Y, metrics)``  the harness' ranking metrics (evaluation.py:70-164, 202-240) on the device
   ``rng='native'|'oracle'``  in-kernel Philox dropout / prior sampling, or the reference's CPU-generator
                            draws in the reference's order (bit-identical masks; used by parity tests)
-  ``impl``  decoder-output kernel: 'simt' (exact fp32 CUDA cores), 'tc' (tcgen05 3xTF32), 'tf32'
+  ``impl``  decoder-output kernel: 'auto', 'simt' (exact fp32 CUDA cores), 'tc' = 'parity' (tcgen05 3xTF32, fp32-accurate),
+            'tf32' = 'fast' (single-pass TF32: ~1e-3 relative logits, outside the parity gates)
   ``device`` / ``rank`` / ``world``  item-sharded multi-GPU
 """
 import numpy as np
