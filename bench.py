@@ -14,7 +14,10 @@ exactly K steps, max over ranks); ``e2e`` = the same through the host-buffer ent
 batch H2D + losses D2H every step inside the timed region); ``roofline`` = the dominant kernel's algorithmic bytes /
 its own CUDA-event time against MEASURED_PEAKS.json; ``cpu_baseline`` = the reference's own
 ``AdversarialAutoEncoder.fit`` (unmodified copy under oracle/_ref, CUDA hidden, all host threads) on a bounded sample;
-``gpu_baseline`` = the same unmodified reference on the B200 through stock PyTorch.
+``gpu_baseline`` = the same unmodified reference on the B200 through stock PyTorch; ``w1_all_rows_hot`` = the headline
+steps again with live Adam moments in every first-layer row (no cold row: the worst case of the time-blocked W1 sweep,
+DESIGN.md 4); the predict legs carry ``cpu_baseline`` = the reference's predict + remove_non_missing + argtopk on the
+host cores (internal ``--impl reference-predict``).
 
 ``--impl reference`` times the reference's CPU path alone (rank 0 only) and prints the same line with
 ``"impl": "reference"``.
