@@ -3,9 +3,11 @@
 Put this directory's parent (``aae-recommender_b200/``) in front of the reference on ``sys.path`` /
 ``PYTHONPATH`` and ``main.py``, ``eval/*.py`` and ``eval/mpd/make_submission.py`` run unchanged: every
 ``aaerec.<module>`` they import resolves to the reference's own file (datasets, evaluation, condition, baselines,
-svd, vae, dae, ...), except ``aaerec.aae``, whose ``AAERecommender`` / ``AdversarialAutoEncoder`` / ``AutoEncoder``
-are the B200-native ones of :mod:`aaerec_b200.aae` (the hot path named in BASELINE.json).  The reference's own
-condition objects (``aaerec.condition.ConditionList`` ...) are accepted by the B200 classes as they are.
+svd, ...), except ``aaerec.aae``, ``aaerec.dae`` and ``aaerec.vae``: those re-export the reference module's namespace
+with the recommenders of main.py:98-124 replaced by the B200-native classes (``AAERecommender`` /
+``AdversarialAutoEncoder`` / ``AutoEncoder`` / ``DecodingRecommender``, ``DAERecommender`` / ``DenoisingAutoEncoder``,
+``VAERecommender`` / ``VAE``).  The reference's own condition objects (``aaerec.condition.ConditionList`` ...) are
+accepted by the B200 classes as they are.
 
 Where the reference lives is taken from ``AAEREC_REFERENCE`` (the directory that contains ``aaerec/``), else from
 the first other ``aaerec`` package on ``sys.path``.  Without a reference package only ``aaerec.aae``,
@@ -34,7 +36,7 @@ def _reference_package_dir():
 
 REFERENCE_DIR = _reference_package_dir()
 if REFERENCE_DIR is not None:
-    # overlay first, reference second: aaerec.aae is ours, every other submodule is the reference's file
+    # overlay first, reference second: aaerec.aae / .dae / .vae are ours, every other submodule is the reference's file
     __path__ = [_HERE, REFERENCE_DIR]
 else:
     import aaerec_b200.base as _base
