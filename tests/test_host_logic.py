@@ -296,3 +296,42 @@ def test_w1_cold_element_bound_holds_in_float32():
     w_any = np.concatenate([w, f32([0.0, 1e-44, -1e-44, 1e-30])])
     w_any_new = (w_any.astype(np.float64) - np.float64(1024.0) * np.float64(0.0)).astype(f32)
     assert np.array_equal(w_any_new.view(np.int32), w_any.view(np.int32))
+
+
+def test_overlay_resolves_the_import_block_of_main_py():
+    """The zero-edit path of INTEGRATION.md A, on the CPU: with aae-recommender_b200/ in front of the reference on the
+    module path, the imports of main.py:11-20 resolve -- recommenders of aaerec.aae / .vae / .dae to the B200 classes,
+    everything else to the reference's own modules (runs in a child process: it rebinds the ``aaerec`` package)."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    from oracle import reference_loader as RL
+    if not RL.reference_available():
+        pytest.skip("no reference tree (neither /root/reference nor oracle/_ref)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+from oracle import reference_loader as RL
+RL.load_reference()                      # gensim / docutils stubs (absent in this image)
+for k in [k for k in sys.modules if k == "aaerec" or k.startswith("aaerec.")]:
+    del sys.modules[k]
+sys.path.insert(0, %r)
+from aaerec.datasets import Bags
+from aaerec.evaluation import Evaluation
+from aaerec.aae import AAERecommender, DecodingRecommender
+from aaerec.baselines import RandomBaseline, Countbased, MostPopular
+from aaerec.svd import SVDRecommender
+from aaerec.vae import VAERecommender
+from aaerec.dae import DAERecommender
+from aaerec.condition import ConditionList, PretrainedWordEmbeddingCondition, CategoricalCondition
+mods = [c.__module__ for c in (AAERecommender, DecodingRecommender, VAERecommender, DAERecommender)]
+assert mods == ["aaerec_b200.aae", "aaerec_b200.decoding", "aaerec_b200.vae", "aaerec_b200.dae"], mods
+for c in (Bags, Evaluation, Countbased, SVDRecommender, ConditionList, CategoricalCondition):
+    assert c.__module__.startswith("aaerec.") and "b200" not in c.__module__, c
+print("OVERLAY_OK")
+''' % (root, os.path.join(root, "aae-recommender_b200"))
+    env = dict(os.environ, AAEREC_REFERENCE=RL.REFERENCE_ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "OVERLAY_OK" in out.stdout, out.stderr[-2000:]
