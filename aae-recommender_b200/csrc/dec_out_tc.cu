@@ -827,11 +827,6 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 #ifndef K3_PF_AHEAD
 #define K3_PF_AHEAD 4
 #endif
-// K3_E2_BULK = 1: the E2 warps write the updated W/m/v rows back INTO the stage and the copy warp stores the tile with
-// six TMA bulk copies (shared -> global) before it refills the stage, instead of 3*CWT scalar st.global per thread.
-#ifndef K3_E2_BULK
-#define K3_E2_BULK 0
-#endif
 #ifdef K3X_TRACE
 // timing experiment only: clock64() of CTA 0 at the synchronisation points of tile iterations 8..39
 static __device__ long long k3x_tr[32 * 16];
@@ -1092,40 +1087,12 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
       for (int j = 1; j < K3_PF_AHEAD; ++j) prefetch_w(j);
     }
     __syncwarp();
-#if K3_E2_BULK
-    // full tile of an Adam launch: the stage now holds the UPDATED rows (E2 wrote them back): store, then refill
-    auto stage_store = [&](int j) {
-      const int v0 = ((int)blockIdx.x + j * G) * TN;
-      if (kAdam && Vloc - v0 >= TN) {
-        const uint32_t wbytes = (uint32_t)(TN * H) * 4u, bbytes = TN * 4u;
-        bulk_s2g(Wd3 + (size_t)v0 * H, sW, wbytes);
-        bulk_s2g(mW + (size_t)v0 * H, sM, wbytes);
-        bulk_s2g(vW + (size_t)v0 * H, sV, wbytes);
-        bulk_s2g(bd3 + v0, sB, bbytes);
-        bulk_s2g(mb + v0, sB + TN, bbytes);
-        bulk_s2g(vb + v0, sB + 2 * TN, bbytes);
-        bulk_commit();
-        bulk_wait_read0();             // the stage has been read: it may be refilled
-      }
-    };
-    for (int j = 0; j < n_my; ++j) {
-      if (lane == 0) prefetch_w(j + K3_PF_AHEAD);
-      named_bar_sync(2, NTT);          // E2(j) is done with the stage (results written back, made visible to the async proxy)
-      if (lane == 0) {
-        stage_store(j);
-        if (j + 1 < n_my) stage_copy(j + 1);
-      }
-      __syncwarp();
-    }
-    if (lane == 0) bulk_wait_all0();   // the last stores have landed before the CTA exits
-#else
     for (int j = 1; j < n_my; ++j) {
       if (lane == 0) prefetch_w(j + K3_PF_AHEAD - 1);
       named_bar_sync(2, NTT);          // E2(j-1) has read the stage
       if (lane == 0) stage_copy(j);
       __syncwarp();
     }
-#endif
   } else if (warp < NWE) {
     // ================= E1 / loader warps: logits -> dZ, the W' tile -> Wb / Wtb =================
     const int q4 = warp & 3, cpart = warp >> 2;      // TMEM lane quarter, CWT-column part of the 32-wide tile
@@ -1425,9 +1392,9 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
     float* const eW = is_bias ? bd3 : Wd3;
     float* const eM = is_bias ? mb : mW;
     float* const eV = is_bias ? vb : vW;
-    float* const sWp = is_bias ? sB + cpart * CWT + jb : sW + cpart * CWT * H + brow;
-    float* const sMp = is_bias ? sB + TN + cpart * CWT + jb : sM + cpart * CWT * H + brow;
-    float* const sVp = is_bias ? sB + 2 * TN + cpart * CWT + jb : sV + cpart * CWT * H + brow;
+    const float* const sWp = is_bias ? sB + cpart * CWT + jb : sW + cpart * CWT * H + brow;
+    const float* const sMp = is_bias ? sB + TN + cpart * CWT + jb : sM + cpart * CWT * H + brow;
+    const float* const sVp = is_bias ? sB + 2 * TN + cpart * CWT + jb : sV + cpart * CWT * H + brow;
     const int ecnt_full = is_bias ? 1 : (brow < H ? CWT : 0);
     uint32_t phase_e = 0, ph_dw0 = 0, ph_dw1 = 0;
     const uint32_t rt_zero = (uint32_t)smem_total >> 31;
@@ -1485,7 +1452,7 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
           }
         }
       }
-      if (!K3_E2_BULK && jt + 1 < n_my) {
+      if (jt + 1 < n_my) {
         // The stage may be refilled (tile jt + 1) -- but only once the loads above have RETURNED: bar.arrive does not
         // order earlier shared-memory reads, and the refill (an L2 hit) can overtake loads that are still queued behind
         // the other warps' traffic.  The barrier id is made to depend on every loaded register (rt_zero is 0 at run time).
@@ -1543,24 +1510,12 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
         for (int j = 0; j < CWT; ++j) { dn[j] = gw[j]; pw[j] += dn[j]; }
 #endif
 #ifndef K3X_NO_E2ST
-        if (K3_E2_BULK && nv == TN) {
 #pragma unroll
-          for (int j = 0; j < CWT; ++j) {
-            if (j < ecnt_full) {
-              sWp[j * H] = pw[j];
-              sMp[j * H] = pm[j];
-              sVp[j * H] = pv[j];
-            }
-          }
-          fence_async_smem();            // generic-proxy writes -> visible to the copy warp's bulk stores
-        } else {
-#pragma unroll
-          for (int j = 0; j < CWT; ++j) {
-            if (j < ecnt) {
-              pW[(size_t)j * H] = pw[j];
-              __stcs(pM + (size_t)j * H, pm[j]);
-              __stcs(pV + (size_t)j * H, pv[j]);
-            }
+        for (int j = 0; j < CWT; ++j) {
+          if (j < ecnt) {
+            pW[(size_t)j * H] = pw[j];
+            __stcs(pM + (size_t)j * H, pm[j]);
+            __stcs(pV + (size_t)j * H, pv[j]);
           }
         }
 #else
@@ -1571,9 +1526,6 @@ __global__ void __launch_bounds__(Tc2Cfg<CWT>::NTHR, 1) dec_out_train_tc2_kernel
         for (int j = 0; j < CWT; ++j)
           if (j < ecnt) pG[(size_t)j * H] = gw[j];
       }
-#if K3_E2_BULK
-      named_bar_arrive(2, NTT);          // this warp is done with the stage of tile jt
-#endif
       if (warp == NWE) K3X_MARK(jt, 7);
     }
   }
