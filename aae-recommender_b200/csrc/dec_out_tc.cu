@@ -812,15 +812,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
-// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 #ifndef K3_PF_MV
 #define K3_PF_MV 1
 #endif
