@@ -1782,15 +1782,8 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(int mode_in, const f
 // Replaces the dense lin3 + sigmoid of predict (aae.py:866-868) and the front half of remove_non_missing + argtopk
 // (evaluation.py:183-199, 20-58).
 // ---------------------------------------------------------------------------------------------
-#ifndef K5_LOAD_LATE
-#define K5_LOAD_LATE 0
-#endif
-// K5_CP_ASYNC=1: W' tiles staged with cp.async straight into the hi operand half (measured: 2.59 ms vs 2.18 ms for the
-// register path at V=2M/B=1000 with 3xTF32 -- the lo pass then sits between the epilogue and the stage hand-over;
-// 1.99 vs 2.07 ms with single-pass TF32).  Kept as an experiment switch.
-#ifndef K5_CP_ASYNC
-#define K5_CP_ASYNC 0
-#endif
+// (Staging the W' tiles with cp.async straight into the hi operand half was measured slower with the 3xTF32 split --
+// 2.59 vs 2.18 ms at V=2M / B=1000: the lo pass then sits between the epilogue and the stage hand-over -- and removed.)
 constexpr int PN = 128;                // items per tile
 constexpr int P_NWE = 16;              // loader / epilogue warps
 constexpr int P_NT = 32 * P_NWE + 32;  // + the MMA warp
@@ -1939,51 +1932,6 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
       }
       const int tile_step = (int)gridDim.x * a.tile_stride * PN;           // items between two tiles of this CTA
       const int v_first = (int)blockIdx.x * a.tile_stride * PN;
-#if K5_CP_ASYNC
-      // W' tile: global -> shared memory with cp.async, straight into the hi half of the stage in operand layout (the
-      // tensor core reads tf32 = the upper 19 bits of the fp32 container, i.e. exactly tf32_hi(x)); no register, no
-      // load scoreboard: the L2/HBM latency runs under the epilogue.  The lo half = x - tf32_hi(x) is then built from
-      // shared memory.  Rows beyond the shard are zero-filled (src-size 0); pad chunks stay zero from the initial fill.
-      auto issue_tile = [&](int stage, int v0) {
-        const bool rv = v0 + lrow < a.Vloc;
-        const float* wt = a.Wd3 + (size_t)(rv ? v0 : 0) * a.H;
-        const uint32_t hi = smem_u32(wst + 2 * stage * wb_bytes);
-        const uint32_t n16 = rv ? 16u : 0u, n4 = rv ? 4u : 0u;
-#pragma unroll
-        for (int j = 0; j < P_WCH; ++j) {
-          if (pc.goff[j] >= 0)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(hi + pc.soff[j]), "l"(wt + pc.goff[j]),
-                         "r"(n16)
-                         : "memory");
-          else if (pc.goff[j] == -1)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(hi + pc.soff[j]),
-                         "l"(a.bd3 + (rv ? v0 + lrow : 0)), "r"(n4)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      auto finish_tile = [&](int stage) {
-        if (with_lo) {
-          unsigned char* hi = wst + 2 * stage * wb_bytes;
-          unsigned char* lo = hi + wb_bytes;
-#pragma unroll
-          for (int j = 0; j < P_WCH; ++j) {
-            if (pc.goff[j] < -1) continue;
-            const float4 x = *reinterpret_cast<const float4*>(hi + pc.soff[j]);
-            *reinterpret_cast<float4*>(lo + pc.soff[j]) =
-                make_float4(x.x - tf32_hi(x.x), x.y - tf32_hi(x.y), x.z - tf32_hi(x.z), x.w - tf32_hi(x.w));
-          }
-        }
-      };
-      for (int p = 0; p < 2 && p < n_my; ++p) issue_tile(p, v_first + p * tile_step);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      for (int p = 0; p < 2 && p < n_my; ++p) {
-        finish_tile(p);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ready[p]);
-      }
-#else
       auto load_tile = [&](float4* wr, int v0) {
         p_load_w(wr, pc, a.Wd3 + (size_t)v0 * a.H, a.bd3 + v0 + lrow, v0 + lrow < a.Vloc);
       };
@@ -1996,33 +1944,25 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
         if (lane == 0) mbar_arrive(&bar_ready[p]);
       }
       if (n_my > 2) load_tile(wr, v_first + 2 * tile_step);
-#endif
       for (int i = 0; i < n_my; ++i) {
         const int s = i & 1;
         const int v0 = v_first + i * tile_step;
         mbar_wait(&bar_mma[s], s ? ph1 : ph0);       // logits of tile i in TMEM buffer s, stage s free again
         if (s) ph1 ^= 1; else ph0 ^= 1;
         tc_fence_after();
-#if K5_CP_ASYNC
-        if (i + 2 < n_my) issue_tile(s, v0 + 2 * tile_step);
-#endif
         uint32_t zr[P_CW];
         TmemIO<16>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW), zr);
         TmemIO<16>::ld_issue(lane_addr + (uint32_t)(s * PN + cpart * P_CW + 16), zr + 16);
         TmemIO<16>::ld_wait(zr);
         TmemIO<16>::ld_wait(zr + 16);
         tc_fence_before();
-#if !K5_CP_ASYNC
         if (i + 2 < n_my) {
           p_store_w(wr, pc, wst + 2 * s * wb_bytes, wst + (2 * s + 1) * wb_bytes, with_lo);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_ready[s]);
-#if !K5_LOAD_LATE
           if (i + 3 < n_my) load_tile(wr, v0 + 3 * tile_step);
-#endif
         }
-#endif
         // ---- epilogue of tile i
         const int c0 = cpart * P_CW;
         const int vm = a.Vloc - v0 - c0;                         // valid columns among this thread's 32
@@ -2069,19 +2009,6 @@ __global__ void __launch_bounds__(P_NT, 1) dec_out_select_kernel(SelArgs a) {
             }
           }
         }
-#if K5_CP_ASYNC
-        if (i + 2 < n_my) {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          finish_tile(s);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_ready[s]);
-        }
-#elif K5_LOAD_LATE
-        // W'(i+3): issued last, so that its L2/HBM latency runs under the wait for the MMAs of tile i+1 instead of in
-        // front of the epilogue (the compiler shares load scoreboards: an epilogue behind the loads waits for them)
-        if (i + 3 < n_my) load_tile(wr, v0 + 3 * tile_step);
-#endif
       }
       if (a.filter && rowv) a.cnt[(size_t)(b0 + brow) * nsub + sub] = my_cnt;
     }
