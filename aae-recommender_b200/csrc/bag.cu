@@ -107,10 +107,6 @@ __global__ void __launch_bounds__(256) bag_fwd_kernel(const int32_t* __restrict_
   }
 }
 
-__global__ void zero_counter_kernel(int32_t* n_uniq) { *n_uniq = 0; }
-
-
-
 
 // ---------------------------------------------------------------------------------------------
 // Fused-step bookkeeping: ONE single-CTA launch builds the touched-row slots and the transposed (item ->
