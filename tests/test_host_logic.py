@@ -255,6 +255,10 @@ def test_reference_predict_leg_and_query_set_lengths():
     lens = np.diff(X.indptr)
     assert set(np.unique(lens)) <= set(range(1, 101)) and lens.max() > 60 and (lens == 1).sum() > 30
     assert (X.data == 1).all() and all(np.all(np.diff(X.indices[X.indptr[r]:X.indptr[r + 1]]) > 0) for r in range(400))
+    # the named shapes of SURVEY 8(d)
+    from aaerec_b200.synth import synth_named, SHAPES
+    E = synth_named("econbiz", 300)
+    assert E.shape == (300, SHAPES["econbiz"][1]) and np.diff(E.indptr).min() >= 1 and np.diff(E.indptr).max() <= 30
 
 
 def test_peer_struct_layout():
