@@ -690,18 +690,19 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 
 // ---------------------------------------------------------------------------------------------
 // Pipelined training kernel (the default for the reference's shapes).  Same three GEMMs and epilogues as
-// above, but the tile loop is software-pipelined around ONE dedicated MMA-issuing warp:
+// above, as a role-split pipeline of 18 warps (CWT = 16 accumulator columns per epilogue thread):
 //
-//   warp 16 (issuer), per iteration i : wait named barrier -> G3(i), G2(i), G1(i+1) -> tcgen05.commit
-//   warps 0-15 (epilogue/loader)      : wait commit(i-1) [G1(i), G23(i-1) done]
-//                                       E1(i): Z[i&1] -> dZ (TMEM + transposed smem)
-//                                       W'(i) -> Wtb, W'(i+1) -> Wb[(i+1)&1], arrive on the named barrier
-//                                       E2(i-1): dW'^T[(i-1)&1] -> Adam -> global     (overlaps the MMAs of i)
-//                                       prefetch: W'(i+2) rows, and W/m/v of tile i in the E2 layout
+//   warps 0-7   E1 / loader : wait G1(i) -> Z[i&1] -> sigmoid / BCE -> dZ(i) (TMEM hi/lo for G2, transposed smem for G3);
+//                             W'(i+2) global -> registers, W'(i+1) -> Wb (hand-over barrier 3), W'(i) transposed -> Wtb
+//                             (hand-over barrier 1, once G2/G3(i-1) are done with dZ / Dtb / Wtb)
+//   warps 8-15  E2          : old W/m/v rows of tile j from the TMA-filled stage (hand-back barrier 2), wait G3(j) ->
+//                             dW'^T[j&1] -> Adam -> global; runs up to two tiles behind the MMA warp
+//   warp 16     MMA issuer  : G1(i+1) as soon as W'(i+1) is stored, then G3(i), G2(i); tcgen05.commit onto bar_g1 /
+//                             bar_dw[i&1] / bar_g23
+//   warp 17     copy        : cp.async.bulk refill of the E2 stage, cp.async.bulk.prefetch.L2 of W/m/v K3_PF_AHEAD tiles ahead
 //
-// Z and dW'^T are double-buffered in TMEM, Wb in shared memory, so the tensor core works on tile i's
-// backward GEMMs and tile i+1's logits while the CUDA cores finish tile i-1; the only block-wide
-// synchronisation per tile is one mbarrier wait and one non-blocking named-barrier arrive.
+// Z and dW'^T are double-buffered in TMEM, so the tensor core works on tile i's backward GEMMs and tile i+1's logits
+// while the CUDA cores finish tile i-1; no block-wide barrier inside the tile loop (mbarriers and named barriers only).
 // TMEM (512 columns): Z 2x32 | dW'^T 2x32 | dZ hi,lo 2x32 | dh2 Np | H2'^T hi,lo 2x round8(B)
 //   -> needs Np + 2*round8(B) <= 320 (n_hidden 100: batch <= 104).
 // Bias: lane k == H of dW'^T holds the bias gradients; they are handed to lanes H+1..H+8 of the same warp,
